@@ -1,0 +1,628 @@
+// tb_api.cu -- the C ABI of include/tendrils_b200.h over the sm_100a kernels.
+//
+// Mirrors, for the one hot path, the GPU-facing behaviour of the reference's
+// Tendrils (src/index.js) and Particles (src/particles.js) classes: ping-pong state
+// buffers, the logic pass, the flow splat, the spawn passes.  No CPU fallback.
+#include "tb_kernels.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace tb;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct tb_ctx {
+    tb_config cfg{};
+    int PW = 0, PH = 0, col0 = 0, col1 = 0;
+    long long n_local = 0;
+    int W = 0, H = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    float4 *buf[2] = {nullptr, nullptr};   // [0] current, [1] previous (src/particles.js:128)
+    float4 *targets = nullptr;
+    float4 *flow = nullptr;
+    float4 *image = nullptr;
+    size_t image_cap = 0;
+    int IW = 0, IH = 0;
+    float4 *layer = nullptr;
+    size_t layer_cap = 0;
+
+    // flow splat scratch
+    PairEntry *pairs = nullptr;
+    int n_pairs = 0;
+    uint32_t *tex_off = nullptr;           // G+1 counters / offsets
+    void *scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    Frag *frags = nullptr;
+    uint32_t frag_cap = 0;
+    uint32_t *h_total = nullptr;           // pinned
+    cudaEvent_t ev_total = nullptr;
+    bool collected = false;
+    float collect_time = 0.f;
+
+    int *d_flag = nullptr;                 // device scratch flag
+    int *h_flag = nullptr;                 // pinned
+    bool targets_finite = true;
+
+    cudaEvent_t ev_int[2] = {nullptr, nullptr}, ev_spl[2] = {nullptr, nullptr};
+    bool timed_int = false, timed_spl = false;
+
+    tb_state state{};
+    bool have_state = false;
+    std::string err;
+    int64_t launches = 0;
+    int64_t last_frags = 0;
+};
+
+namespace {
+
+int fail(tb_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define TB_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, TB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+#define TB_REQUIRE(ctx, cond, msg)                                                                 \
+    do {                                                                                           \
+        if (!(cond)) return fail(ctx, TB_ERR_INVALID, std::string("tendrils-b200: ") + (msg));     \
+    } while (0)
+
+inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+// NEAREST/CLAMP_TO_EDGE texel of a normalised coordinate, float32 as the sampler computes it.
+int host_texel(float u, int size) {
+    volatile float prod = u * static_cast<float>(size);
+    float f = std::floor(prod);
+    if (!(f > 0.0f)) return 0;
+    if (f > static_cast<float>(size - 1)) return size - 1;
+    return static_cast<int>(f);
+}
+
+// The D6 table: Particles.generateLUT (src/particles.js:171-190) gives vertex j of a column
+// uv.y = f32(j/(2PH-1)); stateAtFrame (src/state/state-at-frame.glsl:12-22) turns that into
+// a texel row and a previous/current choice.  Pairs whose two vertices sample the same texel
+// of the same buffer are zero-length lines and produce no fragments: dropped here.
+std::vector<PairEntry> build_pairs(int PH) {
+    std::vector<PairEntry> out;
+    const int h = std::max(2 * PH, 2);
+    const double inv = 1.0 / static_cast<double>(h - 1);
+    auto vertex = [&](int j, int &row, bool &cur) {
+        const float uvy = static_cast<float>(static_cast<double>(j) * inv);
+        volatile float near_index = uvy * static_cast<float>(PH);
+        const float fl = std::floor(near_index);
+        volatile float off = near_index - fl;
+        volatile float lookup = fl / static_cast<float>(PH);
+        row = host_texel(lookup, PH);
+        cur = off > 0.25f;
+    };
+    for (int k = 0; k < PH; ++k) {
+        int ra, rb;
+        bool ca, cb;
+        vertex(2 * k, ra, ca);
+        vertex(2 * k + 1, rb, cb);
+        if (ra == rb && ca == cb) continue;
+        PairEntry e;
+        e.k = k;
+        e.row_a = ra | (ca ? static_cast<int32_t>(0x80000000u) : 0);
+        e.row_b = rb | (cb ? static_cast<int32_t>(0x80000000u) : 0);
+        e.pad = 0;
+        out.push_back(e);
+    }
+    return out;
+}
+
+// column sampled by vertex column i: uv.x = f32(i/(PW-1)) -> floor(uv.x*PW), must be i.
+bool columns_are_identity(int PW) {
+    const int w = std::max(PW, 2);
+    const double inv = 1.0 / static_cast<double>(w - 1);
+    for (int i = 0; i < PW; ++i)
+        if (host_texel(static_cast<float>(static_cast<double>(i) * inv), PW) != i) return false;
+    return true;
+}
+
+int alloc_flow(tb_ctx *c, int w, int h) {
+    TB_REQUIRE(c, w >= 1 && h >= 1 && static_cast<long long>(w) * h < (1LL << 31), "flow grid dimensions out of bounds");
+    if (c->flow) cudaFree(c->flow);
+    if (c->tex_off) cudaFree(c->tex_off);
+    if (c->scan_tmp) cudaFree(c->scan_tmp);
+    c->flow = nullptr; c->tex_off = nullptr; c->scan_tmp = nullptr;
+    c->W = w; c->H = h;
+    const size_t G = static_cast<size_t>(w) * h;
+    TB_CUDA(c, cudaMalloc(&c->flow, G * sizeof(float4)));
+    TB_CUDA(c, cudaMalloc(&c->tex_off, (G + 1) * sizeof(uint32_t)));
+    c->scan_tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, c->scan_tmp_bytes, c->tex_off, c->tex_off, static_cast<int>(G + 1), c->stream);
+    TB_CUDA(c, cudaMalloc(&c->scan_tmp, c->scan_tmp_bytes));
+    TB_CUDA(c, cudaMemsetAsync(c->flow, 0, G * sizeof(float4), c->stream));
+    c->collected = false;
+    return TB_OK;
+}
+
+int ensure_frag_cap(tb_ctx *c, uint64_t need) {
+    if (need <= c->frag_cap) return TB_OK;
+    TB_REQUIRE(c, need < (1ull << 32), "flow splat: more than 2^32 fragments in one draw");
+    uint64_t cap = std::max<uint64_t>(need + need / 4, 1u << 16);
+    if (cap >= (1ull << 32)) cap = (1ull << 32) - 1;
+    if (c->frags) cudaFree(c->frags);
+    c->frags = nullptr;
+    c->frag_cap = 0;
+    TB_CUDA(c, cudaMalloc(&c->frags, cap * sizeof(Frag)));
+    c->frag_cap = static_cast<uint32_t>(cap);
+    return TB_OK;
+}
+
+int check_launch(tb_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, TB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    c->launches += 1;
+    return TB_OK;
+}
+
+SplatArgs splat_args(tb_ctx *c) {
+    SplatArgs A{};
+    A.cur = c->buf[0];
+    A.prev = c->buf[1];
+    A.pairs = c->pairs;
+    A.n_pairs = c->n_pairs;
+    A.PH = c->PH;
+    A.cols = c->col1 - c->col0;
+    A.col0 = c->col0;
+    A.W = c->W;
+    A.H = c->H;
+    A.vsx = c->state.viewSize[0];
+    A.vsy = c->state.viewSize[1];
+    A.speedLimit = c->state.speedLimit;
+    A.tex_off = c->tex_off;
+    A.frags = c->frags;
+    A.cap = c->frag_cap;
+    A.total = c->tex_off + static_cast<size_t>(c->W) * c->H;   // slot G holds the total
+    return A;
+}
+
+// count -> scan -> (async total to host) -> emit, re-run with a larger buffer on overflow
+int collect(tb_ctx *c, float time) {
+    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before the flow splat");
+    const size_t G = static_cast<size_t>(c->W) * c->H;
+    const long long threads = static_cast<long long>(c->col1 - c->col0) * c->n_pairs;
+    c->collect_time = time;
+    c->collected = false;
+    if (threads == 0) {
+        *c->h_total = 0;
+        TB_CUDA(c, cudaMemsetAsync(c->tex_off, 0, (G + 1) * sizeof(uint32_t), c->stream));
+        c->collected = true;
+        c->last_frags = 0;
+        return TB_OK;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        TB_CUDA(c, cudaMemsetAsync(c->tex_off, 0, (G + 1) * sizeof(uint32_t), c->stream));
+        SplatArgs A = splat_args(c);
+        k_splat_count<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
+        if (int r = check_launch(c, "k_splat_count")) return r;
+        // exclusive scan in place over G+1 entries: slot G (zero) receives the total
+        TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp, c->scan_tmp_bytes, c->tex_off, c->tex_off,
+                                                 static_cast<int>(G + 1), c->stream));
+        c->launches += 1;
+        TB_CUDA(c, cudaMemcpyAsync(c->h_total, c->tex_off + G, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cudaEventRecord(c->ev_total, c->stream));
+        k_splat_emit<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
+        if (int r = check_launch(c, "k_splat_emit")) return r;
+        TB_CUDA(c, cudaEventSynchronize(c->ev_total));
+        c->last_frags = *c->h_total;
+        if (*c->h_total <= c->frag_cap) {
+            c->collected = true;
+            return TB_OK;
+        }
+        if (int r = ensure_frag_cap(c, *c->h_total)) return r;   // emit/fold skipped themselves on device
+    }
+    return fail(c, TB_ERR_OVERFLOW, "flow splat: fragment buffer overflow after regrow");
+}
+
+int fold(tb_ctx *c) {
+    TB_REQUIRE(c, c->collected, "tb_splat_fold without a preceding tb_splat_collect");
+    const int G = c->W * c->H;
+    if (c->last_frags > 0) {
+        k_splat_fold<<<blocks_for(G, 128), 128, 0, c->stream>>>(c->flow, c->tex_off, c->frags, G, c->collect_time,
+                                                               c->tex_off + G, c->frag_cap);
+        if (int r = check_launch(c, "k_splat_fold")) return r;
+    }
+    c->collected = false;
+    return TB_OK;
+}
+
+// spawnShader target handling (src/particles.js:123-130): no buffer -> rotate and write
+// buffers[0]; explicit targets FBO -> no rotation.  `particles` is buffers[1] either way.
+float4 *spawn_out(tb_ctx *c, tb_target target) {
+    if (target == TB_TARGET_TARGETS) return c->targets;
+    std::swap(c->buf[0], c->buf[1]);
+    return c->buf[0];
+}
+
+int after_targets_write(tb_ctx *c, tb_target target) {
+    if (target != TB_TARGET_TARGETS) return TB_OK;
+    TB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+    k_check_finite<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(c->targets, c->n_local, c->d_flag);
+    if (int r = check_launch(c, "k_check_finite")) return r;
+    TB_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->targets_finite = (*c->h_flag == 0);
+    return TB_OK;
+}
+
+bool tame(float v, float lim) { return std::isfinite(v) && std::fabs(v) < lim; }
+
+}  // namespace
+
+extern "C" {
+
+int tb_abi_version(void) { return TB_ABI_VERSION; }
+
+const char *tb_last_error(const tb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tb_create(const tb_config *cfg, tb_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, TB_ERR_INVALID, "tendrils-b200: null argument");
+    *out = nullptr;
+    const int PW = cfg->particles_w, PH = cfg->particles_h;
+    if (PW < 2 || PH < 2 || static_cast<long long>(PW) * PH >= (1LL << 32))
+        return fail(nullptr, TB_ERR_INVALID, "tendrils-b200: Texture dimensions are out of bounds");
+    const int col0 = cfg->col0, col1 = cfg->col1 == 0 ? PW : cfg->col1;
+    if (col0 < 0 || col1 > PW || col0 >= col1)
+        return fail(nullptr, TB_ERR_INVALID, "tendrils-b200: invalid column range");
+    if (!columns_are_identity(PW))
+        return fail(nullptr, TB_ERR_UNSUPPORTED, "tendrils-b200: vertex LUT columns do not map 1:1 for this width");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TB_ERR_CUDA, std::string("tendrils-b200: no CUDA device (there is no CPU fallback): ") +
+                                              cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, TB_ERR_INVALID, "tendrils-b200: bad device ordinal");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, TB_ERR_CUDA, cudaGetErrorString(e));
+
+    tb_ctx *c = new tb_ctx();
+    c->cfg = *cfg;
+    c->PW = PW; c->PH = PH; c->col0 = col0; c->col1 = col1;
+    c->n_local = static_cast<long long>(col1 - col0) * PH;
+    c->device = cfg->device;
+    auto bail = [&](int code) {
+        g_create_error = c->err;
+        tb_destroy(c);
+        return code;
+    };
+#define TB_TRY(expr) do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) { c->err = std::string(#expr) + ": " + cudaGetErrorString(e2_); return bail(TB_ERR_CUDA); } } while (0)
+    TB_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
+    TB_TRY(cudaMalloc(&c->buf[0], bytes));
+    TB_TRY(cudaMalloc(&c->buf[1], bytes));
+    TB_TRY(cudaMalloc(&c->targets, bytes));
+    TB_TRY(cudaMemsetAsync(c->targets, 0, bytes, c->stream));       // FBO textures start zeroed
+    TB_TRY(cudaMemsetAsync(c->buf[0], 0, bytes, c->stream));
+    TB_TRY(cudaMemsetAsync(c->buf[1], 0, bytes, c->stream));
+    TB_TRY(cudaMalloc(&c->d_flag, sizeof(int)));
+    TB_TRY(cudaMallocHost(&c->h_flag, sizeof(int)));
+    TB_TRY(cudaMallocHost(&c->h_total, sizeof(uint32_t)));
+    TB_TRY(cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        TB_TRY(cudaEventCreate(&c->ev_int[i]));
+        TB_TRY(cudaEventCreate(&c->ev_spl[i]));
+    }
+    const std::vector<PairEntry> pairs = build_pairs(PH);
+    c->n_pairs = static_cast<int>(pairs.size());
+    if (c->n_pairs) {
+        TB_TRY(cudaMalloc(&c->pairs, pairs.size() * sizeof(PairEntry)));
+        TB_TRY(cudaMemcpyAsync(c->pairs, pairs.data(), pairs.size() * sizeof(PairEntry), cudaMemcpyHostToDevice, c->stream));
+        TB_TRY(cudaStreamSynchronize(c->stream));
+    }
+#undef TB_TRY
+    const int fw = cfg->flow_w > 0 ? cfg->flow_w : 1, fh = cfg->flow_h > 0 ? cfg->flow_h : 1;
+    if (int r = alloc_flow(c, fw, fh)) return bail(r);
+    if (int r = ensure_frag_cap(c, static_cast<uint64_t>(c->n_local) * 2)) return bail(r);
+    if (int r = tb_reset(c)) return bail(r);
+    *out = c;
+    return TB_OK;
+}
+
+int tb_destroy(tb_ctx *c) {
+    if (!c) return TB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
+    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->tex_off);
+    cudaFree(c->scan_tmp); cudaFree(c->frags); cudaFree(c->d_flag);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->h_total) cudaFreeHost(c->h_total);
+    if (c->ev_total) cudaEventDestroy(c->ev_total);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_int[i]) cudaEventDestroy(c->ev_int[i]);
+        if (c->ev_spl[i]) cudaEventDestroy(c->ev_spl[i]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return TB_OK;
+}
+
+int tb_set_state(tb_ctx *c, const tb_state *s) {
+    TB_REQUIRE(c, c && s, "null argument");
+    c->state = *s;
+    c->have_state = true;
+    return TB_OK;
+}
+
+int tb_resize_flow(tb_ctx *c, int32_t w, int32_t h) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return alloc_flow(c, w, h);
+}
+
+int tb_clear_flow(tb_ctx *c) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaMemsetAsync(c->flow, 0, static_cast<size_t>(c->W) * c->H * sizeof(float4), c->stream));
+    return TB_OK;
+}
+
+int tb_step(tb_ctx *c, float time, float dt) {
+    TB_REQUIRE(c, c, "null context");
+    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_step");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    std::swap(c->buf[0], c->buf[1]);                       // utils.step(buffers), src/particles.js:128
+    const tb_state &S = c->state;
+    IntegrateArgs A{};
+    A.S = S;
+    A.in = c->buf[1];
+    A.out = c->buf[0];
+    A.targets = c->targets;
+    A.flow = c->flow;
+    A.PW = c->PW; A.PH = c->PH; A.W = c->W; A.H = c->H;
+    A.p0 = static_cast<long long>(c->col0) * c->PH;
+    A.n = c->n_local;
+    A.time = time; A.dt = dt;
+    // The target / noise terms are exactly +-0 for every finite particle when their weight is 0
+    // and the variances are tame; the kernel still takes the full path for wild positions.
+    A.use_targets = !(S.target == 0.0f && tame(S.varyTarget, 1e6f) && c->targets_finite);
+    A.use_noise = !(S.noiseWeight == 0.0f && tame(S.varyNoise, 1e6f) && tame(S.noiseScale, 1e6f) &&
+                    tame(S.varyNoiseScale, 1e6f) && tame(S.noiseSpeed, 1e6f) && tame(S.varyNoiseSpeed, 1e6f) &&
+                    tame(time, 1e9f) && tame(dt, 1e6f));
+    TB_CUDA(c, cudaEventRecord(c->ev_int[0], c->stream));
+    k_integrate<<<blocks_for(A.n, 256), 256, 0, c->stream>>>(A);
+    if (int r = check_launch(c, "k_integrate")) return r;
+    TB_CUDA(c, cudaEventRecord(c->ev_int[1], c->stream));
+    c->timed_int = true;
+    return TB_OK;
+}
+
+int tb_splat_collect(tb_ctx *c, float time) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    return collect(c, time);
+}
+
+int tb_splat_fold(tb_ctx *c) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    return fold(c);
+}
+
+int tb_splat_flow(tb_ctx *c, float time) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaEventRecord(c->ev_spl[0], c->stream));
+    if (int r = collect(c, time)) return r;
+    if (int r = fold(c)) return r;
+    TB_CUDA(c, cudaEventRecord(c->ev_spl[1], c->stream));
+    c->timed_spl = true;
+    return TB_OK;
+}
+
+int tb_reset(tb_ctx *c) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    for (int b = 0; b < 2; ++b) {
+        k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(c->buf[b], c->n_local);
+        if (int r = check_launch(c, "k_spawn_init")) return r;
+    }
+    return TB_OK;
+}
+
+int tb_spawn_init(tb_ctx *c, tb_target target) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    float4 *out = spawn_out(c, target);
+    k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(out, c->n_local);
+    if (int r = check_launch(c, "k_spawn_init")) return r;
+    return after_targets_write(c, target);
+}
+
+int tb_spawn_ball(tb_ctx *c, float radius, float speed, tb_target target) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    SpawnArgs A{};
+    A.out = spawn_out(c, target);
+    A.PW = c->PW; A.PH = c->PH;
+    A.p0 = static_cast<long long>(c->col0) * c->PH;
+    A.n = c->n_local;
+    A.radius = radius; A.speed = speed;
+    k_spawn_ball<<<blocks_for(A.n, 256), 256, 0, c->stream>>>(A);
+    if (int r = check_launch(c, "k_spawn_ball")) return r;
+    return after_targets_write(c, target);
+}
+
+int tb_set_spawn_image(tb_ctx *c, const float *rgba, int32_t w, int32_t h) {
+    TB_REQUIRE(c, c && rgba, "null argument");
+    TB_REQUIRE(c, w >= 1 && h >= 1, "gl-texture2d: Texture dimensions are out of bounds");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const size_t need = static_cast<size_t>(w) * h;
+    if (need > c->image_cap) {
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->image) cudaFree(c->image);
+        c->image = nullptr; c->image_cap = 0;
+        TB_CUDA(c, cudaMalloc(&c->image, need * sizeof(float4)));
+        c->image_cap = need;
+    }
+    TB_CUDA(c, cudaMemcpyAsync(c->image, rgba, need * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));       // the host pointer is only borrowed
+    c->IW = w; c->IH = h;
+    return TB_OK;
+}
+
+int tb_spawn_pixels(tb_ctx *c, const tb_pixel_spawner *params, tb_spawn_variant variant, tb_spawn_source source,
+                    float time, tb_target target) {
+    TB_REQUIRE(c, c && params, "null argument");
+    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_spawn_pixels");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    SpawnArgs A{};
+    A.U = *params;
+    A.PW = c->PW; A.PH = c->PH;
+    A.p0 = static_cast<long long>(c->col0) * c->PH;
+    A.n = c->n_local;
+    A.time = time;
+    A.flowDecay = c->state.flowDecay;
+    switch (variant) {
+        case TB_SPAWN_DIRECT:        A.apply = APPLY_COLOR;     A.vignette = 1; A.samples = 0; break;
+        case TB_SPAWN_BEST_SAMPLE:   A.apply = APPLY_COLOR;     A.vignette = 1; A.samples = 6; break;
+        case TB_SPAWN_BRIGHT_SAMPLE: A.apply = APPLY_BRIGHTEST; A.vignette = 0; A.samples = 6; break;
+        case TB_SPAWN_COLOR_SAMPLE:  A.apply = APPLY_COLOR;     A.vignette = 0; A.samples = 3; break;
+        case TB_SPAWN_DATA_SAMPLE:   A.apply = APPLY_IDENTITY;  A.vignette = 1; A.samples = 2; break;
+        case TB_SPAWN_FLOW_SAMPLE:   A.apply = APPLY_FLOW;      A.vignette = 0; A.samples = 5; break;
+        default: return fail(c, TB_ERR_UNSUPPORTED, "tendrils-b200: custom spawn shaders are not supported");
+    }
+    // `particles` and spawnData are bound BEFORE the ping-pong rotates (src/particles.js:124-141):
+    // particles = buffers[1] after rotation = the current state before it.
+    const float4 *current_before = c->buf[0];
+    switch (source) {
+        case TB_SOURCE_IMAGE:
+            TB_REQUIRE(c, c->image && c->IW > 0, "tb_set_spawn_image must be called first");
+            A.image = c->image; A.IW = c->IW; A.IH = c->IH; A.image_xmajor = 0;
+            break;
+        case TB_SOURCE_FLOW:
+            A.image = c->flow; A.IW = c->W; A.IH = c->H; A.image_xmajor = 0;
+            break;
+        case TB_SOURCE_PARTICLES:
+            TB_REQUIRE(c, c->col0 == 0 && c->col1 == c->PW, "spawning from the particle texture needs an unsharded context");
+            A.image = current_before; A.IW = c->PW; A.IH = c->PH; A.image_xmajor = 1;
+            break;
+        default: return fail(c, TB_ERR_INVALID, "tendrils-b200: bad spawn source");
+    }
+    A.out = spawn_out(c, target);
+    A.state = c->buf[1];
+    if (variant == TB_SPAWN_DIRECT) {
+        k_spawn_direct<<<blocks_for(A.n, 256), 256, 0, c->stream>>>(A);
+        if (int r = check_launch(c, "k_spawn_direct")) return r;
+    } else {
+        k_spawn_sample<<<blocks_for(A.n, 256), 256, 0, c->stream>>>(A);
+        if (int r = check_launch(c, "k_spawn_sample")) return r;
+    }
+    return after_targets_write(c, target);
+}
+
+static int buffer_of(tb_ctx *c, tb_buffer which, float4 **ptr, int64_t *n_floats) {
+    switch (which) {
+        case TB_BUF_CURRENT:  *ptr = c->buf[0];  *n_floats = 4 * c->n_local; return TB_OK;
+        case TB_BUF_PREVIOUS: *ptr = c->buf[1];  *n_floats = 4 * c->n_local; return TB_OK;
+        case TB_BUF_TARGETS:  *ptr = c->targets; *n_floats = 4 * c->n_local; return TB_OK;
+        case TB_BUF_FLOW:     *ptr = c->flow;    *n_floats = 4LL * c->W * c->H; return TB_OK;
+    }
+    return fail(c, TB_ERR_INVALID, "tendrils-b200: bad buffer id");
+}
+
+int tb_upload(tb_ctx *c, tb_buffer which, const float *host, int64_t n_floats) {
+    TB_REQUIRE(c, c && host, "null argument");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    float4 *dst; int64_t n;
+    if (int r = buffer_of(c, which, &dst, &n)) return r;
+    TB_REQUIRE(c, n == n_floats, "tb_upload: size mismatch");
+    TB_CUDA(c, cudaMemcpyAsync(dst, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (which == TB_BUF_TARGETS) return after_targets_write(c, TB_TARGET_TARGETS);
+    return TB_OK;
+}
+
+int tb_download(tb_ctx *c, tb_buffer which, float *host, int64_t n_floats) {
+    TB_REQUIRE(c, c && host, "null argument");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    float4 *src; int64_t n;
+    if (int r = buffer_of(c, which, &src, &n)) return r;
+    TB_REQUIRE(c, n == n_floats, "tb_download: size mismatch");
+    TB_CUDA(c, cudaMemcpyAsync(host, src, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+int tb_blend_into_flow(tb_ctx *c, const float *rgba, int32_t w, int32_t h) {
+    TB_REQUIRE(c, c && rgba, "null argument");
+    TB_REQUIRE(c, w == c->W && h == c->H, "tb_blend_into_flow: layer must have the flow grid's shape");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const size_t G = static_cast<size_t>(w) * h;
+    if (G > c->layer_cap) {
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->layer) cudaFree(c->layer);
+        c->layer = nullptr; c->layer_cap = 0;
+        TB_CUDA(c, cudaMalloc(&c->layer, G * sizeof(float4)));
+        c->layer_cap = G;
+    }
+    TB_CUDA(c, cudaMemcpyAsync(c->layer, rgba, G * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    k_blend_layer<<<blocks_for(static_cast<long long>(G), 256), 256, 0, c->stream>>>(c->flow, c->layer, static_cast<int>(G));
+    if (int r = check_launch(c, "k_blend_layer")) return r;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+int tb_device_ptr(tb_ctx *c, tb_buffer which, void **ptr, int64_t *n_floats) {
+    TB_REQUIRE(c, c && ptr && n_floats, "null argument");
+    float4 *p; int64_t n;
+    if (int r = buffer_of(c, which, &p, &n)) return r;
+    *ptr = p; *n_floats = n;
+    return TB_OK;
+}
+
+int tb_stream(tb_ctx *c, void **cuda_stream) {
+    TB_REQUIRE(c, c && cuda_stream, "null argument");
+    *cuda_stream = c->stream;
+    return TB_OK;
+}
+
+int tb_sync(tb_ctx *c) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+int tb_stats(tb_ctx *c, int64_t *kernel_launches, int64_t *last_fragments) {
+    TB_REQUIRE(c, c, "null context");
+    if (kernel_launches) *kernel_launches = c->launches;
+    if (last_fragments) *last_fragments = c->last_frags;
+    return TB_OK;
+}
+
+int tb_last_timing(tb_ctx *c, float *integrate_ms, float *splat_ms) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (integrate_ms) {
+        *integrate_ms = 0.f;
+        if (c->timed_int) TB_CUDA(c, cudaEventElapsedTime(integrate_ms, c->ev_int[0], c->ev_int[1]));
+    }
+    if (splat_ms) {
+        *splat_ms = 0.f;
+        if (c->timed_spl) TB_CUDA(c, cudaEventElapsedTime(splat_ms, c->ev_spl[0], c->ev_spl[1]));
+    }
+    return TB_OK;
+}
+
+}  // extern "C"

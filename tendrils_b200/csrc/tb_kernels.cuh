@@ -1,0 +1,416 @@
+// tb_kernels.cuh -- sm_100a kernels of the Tendrils step: integrate, flow splat, spawners.
+// Compiled with -fmad=false; see tb_math.cuh for the arithmetic contract.
+#pragma once
+
+#include "tb_math.cuh"
+#include "../../include/tendrils_b200.h"
+
+namespace tb {
+
+static constexpr float kInert = -1000000.0f;   // src/const/inert.glsl:1
+
+// One fragment of the flow splat, as stored in the per-texel lists.  The colour's time
+// channel is the uniform `time` at both vertices, hence constant along the line.
+struct __align__(16) Frag {
+    uint32_t prim;    // primitive (draw) order x*PH + k  (src/particles.js:182-186)
+    float cx, cy;     // interpolated vel.xy
+    float a;          // interpolated alpha
+};
+
+// Line pair k of a column: which texel row and which buffer each of its 2 vertices samples
+// (src/particles.js:171-190 seen through src/state/state-at-frame.glsl:12-22).
+struct PairEntry {
+    int32_t k;        // pair index within the column = position in draw order
+    int32_t row_a;    // texel row of vertex 2k;   bit 31 set: samples the CURRENT buffer
+    int32_t row_b;    // texel row of vertex 2k+1; bit 31 set: samples the CURRENT buffer
+    int32_t pad;
+};
+
+struct IntegrateArgs {
+    tb_state S;
+    const float4 *__restrict__ in;
+    float4 *__restrict__ out;
+    const float4 *__restrict__ targets;
+    const float4 *__restrict__ flow;
+    int PW, PH, W, H;
+    long long p0;          // global index of the first local particle (col0*PH)
+    long long n;           // local particle count
+    float time, dt;
+    int use_targets;       // 0: the target term is provably +-0 for every finite particle
+    int use_noise;         // 0: the noise term is provably +-0 for every finite particle
+};
+
+// a3: src/logic.frag:45-101.  One thread per particle, 16 B in / 16 B out, flow gather via L2.
+__global__ void __launch_bounds__(256) k_integrate(const IntegrateArgs A) {
+    const long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (l >= A.n) return;
+    const float4 st = __ldcs(A.in + l);
+    float posx = st.x, posy = st.y, velx = st.z, vely = st.w;
+    if (!(posx != kInert || posy != kInert)) {
+        __stcs(A.out + l, st);
+        return;
+    }
+    const long long p = A.p0 + l;
+    const int x = static_cast<int>(p / A.PH);
+    const int y = static_cast<int>(p - static_cast<long long>(x) * A.PH);
+    const float resx = static_cast<float>(A.PW), resy = static_cast<float>(A.PH);
+    const float fcx = __fadd_rn(static_cast<float>(x), 0.5f), fcy = __fadd_rn(static_cast<float>(y), 0.5f);
+    const float uvx = __fdiv_rn(fcx, resx), uvy = __fdiv_rn(fcy, resy);
+    const float i = __fdiv_rn(__fadd_rn(fcx, __fmul_rn(fcy, resx)), __fmul_rn(resx, resy));
+    const tb_state &S = A.S;
+
+    const bool tame = fabsf(posx) < 1.0e6f && fabsf(posy) < 1.0e6f;
+    float wx = 0.0f, wy = 0.0f;
+    if (A.use_noise || !tame) {
+        const float ns = vary(S.noiseScale, i, S.varyNoiseScale);
+        const float npx = __fmul_rn(posx, ns), npy = __fmul_rn(posy, ns);
+        const float noiseTime = __fmul_rn(A.time, vary(S.noiseSpeed, i, S.varyNoiseSpeed));
+        wx = snoise3(npx, npy, __fadd_rn(uvx, noiseTime));
+        wy = snoise3(npx, npy, __fadd_rn(__fadd_rn(uvy, noiseTime), 1234.5678f));
+    }
+
+    // flowAtScreenPos (flow/flow-at-screen-pos.glsl:13-27) with levels = stride = 1
+    const float spx = __fmul_rn(posx, S.viewSize[0]), spy = __fmul_rn(posy, S.viewSize[1]);
+    const float fu = __fadd_rn(0.0f, __fdiv_rn(__fmul_rn(1.0f, __fsub_rn(spx, -1.0f)), 2.0f));
+    const float fv = __fadd_rn(0.0f, __fdiv_rn(__fmul_rn(1.0f, __fsub_rn(spy, -1.0f)), 2.0f));
+    const float4 fd = __ldg(A.flow + (static_cast<size_t>(texel_of(fv, A.H)) * A.W + texel_of(fu, A.W)));
+    const float fac = gmax(0.0f, __fsub_rn(1.0f, __fmul_rn(__fsub_rn(A.time, fd.z), S.flowDecay)));
+    float ffx = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(fd.x, fac), 1.0f));
+    float ffy = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(fd.y, fac), 1.0f));
+    ffx = __fdiv_rn(ffx, 1.0f);
+    ffy = __fdiv_rn(ffy, 1.0f);
+
+    const float vforce = vary(S.forceWeight, i, S.varyForce);
+    const float vflow = vary(S.flowWeight, i, S.varyFlow);
+    const float vnoise = vary(S.noiseWeight, i, S.varyNoise);
+    float nvx = __fadd_rn(__fmul_rn(__fmul_rn(velx, S.damping), A.dt),
+                          __fmul_rn(vforce, __fadd_rn(__fmul_rn(__fmul_rn(ffx, A.dt), vflow),
+                                                      __fmul_rn(__fmul_rn(wx, A.dt), vnoise))));
+    float nvy = __fadd_rn(__fmul_rn(__fmul_rn(vely, S.damping), A.dt),
+                          __fmul_rn(vforce, __fadd_rn(__fmul_rn(__fmul_rn(ffy, A.dt), vflow),
+                                                      __fmul_rn(__fmul_rn(wy, A.dt), vnoise))));
+    if (A.use_targets || !tame) {
+        const float4 tg = __ldcs(A.targets + l);
+        const float vt = vary(S.target, i, S.varyTarget);
+        nvx = __fadd_rn(nvx, __fmul_rn(__fsub_rn(tg.x, posx), vt));
+        nvy = __fadd_rn(nvy, __fmul_rn(__fsub_rn(tg.y, posy), vt));
+    }
+    const float speed = glength(nvx, nvy);
+    const float sc = __fdiv_rn(gmin(speed, S.speedLimit), speed);
+    nvx = __fmul_rn(nvx, sc);
+    nvy = __fmul_rn(nvy, sc);
+    __stcs(A.out + l, make_float4(__fadd_rn(posx, nvx), __fadd_rn(posy, nvy), nvx, nvy));
+}
+
+// ------------------------------------------------------------------------------------------
+// Flow splat (a7-a10).  RASTER-1 (spec/PARITY.md): GL_LINES of width 1, centre-sampled along
+// the major axis, half-open towards the second vertex, scissored to the grid.
+// ------------------------------------------------------------------------------------------
+struct SplatArgs {
+    const float4 *__restrict__ cur;
+    const float4 *__restrict__ prev;
+    const PairEntry *__restrict__ pairs;
+    int n_pairs;           // active (non-degenerate) pairs per column
+    int PH;
+    int cols;              // local columns
+    int col0;              // first global column
+    int W, H;
+    float vsx, vsy, speedLimit;
+    uint32_t *tex_off;     // count pass: per-texel counters; emit pass: running offsets
+    Frag *frags;
+    uint32_t cap;          // capacity of frags
+    const uint32_t *total; // device: total fragments of this collect (after the scan)
+};
+
+template <class Emit>
+__device__ __forceinline__ void raster_line(float xa, float ya, float xb, float yb, int W, int H, Emit &&emit) {
+    const float dx = __fsub_rn(xb, xa), dy = __fsub_rn(yb, ya);
+    const float adx = fabsf(dx), ady = fabsf(dy);
+    const bool xmajor = adx >= ady;
+    // major/minor axis views
+    const float ma = xmajor ? xa : ya, mb = xmajor ? xb : yb, dm = xmajor ? dx : dy;
+    const float na = xmajor ? ya : xa, dn = xmajor ? dy : dx;
+    const int M = xmajor ? W : H, N = xmajor ? H : W;
+    if (!(fabsf(dm) > 0.0f)) return;
+    float flo = __fsub_rn(floorf(gmin(ma, mb)), 1.0f), fhi = __fadd_rn(floorf(gmax(ma, mb)), 1.0f);
+    if (flo < 0.0f) flo = 0.0f;
+    if (fhi > static_cast<float>(M - 1)) fhi = static_cast<float>(M - 1);
+    if (!(flo <= fhi)) return;
+    const int ihi = static_cast<int>(fhi);
+    for (int i = static_cast<int>(flo); i <= ihi; ++i) {
+        const float ic = __fadd_rn(static_cast<float>(i), 0.5f);
+        const bool in = (dm > 0.0f) ? (ma <= ic && ic < mb) : (mb < ic && ic <= ma);
+        if (!in) continue;
+        const float t = __fdiv_rn(__fsub_rn(ic, ma), dm);
+        const float nn = __fadd_rn(na, __fmul_rn(t, dn));
+        const float fj = floorf(nn);
+        if (!(fj >= 0.0f && fj <= static_cast<float>(N - 1))) continue;
+        const int j = static_cast<int>(fj);
+        emit(xmajor ? i : j, xmajor ? j : i, t);
+    }
+}
+
+// Loads the two vertices of pair (column, entry) and hands window coordinates + colours on.
+template <class Body>
+__device__ __forceinline__ void splat_pair(const SplatArgs &A, Body &&body) {
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tid >= static_cast<long long>(A.cols) * A.n_pairs) return;
+    const int xl = static_cast<int>(tid / A.n_pairs);
+    const PairEntry pe = A.pairs[tid - static_cast<long long>(xl) * A.n_pairs];
+    const size_t base = static_cast<size_t>(xl) * A.PH;
+    const float4 sa = __ldg(((pe.row_a < 0) ? A.cur : A.prev) + base + (pe.row_a & 0x7fffffff));
+    const float4 sb = __ldg(((pe.row_b < 0) ? A.cur : A.prev) + base + (pe.row_b & 0x7fffffff));
+    // inert vertices leave gl_Position unwritten: culled (V1); non-finite vertices: culled (V2)
+    if (!(sa.x != kInert || sa.y != kInert)) return;
+    if (!(sb.x != kInert || sb.y != kInert)) return;
+    if (!(is_finite(sa.x) && is_finite(sa.y) && is_finite(sa.z) && is_finite(sa.w))) return;
+    if (!(is_finite(sb.x) && is_finite(sb.y) && is_finite(sb.z) && is_finite(sb.w))) return;
+    const float hw = __fmul_rn(0.5f, static_cast<float>(A.W)), hh = __fmul_rn(0.5f, static_cast<float>(A.H));
+    const float xa = __fadd_rn(__fmul_rn(__fmul_rn(sa.x, A.vsx), hw), hw);
+    const float ya = __fadd_rn(__fmul_rn(__fmul_rn(sa.y, A.vsy), hh), hh);
+    const float xb = __fadd_rn(__fmul_rn(__fmul_rn(sb.x, A.vsx), hw), hw);
+    const float yb = __fadd_rn(__fmul_rn(__fmul_rn(sb.y, A.vsy), hh), hh);
+    const uint32_t prim = static_cast<uint32_t>(A.col0 + xl) * static_cast<uint32_t>(A.PH) + static_cast<uint32_t>(pe.k);
+    body(prim, xa, ya, xb, yb, sa, sb);
+}
+
+__global__ void __launch_bounds__(256) k_splat_count(const SplatArgs A) {
+    splat_pair(A, [&](uint32_t, float xa, float ya, float xb, float yb, const float4 &, const float4 &) {
+        raster_line(xa, ya, xb, yb, A.W, A.H, [&](int gx, int gy, float) {
+            atomicAdd(A.tex_off + (static_cast<size_t>(gy) * A.W + gx), 1u);
+        });
+    });
+}
+
+__global__ void __launch_bounds__(256) k_splat_emit(const SplatArgs A) {
+    if (*A.total > A.cap) return;            // host re-runs the collect with a larger buffer
+    splat_pair(A, [&](uint32_t prim, float xa, float ya, float xb, float yb, const float4 &sa, const float4 &sb) {
+        // flow(vel, speedLimit): src/flow/apply/state.glsl:5-16
+        const float aa = gmin(__fdiv_rn(glength(sa.z, sa.w), A.speedLimit), 1.0f);
+        const float ab = gmin(__fdiv_rn(glength(sb.z, sb.w), A.speedLimit), 1.0f);
+        raster_line(xa, ya, xb, yb, A.W, A.H, [&](int gx, int gy, float t) {
+            Frag f;
+            f.prim = prim;
+            f.cx = __fadd_rn(sa.z, __fmul_rn(t, __fsub_rn(sb.z, sa.z)));
+            f.cy = __fadd_rn(sa.w, __fmul_rn(t, __fsub_rn(sb.w, sa.w)));
+            f.a = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
+            const uint32_t slot = atomicAdd(A.tex_off + (static_cast<size_t>(gy) * A.W + gx), 1u);
+            *reinterpret_cast<uint4 *>(A.frags + slot) = *reinterpret_cast<const uint4 *>(&f);
+        });
+    });
+}
+
+// Ordered alpha-over fold of one texel's fragment list: blendFunc(SRC_ALPHA,
+// ONE_MINUS_SRC_ALPHA) on all four channels, in primitive order (src/index.js:267-268).
+// ends[t] is the running offset left by the emit pass = end of texel t's list.
+__global__ void __launch_bounds__(128) k_splat_fold(float4 *__restrict__ flow, const uint32_t *__restrict__ ends,
+                                                     Frag *__restrict__ frags, int G, float time,
+                                                     const uint32_t *total, uint32_t cap) {
+    if (*total > cap) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G) return;
+    const uint32_t begin = t ? ends[t - 1] : 0u, end = ends[t];
+    const uint32_t n = end - begin;
+    if (n == 0) return;
+    uint4 *r = reinterpret_cast<uint4 *>(frags + begin);
+    // lists arrive almost sorted (CTAs run in primitive order): insertion sort by prim
+    for (uint32_t i = 1; i < n; ++i) {
+        const uint4 v = r[i];
+        uint32_t j = i;
+        while (j > 0) {
+            const uint4 u = r[j - 1];
+            if (u.x <= v.x) break;
+            r[j] = u;
+            --j;
+        }
+        if (j != i) r[j] = v;
+    }
+    float4 d = flow[t];
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint4 v = r[i];
+        const float cx = __uint_as_float(v.y), cy = __uint_as_float(v.z), a = __uint_as_float(v.w);
+        const float om = __fsub_rn(1.0f, a);
+        d.x = __fadd_rn(__fmul_rn(cx, a), __fmul_rn(d.x, om));
+        d.y = __fadd_rn(__fmul_rn(cy, a), __fmul_rn(d.y, om));
+        d.z = __fadd_rn(__fmul_rn(time, a), __fmul_rn(d.z, om));
+        d.w = __fadd_rn(__fmul_rn(a, a), __fmul_rn(d.w, om));
+    }
+    flow[t] = d;
+}
+
+// Full-grid alpha-over of an RGBA layer (L4 inputs drawn into the flow FBO).
+__global__ void k_blend_layer(float4 *__restrict__ flow, const float4 *__restrict__ layer, int G) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G) return;
+    const float4 s = layer[t];
+    float4 d = flow[t];
+    const float a = s.w, om = __fsub_rn(1.0f, a);
+    d.x = __fadd_rn(__fmul_rn(s.x, a), __fmul_rn(d.x, om));
+    d.y = __fadd_rn(__fmul_rn(s.y, a), __fmul_rn(d.y, om));
+    d.z = __fadd_rn(__fmul_rn(s.z, a), __fmul_rn(d.z, om));
+    d.w = __fadd_rn(__fmul_rn(s.w, a), __fmul_rn(d.w, om));
+    flow[t] = d;
+}
+
+// ------------------------------------------------------------------------------------------
+// Spawners (a12-a15)
+// ------------------------------------------------------------------------------------------
+struct SpawnArgs {
+    float4 *__restrict__ out;
+    const float4 *__restrict__ state;   // `particles` sampler = buffers[1]
+    const float4 *__restrict__ image;   // spawnData
+    int PW, PH, IW, IH;
+    int image_xmajor;                   // spawnData is a particle buffer (texel (x,y) at x*IH+y)
+    long long p0, n;
+    tb_pixel_spawner U;
+    float time, flowDecay;
+    float radius, speed;
+    int apply, vignette, samples;       // pixel spawner composition
+};
+
+static constexpr float kTau = 6.28318530717958647692f;
+enum { APPLY_COLOR = 0, APPLY_BRIGHTEST = 1, APPLY_IDENTITY = 2, APPLY_FLOW = 3 };
+
+__global__ void k_spawn_init(float4 *__restrict__ out, long long n) {          // spawn/init/index.frag:5-10
+    const long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (l < n) out[l] = make_float4(kInert, kInert, 0.0f, 0.0f);
+}
+
+__global__ void k_spawn_ball(const SpawnArgs A) {                                // spawn/ball/index.frag:11-19
+    const long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (l >= A.n) return;
+    const long long p = A.p0 + l;
+    const int x = static_cast<int>(p / A.PH), y = static_cast<int>(p - static_cast<long long>(x) * A.PH);
+    const float fx = __fadd_rn(static_cast<float>(x), 0.5f), fy = __fadd_rn(static_cast<float>(y), 0.5f);
+    const float r0 = grandom(__fadd_rn(__fmul_rn(fx, 1.7654f), 2.3675f), __fadd_rn(__fmul_rn(fy, 1.7654f), 2.3675f));
+    const float r1 = grandom(__fadd_rn(__fmul_rn(fx, 1.23494f), 0.36434f), __fadd_rn(__fmul_rn(fy, 1.23494f), 0.36434f));
+    const float r2 = grandom(__fadd_rn(__fmul_rn(fx, 0.327789f), 3.498787f), __fadd_rn(__fmul_rn(fy, 0.327789f), 3.498787f));
+    const float r3 = grandom(__fadd_rn(__fmul_rn(fx, 9.0374f), 0.2773f), __fadd_rn(__fmul_rn(fy, 9.0374f), 0.2773f));
+    float s0, c0, s1, c1;
+    sincos_t1(__fmul_rn(r0, kTau), s0, c0);
+    sincos_t1(__fmul_rn(r2, kTau), s1, c1);
+    A.out[l] = make_float4(__fmul_rn(__fmul_rn(c0, r1), A.radius), __fmul_rn(__fmul_rn(s0, r1), A.radius),
+                           __fmul_rn(__fmul_rn(c1, r3), A.speed), __fmul_rn(__fmul_rn(s1, r3), A.speed));
+}
+
+// spawn/pixels/frag/head.frag:28-34
+__device__ __forceinline__ float2 spawn_to_pos(const tb_pixel_spawner &U, float u, float v, float time) {
+    const float tt = __fmul_rn(time, 0.001f);
+    const float ox = gmix(-U.jitter[0], U.jitter[0],
+                          grandom(__fadd_rn(__fsub_rn(u, 1.2345f), tt), __fadd_rn(__fsub_rn(v, 1.2345f), tt)));
+    const float oy = gmix(-U.jitter[1], U.jitter[1],
+                          grandom(__fadd_rn(__fadd_rn(u, 1.2345f), tt), __fadd_rn(__fadd_rn(v, 1.2345f), tt)));
+    const float uu = __fadd_rn(u, ox), vv = __fadd_rn(v, oy);
+    // uvToPos = glsl-map(uv, 0, 1, -1, 1)
+    float qx = __fadd_rn(-1.0f, __fdiv_rn(__fmul_rn(2.0f, __fsub_rn(uu, 0.0f)), 1.0f));
+    float qy = __fadd_rn(-1.0f, __fdiv_rn(__fmul_rn(2.0f, __fsub_rn(vv, 0.0f)), 1.0f));
+    qx = __fmul_rn(__fmul_rn(qx, 1.0f), U.spawnSize[0]);
+    qy = __fmul_rn(__fmul_rn(qy, -1.0f), U.spawnSize[1]);
+    const float *m = U.spawnMatrix;
+    return make_float2(__fadd_rn(__fadd_rn(__fmul_rn(m[0], qx), __fmul_rn(m[3], qy)), __fmul_rn(m[6], 1.0f)),
+                       __fadd_rn(__fadd_rn(__fmul_rn(m[1], qx), __fmul_rn(m[4], qy)), __fmul_rn(m[7], 1.0f)));
+}
+
+// filter/vignette.glsl:5-24, spawn/pixels/vignette-head.glsl:4-6, utils/bezier.glsl:9-13
+__device__ __forceinline__ float vignette(float u, float v) {
+    const float amount = gmin(__fsub_rn(1.0f, __fdiv_rn(glength(__fsub_rn(u, 0.5f), __fsub_rn(v, 0.5f)), 0.6f)), 1.0f);
+    const float t = amount, ut = __fsub_rn(1.0f, t);
+    const float l = __fmul_rn(__fadd_rn(__fmul_rn(0.1f, ut), __fmul_rn(1.0f, t)), ut);
+    const float r = __fmul_rn(__fadd_rn(__fmul_rn(1.0f, ut), __fmul_rn(1.0f, t)), t);
+    return gmax(0.0f, __fadd_rn(l, r));
+}
+
+// libs/glsl-hsv/rgb-hsv.glsl:4-11
+__device__ __forceinline__ float3 rgb2hsv(float r, float g, float b) {
+    const float ky = -1.0f / 3.0f, kz = 2.0f / 3.0f, e = 1.0e-10f;
+    float p0, p1, p2, p3;
+    if (g < b) { p0 = b; p1 = g; p2 = -1.0f; p3 = kz; } else { p0 = g; p1 = b; p2 = 0.0f; p3 = ky; }
+    float q0, q1, q2, q3;
+    if (r < p0) { q0 = p0; q1 = p1; q2 = p3; q3 = r; } else { q0 = r; q1 = p1; q2 = p2; q3 = p0; }
+    const float d = __fsub_rn(q0, gmin(q3, q1));
+    const float h = fabsf(__fadd_rn(q2, __fdiv_rn(__fsub_rn(q3, q1), __fadd_rn(__fmul_rn(6.0f, d), e))));
+    return make_float3(h, __fdiv_rn(d, __fadd_rn(q0, e)), q0);
+}
+
+__device__ __forceinline__ float4 fetch_image(const SpawnArgs &A, float u, float v) {
+    const int tx = texel_of(u, A.IW), ty = texel_of(v, A.IH);
+    const size_t idx = A.image_xmajor ? (static_cast<size_t>(tx) * A.IH + ty) : (static_cast<size_t>(ty) * A.IW + tx);
+    return __ldg(A.image + idx);
+}
+
+// apply/<kind>.glsl, optionally composed with filter/pass/vignette.glsl (apply/compose-filter.glsl)
+__device__ __forceinline__ float4 apply_pixel(const SpawnArgs &A, float u, float v, float2 pos, float4 px) {
+    if (A.vignette) {
+        const float w = vignette(u, v);
+        px = make_float4(__fmul_rn(px.x, w), __fmul_rn(px.y, w), __fmul_rn(px.z, w), __fmul_rn(px.w, w));
+    }
+    float s, c;
+    if (A.apply == APPLY_COLOR) {                  // apply/color.glsl:13-17
+        const float3 hsv = rgb2hsv(px.x, px.y, px.z);
+        sincos_t1(__fmul_rn(__fadd_rn(hsv.x, __fmul_rn(A.time, 0.00003f)), kTau), s, c);
+        return make_float4(pos.x, pos.y, __fmul_rn(__fmul_rn(__fmul_rn(c, hsv.y), hsv.z), px.w),
+                           __fmul_rn(__fmul_rn(__fmul_rn(s, hsv.y), hsv.z), px.w));
+    }
+    if (A.apply == APPLY_BRIGHTEST) {              // apply/brightest.glsl:12-16, glsl-luma
+        const float dd = __fadd_rn(__fmul_rn(px.x, px.z), __fmul_rn(px.y, px.w));
+        const float ang = __fmul_rn(gmod(grandom(__fmul_rn(u, dd), __fmul_rn(v, dd)), 1.0f), kTau);
+        const float luma = dot3(px.x, px.y, px.z, 0.299f, 0.587f, 0.114f);
+        sincos_t1(ang, s, c);
+        return make_float4(pos.x, pos.y, __fmul_rn(__fmul_rn(c, luma), px.w), __fmul_rn(__fmul_rn(s, luma), px.w));
+    }
+    if (A.apply == APPLY_IDENTITY) return px;      // apply/identity.glsl
+    const float fac = gmax(0.0f, __fsub_rn(1.0f, __fmul_rn(__fsub_rn(A.time, px.z), A.flowDecay)));
+    return make_float4(pos.x, pos.y, __fmul_rn(px.x, fac), __fmul_rn(px.y, fac));   // apply/flow.glsl
+}
+
+// a14: spawn/pixels/index.frag -> frag/direct-main.frag:9-20
+__global__ void k_spawn_direct(const SpawnArgs A) {
+    const long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (l >= A.n) return;
+    const long long p = A.p0 + l;
+    const int x = static_cast<int>(p / A.PH), y = static_cast<int>(p - static_cast<long long>(x) * A.PH);
+    const float pw = static_cast<float>(A.PW), ph = static_cast<float>(A.PH);
+    const float u = __fmul_rn(__fdiv_rn(__fadd_rn(static_cast<float>(x), 0.5f), pw), __fdiv_rn(pw, pw));
+    const float v = __fmul_rn(__fdiv_rn(__fadd_rn(static_cast<float>(y), 0.5f), ph),
+                              __fdiv_rn(static_cast<float>(2 * A.PH), ph));
+    const float2 pos = spawn_to_pos(A.U, u, v, A.time);
+    const float4 st = apply_pixel(A, u, v, pos, fetch_image(A, u, v));
+    A.out[l] = make_float4(st.x, st.y, __fmul_rn(st.z, A.U.speed), __fmul_rn(st.w, A.U.speed));
+}
+
+// a15: spawn/pixels/*-sample.frag -> frag/best-sample-main.frag:21-46, test/particles.glsl:8-10
+__global__ void k_spawn_sample(const SpawnArgs A) {
+    const long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (l >= A.n) return;
+    const long long p = A.p0 + l;
+    const int x = static_cast<int>(p / A.PH), y = static_cast<int>(p - static_cast<long long>(x) * A.PH);
+    const float u = __fdiv_rn(__fadd_rn(static_cast<float>(x), 0.5f), static_cast<float>(A.PW));
+    const float v = __fdiv_rn(__fadd_rn(static_cast<float>(y), 0.5f), static_cast<float>(A.PH));
+    float4 st = A.state[l];
+    const float k0 = __fadd_rn(1.2345f, __fmul_rn(A.time, 0.001f));
+    const float b0 = __fadd_rn(__fadd_rn(st.x, u), k0), b1 = __fadd_rn(__fadd_rn(st.y, v), k0);
+    const float b2 = __fadd_rn(__fadd_rn(st.z, u), k0), b3 = __fadd_rn(__fadd_rn(st.w, v), k0);
+    for (int n = 0; n < A.samples; ++n) {
+        const float fn = static_cast<float>(n);
+        const float su = gmod(grandom(__fadd_rn(b0, fn), __fadd_rn(b1, fn)), 1.0f);
+        const float sv = gmod(grandom(__fadd_rn(b2, fn), __fadd_rn(b3, fn)), 1.0f);
+        const float2 pos = spawn_to_pos(A.U, su, sv, A.time);
+        float4 o = apply_pixel(A, su, sv, pos, fetch_image(A, su, sv));
+        o.z = __fmul_rn(o.z, A.U.speed);
+        o.w = __fmul_rn(o.w, A.U.speed);
+        const float tc = __fadd_rn(__fmul_rn(st.z, st.z), __fmul_rn(st.w, st.w));
+        const float tn = __fadd_rn(__fmul_rn(o.z, o.z), __fmul_rn(o.w, o.w));
+        if (!(tc > __fmul_rn(A.U.bias, tn))) st = o;
+    }
+    A.out[l] = st;
+}
+
+// sets *flag to 1 if any component of the buffer is non-finite
+__global__ void k_check_finite(const float4 *__restrict__ buf, long long n, int *flag) {
+    const long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const float4 v = buf[l];
+    if (!(is_finite(v.x) && is_finite(v.y) && is_finite(v.z) && is_finite(v.w))) *flag = 1;
+}
+
+}  // namespace tb
