@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the Tendrils step (integrate + flow splat + respawn) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
+
+N > 1 is launched by torchrun (one rank per GPU); rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json): at N = 1 `configs[2]` -- 4096x4096 particles, 1024x1024 flow grid with
+flowDecay + trail splat, image-pixel (best-sample) respawn every 60th step -- which is the
+configuration the metric's target (">= 70 % of HBM roofline ... at 16M particles on 1 B200") is
+quoted on; at N > 1 `configs[3]`, the same per GPU (weak scaling, global texture 4096N x 4096).
+
+A "step" = Tendrils.step() + the flow half of Tendrils.draw() (+ the respawn pass when due).
+`value` counts inputs resident in HBM; `e2e` re-measures with the particle state crossing
+PCIe in both directions every step.  `--impl reference` times the CPU oracle port (the
+reference itself -- WebGL shaders -- cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: particle texture root, flow grid, respawn
+    "cfg1": dict(R=512, G=256, respawn="ball", every=0, desc="512x512 particles, 256^2 flow grid, ball spawn"),
+    "cfg2": dict(R=2048, G=512, respawn="ball", every=0, desc="2048x2048 particles, 512^2 flow grid, defaults, noise on"),
+    "cfg3": dict(R=4096, G=1024, respawn="best-sample", every=60,
+                 desc="4096x4096 particles per GPU, 1024^2 flow grid, flowDecay + trail splat, "
+                      "direct image-pixel spawn (spawnImage) at step 0, best-sample image respawn (spawnSamples) every 60th step"),
+}
+METRIC = "particle_steps_per_sec"
+UNIT = "particle-steps/s"
+
+
+def synthetic_image(n):
+    from util import synthetic_image as mk
+    return mk(n, n)
+
+
+def algorithmic_bytes(n_particles, grid):
+    """state read+write 32 B/particle; flow grid gathered once 16 B/texel;
+    flow update read+write 32 B/texel."""
+    return {"integrate": 32 * n_particles + 16 * grid, "splat": 32 * grid, "step": 32 * n_particles + 48 * grid}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = the upper half of the samples (idle samples at the edges pull the median down)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_sim(wl, rank, world, local_rank, group):
+    import tendrils_b200 as T
+    from tendrils_b200.spawn import PixelSpawner, spawnBall
+    from tendrils_b200.spawn.pixels import bestSampleFrag, mat3_identity, mat3_scale, pixelsFrag
+    R, G = wl["R"], wl["G"]
+    t = T.Tendrils(T.Device(G, G, device=local_rank, rank=rank, world_size=world, group=group))
+    t.setup([R * world, R])
+    t.resize()
+    first = spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}})  # src/demo.main.js:1402-1405
+    sp = None
+    if wl["respawn"] == "best-sample":
+        img = synthetic_image(G)
+        flip = mat3_scale(mat3_identity(), [-1, 1])                       # src/demo.main.js:462-463
+        # spawnImage: direct pixel spawn, speed 0.3 (src/demo.main.js:511-512); spawnSamples: best-sample, speed 1 (:514-515)
+        first = PixelSpawner(t.gl, {"shader": pixelsFrag, "buffer": img, "speed": 0.3, "jitterRad": 2, "spawnSize": [1, 1]})
+        sp = PixelSpawner(t.gl, {"shader": bestSampleFrag, "buffer": img, "speed": 1, "bias": 1, "jitterRad": 2,
+                                 "spawnSize": [1, 1]})
+        first.spawnMatrix = sp.spawnMatrix = flip
+    return t, first, sp
+
+
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        group = dist.group.WORLD
+    torch.cuda.set_device(local_rank)
+    t, first, sp = build_sim(wl, rank, world, local_rank, group)
+    P = t.particles
+    n_local = (P.col1 - P.col0) * P.shape[1]
+    n_total = P.shape[0] * P.shape[1]
+    grid = wl["G"] * wl["G"]
+    stream = torch.cuda.ExternalStream(P.stream_handle(), device=torch.device("cuda", local_rank))
+    counter = {"k": 0}
+
+    def one_step():
+        k = counter["k"]
+        if k == 0:
+            first.spawn(t)                    # spawnShader ticks the timer itself (src/index.js:433)
+        elif wl["every"] and k % wl["every"] == 0:
+            sp.spawn(t)
+        t.timer.tick()
+        t.step().draw()
+        counter["k"] = k + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    P.timing(reset=True)
+    launches0 = P.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = P.stats()["kernel_launches"] - launches0
+    frags = P.stats()["last_fragments"]
+    tm = P.timing()
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+
+    # ---- e2e: the same steps with the particle state crossing PCIe both ways every step -------
+    e2e_steps = max(1, min(args.steps, 6))
+    host = torch.empty((P.col1 - P.col0, P.shape[1], 4), dtype=torch.float32, pin_memory=True)
+    hview = host.numpy()
+    hview[...] = P.buffers[0].download()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        P.buffers[0].upload(hview)            # H2D: this step's input state, from pinned memory
+        one_step()
+        hview[...] = P.buffers[0].download()  # D2H: the step's result
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ab = algorithmic_bytes(n_local, grid)
+    int_us = 1e3 * tm["integrate_ms"] / max(tm["n_integrate"], 1)
+    spl_us = 1e3 * tm["splat_ms"] / max(tm["n_splat"], 1)
+    dominant = "k_integrate" if int_us >= spl_us else "flow splat (k_splat_count+scan+k_splat_emit+k_splat_fold)"
+    dom_bytes, dom_us = (ab["integrate"], int_us) if int_us >= spl_us else (ab["splat"], spl_us)
+    achieved = dom_bytes / (dom_us * 1e-6) / 1e9
+    step_gbs = ab["step"] / (ms / args.steps * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "particles_per_gpu": n_local, "particles_total": n_total,
+                   "flow_grid": [wl["G"], wl["G"]], "state": "reference defaults (src/index.js:29-57), noise on",
+                   "splat": "exact ordered alpha-over (reference semantics)", "fragments_last_step": frags,
+                   "l2": "inputs larger than L2 (state 2 x %d MiB per GPU)" % (n_local * 16 >> 20),
+                   "parallelism": f"particle columns sharded over {world} GPU(s), ordered ring fold of the flow grid"},
+        "clocks": clocks,
+        "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": UNIT, "steps": e2e_steps,
+                "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 16},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": dom_us,
+                     "integrate_us": int_us, "splat_us": spl_us,
+                     "whole_step": {"algorithmic_bytes": ab["step"], "achieved": step_gbs, "frac": step_gbs / peak}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_arm(args, wl, budget_s=args.cpu_budget, as_reference=False)
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(args, wl, budget_s, as_reference):
+    from oracle import oracle as O
+    O.build()
+    R, G = wl["R"], wl["G"]
+    cols = (0, max(R // 4, 1))                          # the bounded sample: the first quarter of the columns
+    n_sample = (cols[1] - cols[0]) * R
+    Pm = O.make_params()
+    S = O.make_spawn_pixels(jitter=(np.float32(np.float32(1.0 / G) * 2), np.float32(np.float32(1.0 / G) * 2)),
+                            spawnMatrix=(-1, 0, 0, 0, 1, 0, 0, 0, 1))
+    img = synthetic_image(G)
+    state = {"cur": O.spawn_init(R, R), "prev": O.spawn_init(R, R), "k": 0, "time": 0.0}
+    targets = np.zeros((R, R, 4), np.float32)
+    flow = np.zeros((G, G, 4), np.float32)
+    dt = 1000 / 60
+
+    def one_step():
+        k = state["k"]
+        if k == 0 or (wl["every"] and k % wl["every"] == 0):
+            state["time"] += dt
+            if k == 0 and wl["respawn"] == "ball":
+                new = O.spawn_ball(R, R, 0.3, 0.005, cols=cols)
+            elif k == 0:
+                S.speed = 0.3
+                new = O.spawn_pixels_direct(S, R, R, img, state["time"], cols=cols)
+                S.speed = 1.0
+            else:
+                new = O.spawn_pixels_sample(S, "best", state["cur"], img, state["time"], cols=cols)
+            state["prev"], state["cur"] = state["cur"], new
+        state["time"] += dt
+        new = O.integrate(Pm, state["cur"], targets, flow, state["time"], dt, cols=cols)
+        state["prev"], state["cur"] = state["cur"], new
+        O.splat(Pm, state["cur"], state["prev"], flow, state["time"], cols=cols, mt=True)
+        state["k"] = k + 1
+
+    if as_reference:
+        warm, steps = args.warmup, args.steps
+    else:
+        one_step()                                   # calibrate the bounded sample
+        t0 = time.perf_counter(); one_step(); per = time.perf_counter() - t0
+        warm, steps = 0, int(min(max(budget_s / max(per, 1e-3), 3), 200))
+    for _ in range(warm):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    el = time.perf_counter() - t0
+    return {"value": n_sample * steps / el, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": f"columns [{cols[0]},{cols[1]}) of the {R}x{R} particle texture ({n_sample} particles) on the full "
+                      f"{G}^2 flow grid, {steps} steps of integrate + ordered splat (+ respawn when due), OpenMP over "
+                      f"{O.num_threads()} threads; oracle/tendrils_oracle.c",
+            "steps": steps, "seconds": el, "ms_per_step": 1e3 * el / steps}
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return None
+    cb = cpu_arm(args, wl, budget_s=0, as_reference=True)
+    return {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}",
+                   "note": "CPU oracle port of the reference shaders (the WebGL reference cannot run here); host cores only"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=120)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py: --gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    wl = WORKLOADS[args.workload]
+    out = run_reference(args, wl, rank, world) if args.impl == "reference" else run_ours(args, wl, rank, world, local_rank)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -168,8 +168,10 @@ int tb_stream(tb_ctx *ctx, void **cuda_stream);
 int tb_sync(tb_ctx *ctx);
 /* counters since creation: kernels launched by this library, fragments blended by the last splat */
 int tb_stats(tb_ctx *ctx, int64_t *kernel_launches, int64_t *last_fragments);
-/* CUDA-event timing of the last tb_step / tb_splat_flow kernels in milliseconds (after tb_sync) */
-int tb_last_timing(tb_ctx *ctx, float *integrate_ms, float *splat_ms);
+/* CUDA-event timing, recorded on the context's stream around every integrate launch and every
+ * tb_splat_flow: number of timed calls since the last reset (at most 512 are kept) and their
+ * summed device time in milliseconds.  Synchronises the stream.  reset != 0 restarts the count. */
+int tb_timing(tb_ctx *ctx, int reset, int64_t *n_integrate, float *integrate_ms, int64_t *n_splat, float *splat_ms);
 
 #ifdef __cplusplus
 }

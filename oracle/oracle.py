@@ -98,6 +98,8 @@ def lib():
         L.or_splat.restype = C.c_longlong
         L.or_splat.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int,
                                _fp, _fp, _fp, C.c_int, C.c_int, C.c_float]
+        L.or_splat_mt.restype = C.c_longlong
+        L.or_splat_mt.argtypes = L.or_splat.argtypes
         L.or_spawn_init.restype = None
         L.or_spawn_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _fp]
         L.or_spawn_ball.restype = None
@@ -131,7 +133,7 @@ def integrate(P, state, targets, flow, time, dt, cols=None):
     PW, PH = state.shape[:2]
     H, W = flow.shape[:2]
     x0, x1 = cols or (0, PW)
-    out = np.array(state, copy=True)
+    out = np.array(state, copy=True) if cols is None else np.empty_like(state)
     lib().or_integrate(C.byref(P), PW, PH, x0, x1, _p(state), _p(out), _p(targets), _p(flow),
                        W, H, f32(time), f32(dt))
     return out
@@ -150,30 +152,34 @@ def column_table(PW):
     return col
 
 
-def splat(P, cur, prev, flow, time, cols=None):
+def splat(P, cur, prev, flow, time, cols=None, mt=False):
     """Blends in place into flow ([H,W,4]); returns the fragment count."""
     PW, PH = cur.shape[:2]
     H, W = flow.shape[:2]
     x0, x1 = cols or (0, PW)
-    return lib().or_splat(C.byref(P), PW, PH, x0, x1, _p(cur), _p(prev), _p(flow), W, H, f32(time))
+    fn = lib().or_splat_mt if mt else lib().or_splat
+    return fn(C.byref(P), PW, PH, x0, x1, _p(cur), _p(prev), _p(flow), W, H, f32(time))
 
 
-def spawn_init(PW, PH):
+def spawn_init(PW, PH, cols=None):
     out = np.empty((PW, PH, 4), np.float32)
-    lib().or_spawn_init(PW, PH, 0, PW, _p(out))
+    x0, x1 = cols or (0, PW)
+    lib().or_spawn_init(PW, PH, x0, x1, _p(out))
     return out
 
 
-def spawn_ball(PW, PH, radius=1.0, speed=0.0):
+def spawn_ball(PW, PH, radius=1.0, speed=0.0, cols=None):
     out = np.empty((PW, PH, 4), np.float32)
-    lib().or_spawn_ball(PW, PH, 0, PW, f32(radius), f32(speed), _p(out))
+    x0, x1 = cols or (0, PW)
+    lib().or_spawn_ball(PW, PH, x0, x1, f32(radius), f32(speed), _p(out))
     return out
 
 
-def spawn_pixels_direct(S, PW, PH, image, time):
+def spawn_pixels_direct(S, PW, PH, image, time, cols=None):
     out = np.empty((PW, PH, 4), np.float32)
     IH, IW = image.shape[:2]
-    lib().or_spawn_pixels_direct(C.byref(S), PW, PH, 0, PW, _p(image), IW, IH, f32(time), _p(out))
+    x0, x1 = cols or (0, PW)
+    lib().or_spawn_pixels_direct(C.byref(S), PW, PH, x0, x1, _p(image), IW, IH, f32(time), _p(out))
     return out
 
 
@@ -186,11 +192,12 @@ SAMPLE_VARIANTS = {            # name: (apply, vignette, samples)  -- src/spawn/
 }
 
 
-def spawn_pixels_sample(S, variant, state, image, time):
+def spawn_pixels_sample(S, variant, state, image, time, cols=None):
     PW, PH = state.shape[:2]
     IH, IW = image.shape[:2]
     apply, vig, samples = SAMPLE_VARIANTS[variant]
     out = np.empty((PW, PH, 4), np.float32)
-    lib().or_spawn_pixels_sample(C.byref(S), apply, vig, samples, PW, PH, 0, PW, _p(state),
+    x0, x1 = cols or (0, PW)
+    lib().or_spawn_pixels_sample(C.byref(S), apply, vig, samples, PW, PH, x0, x1, _p(state),
                                  _p(image), IW, IH, f32(time), _p(out))
     return out

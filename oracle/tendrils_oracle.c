@@ -361,6 +361,95 @@ long long or_splat(const or_params *P, int PW, int PH, int x0, int x1,
     return frags;
 }
 
+/* Multi-threaded form of or_splat for the timed CPU baseline.  Same result bit for bit
+ * (tests/test_oracle.py): fragments are generated in draw order, stably counting-sorted by
+ * texel, and each texel's list is folded sequentially. */
+typedef struct { int texel; float cx, cy, a; } o_frag;
+typedef struct { o_frag *out; long long n; int W; } collect_ctx;
+static void emit_collect(void *vctx, int gx, int gy, const float c[4]) {
+    collect_ctx *cc = (collect_ctx *)vctx;
+    if (cc->out) { o_frag f = { gy * cc->W + gx, c[0], c[1], c[3] }; cc->out[cc->n] = f; }
+    cc->n++;
+}
+
+static long long splat_column(const or_params *P, int PH, int x, const int *row, const int *isc, const int *col,
+                              const float *cur, const float *prev, int W, int H, float time, o_frag *out) {
+    collect_ctx cc = { out, 0, W };
+    const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+    for (int k = 0; k < PH; ++k) {
+        const float *sa = (isc[2 * k] ? cur : prev) + 4 * ((size_t)col[x] * PH + row[2 * k]);
+        const float *sb = (isc[2 * k + 1] ? cur : prev) + 4 * ((size_t)col[x] * PH + row[2 * k + 1]);
+        if (sa == sb) continue;
+        if (!(sa[0] != -1000000.0f || sa[1] != -1000000.0f)) continue;
+        if (!(sb[0] != -1000000.0f || sb[1] != -1000000.0f)) continue;
+        if (!finite4(sa) || !finite4(sb)) continue;
+        float ca[4], cb[4];
+        flow_colour(sa[2], sa[3], time, P->speedLimit, ca);
+        flow_colour(sb[2], sb[3], time, P->speedLimit, cb);
+        float xa = (sa[0] * P->viewSize[0]) * hw + hw, ya = (sa[1] * P->viewSize[1]) * hh + hh;
+        float xb = (sb[0] * P->viewSize[0]) * hw + hw, yb = (sb[1] * P->viewSize[1]) * hh + hh;
+        raster_line(xa, ya, xb, yb, ca, cb, W, H, emit_collect, &cc);
+    }
+    return cc.n;
+}
+
+long long or_splat_mt(const or_params *P, int PW, int PH, int x0, int x1,
+                      const float *cur, const float *prev, float *flow, int W, int H, float time) {
+    int *row = (int *)malloc(sizeof(int) * 2 * PH), *isc = (int *)malloc(sizeof(int) * 2 * PH);
+    int *col = (int *)malloc(sizeof(int) * PW);
+    or_vertex_table(PH, row, isc);
+    or_column_table(PW, col);
+    const int ncol = x1 - x0;
+    const size_t G = (size_t)W * H;
+    long long *cstart = (long long *)calloc((size_t)ncol + 1, sizeof(long long));
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int x = x0; x < x1; ++x)
+        cstart[x - x0 + 1] = splat_column(P, PH, x, row, isc, col, cur, prev, W, H, time, NULL);
+    for (int i = 0; i < ncol; ++i) cstart[i + 1] += cstart[i];
+    const long long F = cstart[ncol];
+    o_frag *frags = (o_frag *)malloc(sizeof(o_frag) * (size_t)(F > 0 ? F : 1));
+    o_frag *sorted = (o_frag *)malloc(sizeof(o_frag) * (size_t)(F > 0 ? F : 1));
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int x = x0; x < x1; ++x)
+        splat_column(P, PH, x, row, isc, col, cur, prev, W, H, time, frags + cstart[x - x0]);
+    /* stable parallel counting sort by texel */
+    int T = or_num_threads();
+    if (T > 64) T = 64;
+    long long *hist = (long long *)calloc((size_t)T * G, sizeof(long long));
+    long long *tstart = (long long *)malloc(sizeof(long long) * (G + 1));
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        long long b = F * t / T, e = F * (t + 1) / T;
+        long long *h = hist + (size_t)t * G;
+        for (long long i = b; i < e; ++i) h[frags[i].texel]++;
+    }
+    {
+        long long run = 0;
+        for (size_t g = 0; g < G; ++g) {
+            tstart[g] = run;
+            for (int t = 0; t < T; ++t) { long long c = hist[(size_t)t * G + g]; hist[(size_t)t * G + g] = run; run += c; }
+        }
+        tstart[G] = run;
+    }
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t) {
+        long long b = F * t / T, e = F * (t + 1) / T;
+        long long *h = hist + (size_t)t * G;
+        for (long long i = b; i < e; ++i) sorted[h[frags[i].texel]++] = frags[i];
+    }
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (long long g = 0; g < (long long)G; ++g) {
+        float *dst = flow + 4 * g;
+        for (long long i = tstart[g]; i < tstart[g + 1]; ++i) {
+            float c[4] = { sorted[i].cx, sorted[i].cy, time, sorted[i].a };
+            blend_over(dst, c);
+        }
+    }
+    free(hist); free(tstart); free(frags); free(sorted); free(cstart);
+    free(row); free(isc); free(col);
+    return F;
+}
+
 /* ------------------------------------------------------------------------------------
  * Spawners
  * ---------------------------------------------------------------------------------- */

@@ -77,6 +77,10 @@ void or_column_table(int PW, int *col_of_vertex_col);
 long long or_splat(const or_params *P, int PW, int PH, int x0, int x1,
                    const float *cur, const float *prev, float *flow, int W, int H, float time);
 
+/* same result as or_splat, multi-threaded (used by the timed CPU baseline) */
+long long or_splat_mt(const or_params *P, int PW, int PH, int x0, int x1,
+                      const float *cur, const float *prev, float *flow, int W, int H, float time);
+
 /* a12-a15 spawners; out may alias nothing. columns [x0,x1). */
 void or_spawn_init(int PW, int PH, int x0, int x1, float *out);
 void or_spawn_ball(int PW, int PH, int x0, int x1, float radius, float speed, float *out);

@@ -5,8 +5,10 @@
 // buffers, the logic pass, the flow splat, the spawn passes.  No CPU fallback.
 #include "tb_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -39,11 +41,17 @@ struct tb_ctx {
     // flow splat scratch
     PairEntry *pairs = nullptr;
     int n_pairs = 0;
-    uint32_t *tex_off = nullptr;           // G+1 counters / offsets
+    long long n_prims = 0;                 // local primitives = columns * n_pairs
+    uint32_t *prim_off = nullptr;          // n_prims+1: fragments per primitive -> exclusive offsets, [n_prims] = total
     void *scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
-    Frag *frags = nullptr;
+    uint32_t *keys[2] = {nullptr, nullptr};   // texel of each fragment (draw order / sorted)
+    FragVal *vals[2] = {nullptr, nullptr};
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     uint32_t frag_cap = 0;
+    uint32_t *seg = nullptr;               // 2*G: [begin,end) of every texel's sorted segment
+    int key_bits = 1;
     uint32_t *h_total = nullptr;           // pinned
     cudaEvent_t ev_total = nullptr;
     bool collected = false;
@@ -53,8 +61,10 @@ struct tb_ctx {
     int *h_flag = nullptr;                 // pinned
     bool targets_finite = true;
 
-    cudaEvent_t ev_int[2] = {nullptr, nullptr}, ev_spl[2] = {nullptr, nullptr};
-    bool timed_int = false, timed_spl = false;
+    // CUDA-event timing rings: [class][slot][begin/end]; class 0 = integrate, 1 = flow splat
+    static constexpr int kTimingSlots = 512;
+    cudaEvent_t ev_ring[2][kTimingSlots][2] = {};
+    int64_t ev_count[2] = {0, 0};
 
     tb_state state{};
     bool have_state = false;
@@ -138,30 +148,41 @@ bool columns_are_identity(int PW) {
 int alloc_flow(tb_ctx *c, int w, int h) {
     TB_REQUIRE(c, w >= 1 && h >= 1 && static_cast<long long>(w) * h < (1LL << 31), "flow grid dimensions out of bounds");
     if (c->flow) cudaFree(c->flow);
-    if (c->tex_off) cudaFree(c->tex_off);
-    if (c->scan_tmp) cudaFree(c->scan_tmp);
-    c->flow = nullptr; c->tex_off = nullptr; c->scan_tmp = nullptr;
+    if (c->seg) cudaFree(c->seg);
+    c->flow = nullptr; c->seg = nullptr;
     c->W = w; c->H = h;
     const size_t G = static_cast<size_t>(w) * h;
     TB_CUDA(c, cudaMalloc(&c->flow, G * sizeof(float4)));
-    TB_CUDA(c, cudaMalloc(&c->tex_off, (G + 1) * sizeof(uint32_t)));
-    c->scan_tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, c->scan_tmp_bytes, c->tex_off, c->tex_off, static_cast<int>(G + 1), c->stream);
-    TB_CUDA(c, cudaMalloc(&c->scan_tmp, c->scan_tmp_bytes));
+    TB_CUDA(c, cudaMalloc(&c->seg, 2 * G * sizeof(uint32_t)));
     TB_CUDA(c, cudaMemsetAsync(c->flow, 0, G * sizeof(float4), c->stream));
+    c->key_bits = 1;
+    while ((1ull << c->key_bits) < G) c->key_bits += 1;
     c->collected = false;
     return TB_OK;
 }
 
 int ensure_frag_cap(tb_ctx *c, uint64_t need) {
     if (need <= c->frag_cap) return TB_OK;
-    TB_REQUIRE(c, need < (1ull << 32), "flow splat: more than 2^32 fragments in one draw");
+    TB_REQUIRE(c, need < (1ull << 31), "flow splat: more than 2^31 fragments in one draw");
     uint64_t cap = std::max<uint64_t>(need + need / 4, 1u << 16);
-    if (cap >= (1ull << 32)) cap = (1ull << 32) - 1;
-    if (c->frags) cudaFree(c->frags);
-    c->frags = nullptr;
+    if (cap >= (1ull << 31)) cap = (1ull << 31) - 1;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; ++i) {
+        if (c->keys[i]) cudaFree(c->keys[i]);
+        if (c->vals[i]) cudaFree(c->vals[i]);
+        c->keys[i] = nullptr; c->vals[i] = nullptr;
+    }
+    if (c->sort_tmp) cudaFree(c->sort_tmp);
+    c->sort_tmp = nullptr;
     c->frag_cap = 0;
-    TB_CUDA(c, cudaMalloc(&c->frags, cap * sizeof(Frag)));
+    for (int i = 0; i < 2; ++i) {
+        TB_CUDA(c, cudaMalloc(&c->keys[i], cap * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMalloc(&c->vals[i], cap * sizeof(FragVal)));
+    }
+    c->sort_tmp_bytes = 0;
+    TB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, c->sort_tmp_bytes, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
+                                               static_cast<int64_t>(cap), 0, 32, c->stream));
+    TB_CUDA(c, cudaMalloc(&c->sort_tmp, c->sort_tmp_bytes));
     c->frag_cap = static_cast<uint32_t>(cap);
     return TB_OK;
 }
@@ -181,63 +202,66 @@ SplatArgs splat_args(tb_ctx *c) {
     A.n_pairs = c->n_pairs;
     A.PH = c->PH;
     A.cols = c->col1 - c->col0;
-    A.col0 = c->col0;
     A.W = c->W;
     A.H = c->H;
     A.vsx = c->state.viewSize[0];
     A.vsy = c->state.viewSize[1];
     A.speedLimit = c->state.speedLimit;
-    A.tex_off = c->tex_off;
-    A.frags = c->frags;
+    A.prim_off = c->prim_off;
+    A.keys = c->keys[0];
+    A.vals = c->vals[0];
     A.cap = c->frag_cap;
-    A.total = c->tex_off + static_cast<size_t>(c->W) * c->H;   // slot G holds the total
+    A.total = c->prim_off + c->n_prims;      // slot n_prims holds the total after the scan
     return A;
 }
 
-// count -> scan -> (async total to host) -> emit, re-run with a larger buffer on overflow
+// Rasterise this context's primitives into per-texel fragment segments in draw order:
+//   count per primitive -> exclusive scan -> emit in draw order (no atomics) -> stable radix
+//   sort by texel -> segment bounds.
 int collect(tb_ctx *c, float time) {
     TB_REQUIRE(c, c->have_state, "tb_set_state must be called before the flow splat");
     const size_t G = static_cast<size_t>(c->W) * c->H;
-    const long long threads = static_cast<long long>(c->col1 - c->col0) * c->n_pairs;
+    const long long threads = c->n_prims;
     c->collect_time = time;
     c->collected = false;
-    if (threads == 0) {
-        *c->h_total = 0;
-        TB_CUDA(c, cudaMemsetAsync(c->tex_off, 0, (G + 1) * sizeof(uint32_t), c->stream));
-        c->collected = true;
-        c->last_frags = 0;
-        return TB_OK;
-    }
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        TB_CUDA(c, cudaMemsetAsync(c->tex_off, 0, (G + 1) * sizeof(uint32_t), c->stream));
+    c->last_frags = 0;
+    *c->h_total = 0;
+    if (threads > 0) {
+        TB_CUDA(c, cudaMemsetAsync(c->prim_off, 0, (threads + 1) * sizeof(uint32_t), c->stream));
         SplatArgs A = splat_args(c);
         k_splat_count<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
         if (int r = check_launch(c, "k_splat_count")) return r;
-        // exclusive scan in place over G+1 entries: slot G (zero) receives the total
-        TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp, c->scan_tmp_bytes, c->tex_off, c->tex_off,
-                                                 static_cast<int>(G + 1), c->stream));
-        c->launches += 1;
-        TB_CUDA(c, cudaMemcpyAsync(c->h_total, c->tex_off + G, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp, c->scan_tmp_bytes, c->prim_off, c->prim_off,
+                                                 static_cast<int>(threads + 1), c->stream));
+        c->launches += 2;    // DeviceScanInitKernel + DeviceScanKernel
+        TB_CUDA(c, cudaMemcpyAsync(c->h_total, c->prim_off + threads, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         TB_CUDA(c, cudaEventRecord(c->ev_total, c->stream));
+        TB_CUDA(c, cudaEventSynchronize(c->ev_total));        // the sort needs the count on the host
+        if (int r = ensure_frag_cap(c, *c->h_total)) return r;
+        c->last_frags = *c->h_total;
+    }
+    const uint32_t F = *c->h_total;
+    if (F > 0) {
+        SplatArgs A = splat_args(c);
         k_splat_emit<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
         if (int r = check_launch(c, "k_splat_emit")) return r;
-        TB_CUDA(c, cudaEventSynchronize(c->ev_total));
-        c->last_frags = *c->h_total;
-        if (*c->h_total <= c->frag_cap) {
-            c->collected = true;
-            return TB_OK;
-        }
-        if (int r = ensure_frag_cap(c, *c->h_total)) return r;   // emit/fold skipped themselves on device
+        TB_CUDA(c, cub::DeviceRadixSort::SortPairs(c->sort_tmp, c->sort_tmp_bytes, c->keys[0], c->keys[1], c->vals[0],
+                                                   c->vals[1], static_cast<int64_t>(F), 0, c->key_bits, c->stream));
+        c->launches += 1 + (c->key_bits + 7) / 8;   // histogram + one onesweep pass per 8 key bits (+ scan, not counted)
+        TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * G * sizeof(uint32_t), c->stream));
+        k_splat_bounds<<<blocks_for(F, 256), 256, 0, c->stream>>>(c->keys[1], F, c->seg);
+        if (int r = check_launch(c, "k_splat_bounds")) return r;
     }
-    return fail(c, TB_ERR_OVERFLOW, "flow splat: fragment buffer overflow after regrow");
+    c->collected = true;
+    return TB_OK;
 }
 
 int fold(tb_ctx *c) {
     TB_REQUIRE(c, c->collected, "tb_splat_fold without a preceding tb_splat_collect");
     const int G = c->W * c->H;
     if (c->last_frags > 0) {
-        k_splat_fold<<<blocks_for(G, 128), 128, 0, c->stream>>>(c->flow, c->tex_off, c->frags, G, c->collect_time,
-                                                               c->tex_off + G, c->frag_cap);
+        k_splat_fold<<<blocks_for(G, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(c->flow, reinterpret_cast<const uint2 *>(c->seg),
+                                                               c->vals[1], G, c->collect_time);
         if (int r = check_launch(c, "k_splat_fold")) return r;
     }
     c->collected = false;
@@ -316,10 +340,9 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     TB_TRY(cudaMallocHost(&c->h_flag, sizeof(int)));
     TB_TRY(cudaMallocHost(&c->h_total, sizeof(uint32_t)));
     TB_TRY(cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
-        TB_TRY(cudaEventCreate(&c->ev_int[i]));
-        TB_TRY(cudaEventCreate(&c->ev_spl[i]));
-    }
+    for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
+            for (int j = 0; j < 2; ++j) TB_TRY(cudaEventCreate(&c->ev_ring[k][i][j]));
     const std::vector<PairEntry> pairs = build_pairs(PH);
     c->n_pairs = static_cast<int>(pairs.size());
     if (c->n_pairs) {
@@ -327,10 +350,16 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
         TB_TRY(cudaMemcpyAsync(c->pairs, pairs.data(), pairs.size() * sizeof(PairEntry), cudaMemcpyHostToDevice, c->stream));
         TB_TRY(cudaStreamSynchronize(c->stream));
     }
+    c->n_prims = static_cast<long long>(col1 - col0) * c->n_pairs;
+    if (c->n_prims >= (1LL << 31)) { c->err = "tendrils-b200: too many primitives per context"; return bail(TB_ERR_INVALID); }
+    TB_TRY(cudaMalloc(&c->prim_off, (c->n_prims + 1) * sizeof(uint32_t)));
+    TB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, c->scan_tmp_bytes, c->prim_off, c->prim_off,
+                                         static_cast<int>(c->n_prims + 1), c->stream));
+    TB_TRY(cudaMalloc(&c->scan_tmp, c->scan_tmp_bytes));
 #undef TB_TRY
     const int fw = cfg->flow_w > 0 ? cfg->flow_w : 1, fh = cfg->flow_h > 0 ? cfg->flow_h : 1;
     if (int r = alloc_flow(c, fw, fh)) return bail(r);
-    if (int r = ensure_frag_cap(c, static_cast<uint64_t>(c->n_local) * 2)) return bail(r);
+    if (int r = ensure_frag_cap(c, static_cast<uint64_t>(c->n_prims) * 2)) return bail(r);
     if (int r = tb_reset(c)) return bail(r);
     *out = c;
     return TB_OK;
@@ -341,15 +370,16 @@ int tb_destroy(tb_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
-    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->tex_off);
-    cudaFree(c->scan_tmp); cudaFree(c->frags); cudaFree(c->d_flag);
+    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off);
+    cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->d_flag);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); }
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_total) cudaFreeHost(c->h_total);
     if (c->ev_total) cudaEventDestroy(c->ev_total);
-    for (int i = 0; i < 2; ++i) {
-        if (c->ev_int[i]) cudaEventDestroy(c->ev_int[i]);
-        if (c->ev_spl[i]) cudaEventDestroy(c->ev_spl[i]);
-    }
+    for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
+            for (int j = 0; j < 2; ++j)
+                if (c->ev_ring[k][i][j]) cudaEventDestroy(c->ev_ring[k][i][j]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TB_OK;
@@ -398,11 +428,12 @@ int tb_step(tb_ctx *c, float time, float dt) {
     A.use_noise = !(S.noiseWeight == 0.0f && tame(S.varyNoise, 1e6f) && tame(S.noiseScale, 1e6f) &&
                     tame(S.varyNoiseScale, 1e6f) && tame(S.noiseSpeed, 1e6f) && tame(S.varyNoiseSpeed, 1e6f) &&
                     tame(time, 1e9f) && tame(dt, 1e6f));
-    TB_CUDA(c, cudaEventRecord(c->ev_int[0], c->stream));
+    cudaEvent_t *ev = c->ev_ring[0][c->ev_count[0] % tb_ctx::kTimingSlots];
+    TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
     k_integrate<<<blocks_for(A.n, 256), 256, 0, c->stream>>>(A);
     if (int r = check_launch(c, "k_integrate")) return r;
-    TB_CUDA(c, cudaEventRecord(c->ev_int[1], c->stream));
-    c->timed_int = true;
+    TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    c->ev_count[0] += 1;
     return TB_OK;
 }
 
@@ -421,11 +452,12 @@ int tb_splat_fold(tb_ctx *c) {
 int tb_splat_flow(tb_ctx *c, float time) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
-    TB_CUDA(c, cudaEventRecord(c->ev_spl[0], c->stream));
+    cudaEvent_t *ev = c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots];
+    TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
     if (int r = collect(c, time)) return r;
     if (int r = fold(c)) return r;
-    TB_CUDA(c, cudaEventRecord(c->ev_spl[1], c->stream));
-    c->timed_spl = true;
+    TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    c->ev_count[1] += 1;
     return TB_OK;
 }
 
@@ -610,17 +642,23 @@ int tb_stats(tb_ctx *c, int64_t *kernel_launches, int64_t *last_fragments) {
     return TB_OK;
 }
 
-int tb_last_timing(tb_ctx *c, float *integrate_ms, float *splat_ms) {
+int tb_timing(tb_ctx *c, int reset, int64_t *n_integrate, float *integrate_ms, int64_t *n_splat, float *splat_ms) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (integrate_ms) {
-        *integrate_ms = 0.f;
-        if (c->timed_int) TB_CUDA(c, cudaEventElapsedTime(integrate_ms, c->ev_int[0], c->ev_int[1]));
-    }
-    if (splat_ms) {
-        *splat_ms = 0.f;
-        if (c->timed_spl) TB_CUDA(c, cudaEventElapsedTime(splat_ms, c->ev_spl[0], c->ev_spl[1]));
+    int64_t *n_out[2] = {n_integrate, n_splat};
+    float *ms_out[2] = {integrate_ms, splat_ms};
+    for (int k = 0; k < 2; ++k) {
+        const int64_t n = std::min<int64_t>(c->ev_count[k], tb_ctx::kTimingSlots);
+        double total = 0.0;
+        for (int64_t i = 0; i < n; ++i) {
+            float ms = 0.f;
+            TB_CUDA(c, cudaEventElapsedTime(&ms, c->ev_ring[k][i][0], c->ev_ring[k][i][1]));
+            total += ms;
+        }
+        if (n_out[k]) *n_out[k] = n;
+        if (ms_out[k]) *ms_out[k] = static_cast<float>(total);
+        if (reset) c->ev_count[k] = 0;
     }
     return TB_OK;
 }

@@ -9,10 +9,11 @@ namespace tb {
 
 static constexpr float kInert = -1000000.0f;   // src/const/inert.glsl:1
 
-// One fragment of the flow splat, as stored in the per-texel lists.  The colour's time
-// channel is the uniform `time` at both vertices, hence constant along the line.
-struct __align__(16) Frag {
-    uint32_t prim;    // primitive (draw) order x*PH + k  (src/particles.js:182-186)
+// One fragment of the flow splat: the interpolated colour's (vel.xy, alpha).  The colour's time
+// channel is the uniform `time` at both vertices, hence constant along the line.  Fragments
+// are generated in primitive (draw) order p = x*PH + k (src/particles.js:182-186) and stably
+// sorted by texel, so the order within a texel's segment is the draw order.
+struct FragVal {
     float cx, cy;     // interpolated vel.xy
     float a;          // interpolated alpha
 };
@@ -113,12 +114,12 @@ struct SplatArgs {
     int n_pairs;           // active (non-degenerate) pairs per column
     int PH;
     int cols;              // local columns
-    int col0;              // first global column
     int W, H;
     float vsx, vsy, speedLimit;
-    uint32_t *tex_off;     // count pass: per-texel counters; emit pass: running offsets
-    Frag *frags;
-    uint32_t cap;          // capacity of frags
+    uint32_t *prim_off;    // count pass: fragments per primitive; after the scan: first slot
+    uint32_t *keys;        // texel index of every fragment, in draw order
+    FragVal *vals;
+    uint32_t cap;          // capacity of keys/vals
     const uint32_t *total; // device: total fragments of this collect (after the scan)
 };
 
@@ -151,6 +152,7 @@ __device__ __forceinline__ void raster_line(float xa, float ya, float xb, float 
 }
 
 // Loads the two vertices of pair (column, entry) and hands window coordinates + colours on.
+// Threads are numbered in draw order: tid = local column * n_pairs + index of the active pair.
 template <class Body>
 __device__ __forceinline__ void splat_pair(const SplatArgs &A, Body &&body) {
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -170,72 +172,114 @@ __device__ __forceinline__ void splat_pair(const SplatArgs &A, Body &&body) {
     const float ya = __fadd_rn(__fmul_rn(__fmul_rn(sa.y, A.vsy), hh), hh);
     const float xb = __fadd_rn(__fmul_rn(__fmul_rn(sb.x, A.vsx), hw), hw);
     const float yb = __fadd_rn(__fmul_rn(__fmul_rn(sb.y, A.vsy), hh), hh);
-    const uint32_t prim = static_cast<uint32_t>(A.col0 + xl) * static_cast<uint32_t>(A.PH) + static_cast<uint32_t>(pe.k);
-    body(prim, xa, ya, xb, yb, sa, sb);
+    body(tid, xa, ya, xb, yb, sa, sb);
 }
 
+// Pass 1: fragments per primitive (culled primitives count 0; prim_off is zeroed beforehand).
 __global__ void __launch_bounds__(256) k_splat_count(const SplatArgs A) {
-    splat_pair(A, [&](uint32_t, float xa, float ya, float xb, float yb, const float4 &, const float4 &) {
-        raster_line(xa, ya, xb, yb, A.W, A.H, [&](int gx, int gy, float) {
-            atomicAdd(A.tex_off + (static_cast<size_t>(gy) * A.W + gx), 1u);
-        });
+    splat_pair(A, [&](long long tid, float xa, float ya, float xb, float yb, const float4 &, const float4 &) {
+        uint32_t n = 0;
+        raster_line(xa, ya, xb, yb, A.W, A.H, [&](int, int, float) { ++n; });
+        A.prim_off[tid] = n;
     });
 }
 
+// Pass 2 (after the exclusive scan of prim_off): write (texel, colour) of every fragment at its
+// slot.  No atomics: the slot order IS the draw order.
 __global__ void __launch_bounds__(256) k_splat_emit(const SplatArgs A) {
     if (*A.total > A.cap) return;            // host re-runs the collect with a larger buffer
-    splat_pair(A, [&](uint32_t prim, float xa, float ya, float xb, float yb, const float4 &sa, const float4 &sb) {
+    splat_pair(A, [&](long long tid, float xa, float ya, float xb, float yb, const float4 &sa, const float4 &sb) {
         // flow(vel, speedLimit): src/flow/apply/state.glsl:5-16
         const float aa = gmin(__fdiv_rn(glength(sa.z, sa.w), A.speedLimit), 1.0f);
         const float ab = gmin(__fdiv_rn(glength(sb.z, sb.w), A.speedLimit), 1.0f);
+        uint32_t slot = A.prim_off[tid];
         raster_line(xa, ya, xb, yb, A.W, A.H, [&](int gx, int gy, float t) {
-            Frag f;
-            f.prim = prim;
+            FragVal f;
             f.cx = __fadd_rn(sa.z, __fmul_rn(t, __fsub_rn(sb.z, sa.z)));
             f.cy = __fadd_rn(sa.w, __fmul_rn(t, __fsub_rn(sb.w, sa.w)));
             f.a = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
-            const uint32_t slot = atomicAdd(A.tex_off + (static_cast<size_t>(gy) * A.W + gx), 1u);
-            *reinterpret_cast<uint4 *>(A.frags + slot) = *reinterpret_cast<const uint4 *>(&f);
+            A.keys[slot] = static_cast<uint32_t>(gy) * static_cast<uint32_t>(A.W) + static_cast<uint32_t>(gx);
+            A.vals[slot] = f;
+            ++slot;
         });
     });
 }
 
-// Ordered alpha-over fold of one texel's fragment list: blendFunc(SRC_ALPHA,
-// ONE_MINUS_SRC_ALPHA) on all four channels, in primitive order (src/index.js:267-268).
-// ends[t] is the running offset left by the emit pass = end of texel t's list.
-__global__ void __launch_bounds__(128) k_splat_fold(float4 *__restrict__ flow, const uint32_t *__restrict__ ends,
-                                                     Frag *__restrict__ frags, int G, float time,
-                                                     const uint32_t *total, uint32_t cap) {
-    if (*total > cap) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= G) return;
-    const uint32_t begin = t ? ends[t - 1] : 0u, end = ends[t];
-    const uint32_t n = end - begin;
-    if (n == 0) return;
-    uint4 *r = reinterpret_cast<uint4 *>(frags + begin);
-    // lists arrive almost sorted (CTAs run in primitive order): insertion sort by prim
-    for (uint32_t i = 1; i < n; ++i) {
-        const uint4 v = r[i];
-        uint32_t j = i;
-        while (j > 0) {
-            const uint4 u = r[j - 1];
-            if (u.x <= v.x) break;
-            r[j] = u;
-            --j;
+// Pass 4 (after the stable radix sort by texel): segment bounds of every texel that has fragments.
+// seg[2t], seg[2t+1] = [begin, end) of texel t; zero-filled beforehand (empty).
+__global__ void __launch_bounds__(256) k_splat_bounds(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ seg) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    if (i == 0 || keys[i - 1] != k) seg[2 * k] = i;
+    if (i == n - 1 || keys[i + 1] != k) seg[2 * k + 1] = i + 1;
+}
+
+// Pass 5: ordered alpha-over fold: blendFunc(SRC_ALPHA, ONE_MINUS_SRC_ALPHA) on all four
+// channels, in primitive order (src/index.js:267-268):  dst = src*a + dst*(1-a).
+//
+// One warp owns 32 consecutive texels, whose sorted segments are one contiguous range of the
+// fragment array.  The warp streams that range through shared memory in chunks: all lanes load
+// fragments coalesced and pre-multiply the order-independent part (src*a per channel, 1-a); then
+// each lane folds the part of ITS texel's segment that lies in the chunk, reading shared memory.
+// The only serial work left is the two dependent roundings per fragment the blend demands, so a
+// texel that holds a whole chunk (a hot spot) runs at the latency of that chain, not of DRAM.
+constexpr int kFoldChunk = 256;           // fragments per warp per pass through shared memory
+constexpr int kFoldWarps = 4;             // warps per CTA
+
+struct __align__(16) FoldTerm { float tx, ty, tz, tw; };   // src*a for the four channels
+
+__global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restrict__ flow, const uint2 *__restrict__ seg,
+                                                                 const FragVal *__restrict__ vals, int G, float time) {
+    __shared__ FoldTerm s_term[kFoldWarps][kFoldChunk];
+    __shared__ float s_om[kFoldWarps][kFoldChunk];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * kFoldWarps + warp) * 32 + lane;
+    uint2 se = make_uint2(0u, 0u);
+    if (t < G) se = seg[t];
+    const bool has = se.y > se.x;
+    // the warp's fragment range: segments are stored in texel order, so it is [first begin, last end)
+    uint32_t lo = has ? se.x : 0xffffffffu, hi = has ? se.y : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (hi <= lo) return;                               // no fragments in these 32 texels
+    float4 d = has ? flow[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    FoldTerm *term = s_term[warp];
+    float *om = s_om[warp];
+    for (uint32_t c0 = lo; c0 < hi; c0 += kFoldChunk) {
+        const uint32_t c1 = min(c0 + static_cast<uint32_t>(kFoldChunk), hi);
+#pragma unroll
+        for (int j = 0; j < kFoldChunk / 32; ++j) {
+            const uint32_t i = c0 + j * 32 + lane;
+            if (i < c1) {
+                const float cx = __ldcs(&vals[i].cx), cy = __ldcs(&vals[i].cy), a = __ldcs(&vals[i].a);
+                FoldTerm tm;
+                tm.tx = __fmul_rn(cx, a);
+                tm.ty = __fmul_rn(cy, a);
+                tm.tz = __fmul_rn(time, a);
+                tm.tw = __fmul_rn(a, a);
+                term[j * 32 + lane] = tm;
+                om[j * 32 + lane] = __fsub_rn(1.0f, a);
+            }
         }
-        if (j != i) r[j] = v;
+        __syncwarp();
+        if (has) {
+            const uint32_t b = max(se.x, c0), e = min(se.y, c1);
+            for (uint32_t i = b; i < e; ++i) {
+                const FoldTerm tm = term[i - c0];
+                const float m = om[i - c0];
+                d.x = __fadd_rn(tm.tx, __fmul_rn(d.x, m));
+                d.y = __fadd_rn(tm.ty, __fmul_rn(d.y, m));
+                d.z = __fadd_rn(tm.tz, __fmul_rn(d.z, m));
+                d.w = __fadd_rn(tm.tw, __fmul_rn(d.w, m));
+            }
+        }
+        __syncwarp();
     }
-    float4 d = flow[t];
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint4 v = r[i];
-        const float cx = __uint_as_float(v.y), cy = __uint_as_float(v.z), a = __uint_as_float(v.w);
-        const float om = __fsub_rn(1.0f, a);
-        d.x = __fadd_rn(__fmul_rn(cx, a), __fmul_rn(d.x, om));
-        d.y = __fadd_rn(__fmul_rn(cy, a), __fmul_rn(d.y, om));
-        d.z = __fadd_rn(__fmul_rn(time, a), __fmul_rn(d.z, om));
-        d.w = __fadd_rn(__fmul_rn(a, a), __fmul_rn(d.w, om));
-    }
-    flow[t] = d;
+    if (has) flow[t] = d;
 }
 
 // Full-grid alpha-over of an RGBA layer (L4 inputs drawn into the flow FBO).

@@ -269,10 +269,11 @@ class Particles:
         N.check(self._ctx, self._L.tb_stats(self._ctx, C.byref(a), C.byref(b)))
         return {"kernel_launches": a.value, "last_fragments": b.value}
 
-    def last_timing(self):
-        a, b = C.c_float(), C.c_float()
-        N.check(self._ctx, self._L.tb_last_timing(self._ctx, C.byref(a), C.byref(b)))
-        return {"integrate_ms": a.value, "splat_ms": b.value}
+    def timing(self, reset=False):
+        """Summed CUDA-event time of the integrate launches and the flow splats since the last reset."""
+        ni, ns, mi, ms = C.c_int64(), C.c_int64(), C.c_float(), C.c_float()
+        N.check(self._ctx, self._L.tb_timing(self._ctx, int(reset), C.byref(ni), C.byref(mi), C.byref(ns), C.byref(ms)))
+        return {"n_integrate": ni.value, "integrate_ms": mi.value, "n_splat": ns.value, "splat_ms": ms.value}
 
     def dispose(self):                                                  # src/particles.js:168-169 (@todo there)
         if getattr(self, "_ctx", None):

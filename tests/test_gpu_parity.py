@@ -76,3 +76,206 @@ def test_ball_then_steps_bit_exact(T, oracle, R, G):
         assert_bits_equal(t.flow.download(), sim.flow, f"flow after step {k}")
     assert_bits_equal(t.particles.buffers[1].download(), sim.prev, "previous state")
     assert np.isfinite(sim.cur).all() and (sim.flow != 0).any()
+
+
+# ---------------------------------------------------------------------------------------------
+# spawners
+# ---------------------------------------------------------------------------------------------
+def _spawner_uniforms(G):
+    # jitter = aspect(Float32Array(2), viewRes, jitterRad) (src/spawn/pixels/index.js:55)
+    j = np.float32(np.float32(1.0 / G) * 2.0)
+    return j
+
+
+@pytest.mark.parametrize("variant", ["direct", "best", "bright", "color", "data", "flow"])
+def test_pixel_spawners_bit_exact(T, oracle, variant):
+    from tendrils_b200.spawn import PixelSpawner, spawnBall
+    from tendrils_b200.spawn import pixels as PX
+    R, G = 48, 40
+    t = make(T, R, G)
+    O = oracle
+    P = oracle_params(O, t)
+    sim = OracleSim(O, R, G, G, P)
+    # some history first so that `particles` and the flow grid are non-trivial
+    spawnBall(t.gl, {"uniforms": {"radius": 0.6, "speed": 0.004}}).spawn(t)
+    sim.spawn_ball(0.6, 0.004)
+    for _ in range(4):
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); sim.draw(np.float32(t.timer.time))
+    img = synthetic_image(37, 29)
+    frag = {"direct": PX.pixelsFrag, "best": PX.bestSampleFrag, "bright": PX.brightSampleFrag,
+            "color": PX.colorSampleFrag, "data": PX.dataSampleFrag, "flow": PX.flowSampleFrag}[variant]
+    buf = img
+    if variant == "flow":
+        buf = t.flow
+    if variant == "data":
+        buf = t.particles.buffers[0]
+    sp = PixelSpawner(t.gl, {"shader": frag, "buffer": buf, "speed": 0.7, "bias": 0.9, "jitterRad": 2,
+                             "spawnSize": [0.9, 1.1]})
+    sp.spawnMatrix = PX.mat3_scale(PX.mat3_identity(), [-1, 1])
+    sp.spawn(t)
+    time = np.float32(t.timer.time)
+    j = _spawner_uniforms(G)
+    S = O.make_spawn_pixels(spawnSize=(0.9, 1.1), jitter=(j, j), speed=0.7, bias=0.9,
+                            spawnMatrix=(-1, 0, 0, 0, 1, 0, 0, 0, 1), flowDecay=t.state["flowDecay"])
+    if variant == "flow":
+        src = sim.flow
+    elif variant == "data":
+        src = np.ascontiguousarray(sim.cur.transpose(1, 0, 2))    # texture (x across, y rows) = [row y][col x]
+    else:
+        src = img
+    if variant == "direct":
+        want = O.spawn_pixels_direct(S, R, R, src, time)
+    else:
+        want = O.spawn_pixels_sample(S, variant, sim.cur, src, time)
+    assert_bits_equal(t.particles.buffers[0].download(), want, f"{variant} spawn")
+    assert_bits_equal(t.particles.buffers[1].download(), sim.cur, "previous state after spawn")
+
+
+def test_spawn_into_targets_and_target_pull(T, oracle):
+    """spawnImageTargets (src/demo.main.js:517-521): the direct spawn written into tendrils.targets with
+    no ping-pong rotation, then steps with target != 0."""
+    from tendrils_b200.spawn import PixelSpawner, spawnBall
+    from tendrils_b200.spawn import pixels as PX
+    R, G = 40, 32
+    t = make(T, R, G, state={"target": 0.003, "varyTarget": 2.0})
+    O = oracle
+    sim = OracleSim(O, R, G, G, oracle_params(O, t))
+    spawnBall(t.gl, {"uniforms": {"radius": 0.5, "speed": 0.002}}).spawn(t)
+    sim.spawn_ball(0.5, 0.002)
+    img = synthetic_image(64, 64)
+    sp = PixelSpawner(t.gl, {"shader": PX.pixelsFrag, "buffer": img, "speed": 0.3})
+    sp.spawn(t, None, t.targets)
+    j = _spawner_uniforms(G)
+    S = O.make_spawn_pixels(jitter=(j, j), speed=0.3)
+    sim.targets = O.spawn_pixels_direct(S, R, R, img, np.float32(t.timer.time))
+    assert_bits_equal(t.targets.download(), sim.targets, "targets")
+    assert_bits_equal(t.particles.buffers[0].download(), sim.cur, "state untouched by a targets spawn")
+    for k in range(6):
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); sim.draw(np.float32(t.timer.time))
+        assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state {k}")
+        assert_bits_equal(t.flow.download(), sim.flow, f"flow {k}")
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the reference: inert texels, NaN (0/0 in the speed clamp), out of bounds,
+# non-square view, odd sizes, custom CPU spawn upload
+# ---------------------------------------------------------------------------------------------
+def test_edge_states_bit_exact(T, oracle):
+    R, W, H = 34, 48, 20
+    t = make(T, R, 0, view=(W, H), state={"noiseScale": 40.0, "varyNoiseScale": -50.0, "flowWeight": -0.4,
+                                          "speedLimit": 0.08, "flowDecay": 0.0005})
+    O = oracle
+    rng = np.random.default_rng(5)
+    st = np.zeros((R, R, 4), np.float32)
+    st[..., 0:2] = rng.uniform(-1.3, 1.3, (R, R, 2))
+    st[..., 2:4] = rng.normal(0, 0.03, (R, R, 2))
+    st[0, :, 0:2] = T.INERT                      # a column of inert texels: pass through unchanged
+    st[0, :, 2:4] = 0
+    st[1, 0:4] = (0.25, -0.5, 0.0, 0.0)          # at rest, zero force possible -> 0/0 = NaN (Q2)
+    st[2, 0] = (np.nan, 0.1, 0.0, 0.01)
+    st[2, 1] = (0.1, 0.1, np.inf, 0.0)
+    st[2, 2] = (5.0e7, -3.0e9, 0.01, 0.0)        # far out of bounds; beyond the noise fast-path guard
+    st[3, :, 0] = 0.999999                       # hugging the right edge
+    st[4, :, 1] = -1.0
+
+    def fill(data, x, y):
+        data[:] = st[x, y]
+    t.spawn(fill)
+    assert t.viewSize[0] == pytest.approx(1.0) and t.viewSize[1] == pytest.approx(W / H)
+    sim = OracleSim(O, R, W, H, oracle_params(O, t))
+    sim.cur, sim.prev = st.copy(), st.copy()
+    assert_bits_equal(t.particles.buffers[0].download(), st, "cpu spawn upload")
+    assert_bits_equal(t.particles.buffers[1].download(), st, "cpu spawn upload (all buffers)")
+    for k in range(12):
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); n = sim.draw(np.float32(t.timer.time))
+        assert t.particles.stats()["last_fragments"] == n
+        assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state {k}")
+        assert_bits_equal(t.flow.download(), sim.flow, f"flow {k}")
+    assert np.isnan(sim.cur[2, 0]).any() and (sim.cur[0, :, 0] == T.INERT).all()
+
+
+@pytest.mark.parametrize("weights", [dict(noiseWeight=0.0), dict(noiseWeight=0.0, flowWeight=0.0),
+                                     dict(forceWeight=0.0), dict(damping=0.0)])
+def test_fast_paths_are_exact(T, oracle, weights):
+    """noiseWeight == 0 lets the kernel skip the simplex noise; the result must not change."""
+    from tendrils_b200.spawn import spawnBall
+    R, G = 64, 64
+    t = make(T, R, G, state=weights)
+    sim = OracleSim(oracle, R, G, G, oracle_params(oracle, t))
+    spawnBall(t.gl, {"uniforms": {"radius": 0.8, "speed": 0.006}}).spawn(t)
+    sim.spawn_ball(0.8, 0.006)
+    for k in range(8):
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); sim.draw(np.float32(t.timer.time))
+        assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state {k}")
+        assert_bits_equal(t.flow.download(), sim.flow, f"flow {k}")
+
+
+def test_hot_texel_and_long_lines(T, oracle):
+    """Maximum contention (every particle in one texel) and lines crossing the whole grid."""
+    R, G = 64, 24
+    t = make(T, R, G, state={"speedLimit": 3.0})
+    O = oracle
+    rng = np.random.default_rng(11)
+    cur = np.zeros((R, R, 4), np.float32)
+    cur[..., 0:2] = 0.3 + rng.uniform(0, 0.01, (R, R, 2))
+    cur[..., 2:4] = rng.normal(0, 0.004, (R, R, 2))
+    prev = cur.copy()
+    prev[..., 0:2] -= cur[..., 2:4]
+    prev[: R // 2, :, 0:2] = rng.uniform(-2.5, 2.5, (R // 2, R, 2))      # long lines, partly off-grid
+    t.particles.buffers[0].upload(cur)
+    t.particles.buffers[1].upload(prev)
+    flow0 = rng.normal(0, 0.01, (G, G, 4)).astype(np.float32)
+    t.flow.upload(flow0)
+    sim = OracleSim(O, R, G, G, oracle_params(O, t))
+    sim.cur, sim.prev, sim.flow = cur.copy(), prev.copy(), flow0.copy()
+    t.timer.tick()
+    t.draw()
+    n = sim.draw(np.float32(t.timer.time))
+    assert t.particles.stats()["last_fragments"] == n and n > 5000
+    assert_bits_equal(t.flow.download(), sim.flow, "flow after a contended draw")
+
+
+def test_sharded_contexts_equal_single(T, oracle):
+    """Two column-sharded contexts folded in rank order onto one grid == one context (bit for bit)."""
+    import ctypes as C
+    from tendrils_b200 import _native as N
+    from tendrils_b200.spawn import spawnBall
+    R, G = 64, 48
+    ts = [T.Tendrils(T.Device(G, G, rank=r, world_size=2)) for r in range(2)]
+    for t in ts:
+        t.setup(R); t.resize()
+        assert (t.particles.col0, t.particles.col1) == ((0, 32), (32, 64))[t.gl.rank]
+    one = make(T, R, G)
+    sim = OracleSim(oracle, R, G, G, oracle_params(oracle, one))
+    for t in ts + [one]:
+        t.particles_world = 1
+    L = N.load()
+    ball = dict(uniforms={"radius": 0.4, "speed": 0.005})
+    # spawn + step are purely local; run them through the public API with world_size forced to the ring-free path
+    for t in ts + [one]:
+        spawnBall(t.gl, ball).spawn(t)
+    sim.spawn_ball(0.4, 0.005)
+    for k in range(6):
+        for t in ts + [one]:
+            t.timer.tick(); t.step()
+        one.draw()
+        flow = None
+        for r, t in enumerate(ts):                      # the ordered ring, by hand, on one GPU
+            ctx = t.particles._ctx
+            st = T.tendrils._state_struct({**t.state, "viewSize": t.viewSize})
+            N.check(ctx, L.tb_set_state(ctx, C.byref(st)))
+            N.check(ctx, L.tb_splat_collect(ctx, float(t.timer.time)))
+            if flow is not None:
+                t.flow.upload(flow)
+            N.check(ctx, L.tb_splat_fold(ctx))
+            flow = t.flow.download()
+        ts[0].flow.upload(flow)                         # the "broadcast"
+        sim.step(np.float32(one.timer.time), np.float32(one.timer.dt)); sim.draw(np.float32(one.timer.time))
+        assert_bits_equal(one.flow.download(), sim.flow, f"single flow {k}")
+        assert_bits_equal(flow, sim.flow, f"sharded flow {k}")
+        got = np.concatenate([t.particles.buffers[0].download() for t in ts], 0)
+        assert_bits_equal(got, sim.cur, f"sharded state {k}")
