@@ -162,6 +162,10 @@ int tb_download(tb_ctx *ctx, tb_buffer which, float *host, int64_t n_floats);
  * inputs that draw into the flow FBO: optical flow, pointer flow-lines; src/demo.main.js:1107-1159). */
 int tb_blend_into_flow(tb_ctx *ctx, const float *rgba, int32_t w, int32_t h);
 
+/* diagnostic tap: [fold begin, end) of every texel's fragment segment left by the last splat
+ * (2*W*H words); used by tools/ to study fragment-list length distributions. */
+int tb_debug_segments(tb_ctx *ctx, uint32_t *host, int64_t n_words);
+
 /* plumbing for the host layer (PyTorch / NCCL): raw device pointers, stream, sync, timing */
 int tb_device_ptr(tb_ctx *ctx, tb_buffer which, void **ptr, int64_t *n_floats);
 int tb_stream(tb_ctx *ctx, void **cuda_stream);

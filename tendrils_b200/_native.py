@@ -57,6 +57,7 @@ SYMBOLS = {
     "tb_upload": (C.c_int, [_ctx, C.c_int, _fp, C.c_int64]),
     "tb_download": (C.c_int, [_ctx, C.c_int, _fp, C.c_int64]),
     "tb_blend_into_flow": (C.c_int, [_ctx, _fp, C.c_int32, C.c_int32]),
+    "tb_debug_segments": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_int64]),
     "tb_device_ptr": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "tb_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "tb_sync": (C.c_int, [_ctx]),

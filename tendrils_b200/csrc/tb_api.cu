@@ -51,6 +51,8 @@ struct tb_ctx {
     size_t sort_tmp_bytes = 0;
     uint32_t frag_cap = 0;
     uint32_t *seg = nullptr;               // 2*G: [begin,end) of every texel's sorted segment
+    uint32_t *hot = nullptr;               // [0] = count, [1..G] = worklist of hot texels
+    int n_sms = 148;
     int key_bits = 1;
     uint32_t *h_total = nullptr;           // pinned
     cudaEvent_t ev_total = nullptr;
@@ -149,11 +151,13 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     TB_REQUIRE(c, w >= 1 && h >= 1 && static_cast<long long>(w) * h < (1LL << 31), "flow grid dimensions out of bounds");
     if (c->flow) cudaFree(c->flow);
     if (c->seg) cudaFree(c->seg);
-    c->flow = nullptr; c->seg = nullptr;
+    if (c->hot) cudaFree(c->hot);
+    c->flow = nullptr; c->seg = nullptr; c->hot = nullptr;
     c->W = w; c->H = h;
     const size_t G = static_cast<size_t>(w) * h;
     TB_CUDA(c, cudaMalloc(&c->flow, G * sizeof(float4)));
     TB_CUDA(c, cudaMalloc(&c->seg, 2 * G * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->hot, (G + 1) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMemsetAsync(c->flow, 0, G * sizeof(float4), c->stream));
     c->key_bits = 1;
     while ((1ull << c->key_bits) < G) c->key_bits += 1;
@@ -260,9 +264,13 @@ int fold(tb_ctx *c) {
     TB_REQUIRE(c, c->collected, "tb_splat_fold without a preceding tb_splat_collect");
     const int G = c->W * c->H;
     if (c->last_frags > 0) {
-        k_splat_fold<<<blocks_for(G, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(c->flow, reinterpret_cast<const uint2 *>(c->seg),
-                                                               c->vals[1], G, c->collect_time);
+        TB_CUDA(c, cudaMemsetAsync(c->hot, 0, sizeof(uint32_t), c->stream));
+        k_splat_fold<<<blocks_for(G, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
+            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], G, c->collect_time, c->hot, c->hot + 1);
         if (int r = check_launch(c, "k_splat_fold")) return r;
+        k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
+            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 1);
+        if (int r = check_launch(c, "k_splat_fold_hot")) return r;
     }
     c->collected = false;
     return TB_OK;
@@ -329,6 +337,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     };
 #define TB_TRY(expr) do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) { c->err = std::string(#expr) + ": " + cudaGetErrorString(e2_); return bail(TB_ERR_CUDA); } } while (0)
     TB_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));
     TB_TRY(cudaMalloc(&c->buf[1], bytes));
@@ -371,7 +380,7 @@ int tb_destroy(tb_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
     cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off);
-    cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->d_flag);
+    cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->hot); cudaFree(c->d_flag);
     for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); }
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_total) cudaFreeHost(c->h_total);
@@ -610,6 +619,15 @@ int tb_blend_into_flow(tb_ctx *c, const float *rgba, int32_t w, int32_t h) {
     TB_CUDA(c, cudaMemcpyAsync(c->layer, rgba, G * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     k_blend_layer<<<blocks_for(static_cast<long long>(G), 256), 256, 0, c->stream>>>(c->flow, c->layer, static_cast<int>(G));
     if (int r = check_launch(c, "k_blend_layer")) return r;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+int tb_debug_segments(tb_ctx *c, uint32_t *host, int64_t n_words) {
+    TB_REQUIRE(c, c && host, "null argument");
+    TB_REQUIRE(c, n_words == 2LL * c->W * c->H, "tb_debug_segments: size mismatch");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaMemcpyAsync(host, c->seg, static_cast<size_t>(n_words) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
 }

@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(256) k_integrate(const IntegrateArgs A) {
 // Flow splat (a7-a10).  RASTER-1 (spec/PARITY.md): GL_LINES of width 1, centre-sampled along
 // the major axis, half-open towards the second vertex, scissored to the grid.
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t kOpaqueBit = 0x80000000u;
+
 struct SplatArgs {
     const float4 *__restrict__ cur;
     const float4 *__restrict__ prev;
@@ -198,21 +200,30 @@ __global__ void __launch_bounds__(256) k_splat_emit(const SplatArgs A) {
             f.cx = __fadd_rn(sa.z, __fmul_rn(t, __fsub_rn(sb.z, sa.z)));
             f.cy = __fadd_rn(sa.w, __fmul_rn(t, __fsub_rn(sb.w, sa.w)));
             f.a = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
-            A.keys[slot] = static_cast<uint32_t>(gy) * static_cast<uint32_t>(A.W) + static_cast<uint32_t>(gx);
+            // bit 31 flags a fragment whose alpha is exactly 1; it rides along the sort (which only
+            // looks at the texel bits) and lets the fold skip everything such a fragment overwrites
+            A.keys[slot] = (static_cast<uint32_t>(gy) * static_cast<uint32_t>(A.W) + static_cast<uint32_t>(gx)) |
+                           (f.a == 1.0f ? kOpaqueBit : 0u);
             A.vals[slot] = f;
             ++slot;
         });
     });
 }
 
-// Pass 4 (after the stable radix sort by texel): segment bounds of every texel that has fragments.
-// seg[2t], seg[2t+1] = [begin, end) of texel t; zero-filled beforehand (empty).
+// Pass 4 (after the stable radix sort by texel): for every texel that has fragments,
+// seg[2t+1] = end of its segment and seg[2t] = where its fold starts: the segment's first
+// fragment, or the LAST fragment with alpha == 1 if there is one.  Such a fragment makes all
+// earlier ones irrelevant: dst = c*1 + dst*0 = c + (+-0) for every finite dst, and NaN for a
+// non-finite dst whether or not the earlier fragments were applied (Inf and NaN never become
+// finite under this blend) -- so folding from it onto the ORIGINAL texel is exact.
+// seg is zero-filled beforehand (empty segments stay [0,0)).
 __global__ void __launch_bounds__(256) k_splat_bounds(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ seg) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t k = keys[i];
-    if (i == 0 || keys[i - 1] != k) seg[2 * k] = i;
-    if (i == n - 1 || keys[i + 1] != k) seg[2 * k + 1] = i + 1;
+    const uint32_t raw = keys[i], k = raw & ~kOpaqueBit;
+    const bool first = (i == 0) || ((keys[i - 1] & ~kOpaqueBit) != k);
+    if (first || (raw & kOpaqueBit)) atomicMax(&seg[2 * k], i);
+    if (i == n - 1 || (keys[i + 1] & ~kOpaqueBit) != k) seg[2 * k + 1] = i + 1;
 }
 
 // Pass 5: ordered alpha-over fold: blendFunc(SRC_ALPHA, ONE_MINUS_SRC_ALPHA) on all four
@@ -224,62 +235,154 @@ __global__ void __launch_bounds__(256) k_splat_bounds(const uint32_t *__restrict
 // each lane folds the part of ITS texel's segment that lies in the chunk, reading shared memory.
 // The only serial work left is the two dependent roundings per fragment the blend demands, so a
 // texel that holds a whole chunk (a hot spot) runs at the latency of that chain, not of DRAM.
+// Texels whose segment is longer than kFoldHot fragments ("hot": dense filaments, the centre of
+// a ball spawn) would make their whole warp wait; the lane-per-texel kernel hands them to
+// k_splat_fold_hot through a worklist, where a full warp streams ONE texel's segment.
 constexpr int kFoldChunk = 256;           // fragments per warp per pass through shared memory
 constexpr int kFoldWarps = 4;             // warps per CTA
+constexpr int kFoldPer = kFoldChunk / 32; // fragments per lane per chunk
+constexpr uint32_t kFoldHot = 192;        // segment length above which a texel is "hot"
 
 struct __align__(16) FoldTerm { float tx, ty, tz, tw; };   // src*a for the four channels
 
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// the serial half of the blend for fragments [i, e) of a chunk held in shared memory
+__device__ __forceinline__ void fold_terms(float4 &d, const FoldTerm *term, const float *om, uint32_t i, uint32_t e) {
+    // software-pipelined by 8: the shared-memory reads do not depend on d, so only the multiply-add
+    // chain (two dependent roundings per fragment and channel) is serial
+    for (; i + 8 <= e; i += 8) {
+        FoldTerm tm[8];
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { tm[j] = term[i + j]; m[j] = om[i + j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            d.x = __fadd_rn(tm[j].tx, __fmul_rn(d.x, m[j]));
+            d.y = __fadd_rn(tm[j].ty, __fmul_rn(d.y, m[j]));
+            d.z = __fadd_rn(tm[j].tz, __fmul_rn(d.z, m[j]));
+            d.w = __fadd_rn(tm[j].tw, __fmul_rn(d.w, m[j]));
+        }
+    }
+    for (; i < e; ++i) {
+        const FoldTerm t1 = term[i];
+        const float m1 = om[i];
+        d.x = __fadd_rn(t1.tx, __fmul_rn(d.x, m1));
+        d.y = __fadd_rn(t1.ty, __fmul_rn(d.y, m1));
+        d.z = __fadd_rn(t1.tz, __fmul_rn(d.z, m1));
+        d.w = __fadd_rn(t1.tw, __fmul_rn(d.w, m1));
+    }
+}
+
+// the order-independent half, all lanes in parallel: src*a per channel and 1-a, into shared memory
+__device__ __forceinline__ void stage_terms(FoldTerm *term, float *om, const float (&rcx)[kFoldPer], const float (&rcy)[kFoldPer],
+                                            const float (&ra)[kFoldPer], uint32_t c0, uint32_t c1, int lane, float time) {
+#pragma unroll
+    for (int j = 0; j < kFoldPer; ++j) {
+        if (c0 + j * 32 + lane < c1) {
+            FoldTerm tm;
+            tm.tx = __fmul_rn(rcx[j], ra[j]);
+            tm.ty = __fmul_rn(rcy[j], ra[j]);
+            tm.tz = __fmul_rn(time, ra[j]);
+            tm.tw = __fmul_rn(ra[j], ra[j]);
+            term[j * 32 + lane] = tm;
+            om[j * 32 + lane] = __fsub_rn(1.0f, ra[j]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restrict__ flow, const uint2 *__restrict__ seg,
-                                                                 const FragVal *__restrict__ vals, int G, float time) {
+                                                                 const FragVal *__restrict__ vals, int G, float time,
+                                                                 uint32_t *__restrict__ hot_count, uint32_t *__restrict__ hot_list) {
     __shared__ FoldTerm s_term[kFoldWarps][kFoldChunk];
     __shared__ float s_om[kFoldWarps][kFoldChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = (blockIdx.x * kFoldWarps + warp) * 32 + lane;
     uint2 se = make_uint2(0u, 0u);
     if (t < G) se = seg[t];
-    const bool has = se.y > se.x;
-    // the warp's fragment range: segments are stored in texel order, so it is [first begin, last end)
-    uint32_t lo = has ? se.x : 0xffffffffu, hi = has ? se.y : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    bool has = se.y > se.x;
+    if (has && se.y - se.x > kFoldHot) {                // hot texel: a whole warp will fold it
+        hot_list[atomicAdd(hot_count, 1u)] = static_cast<uint32_t>(t);
+        has = false;
     }
-    if (hi <= lo) return;                               // no fragments in these 32 texels
+    // Segments are stored in texel order, so the warp's fragments lie in [lo, hi); fragments
+    // overwritten by an opaque one (k_splat_bounds) and hot texels leave gaps between the lanes' ranges.
+    const uint32_t lo = warp_min(has ? se.x : 0xffffffffu);
+    if (lo == 0xffffffffu) return;                      // nothing to fold in these 32 texels
+    const uint32_t hi = ~warp_min(has ? ~se.y : 0xffffffffu);
+    // first chunk at or after `from` that some lane needs (chunks are aligned to lo)
+    auto next_chunk = [&](uint32_t from) -> uint32_t {
+        const uint32_t need = warp_min((has && se.y > from) ? max(se.x, from) : 0xffffffffu);
+        return need == 0xffffffffu ? hi : lo + (need - lo) / kFoldChunk * kFoldChunk;
+    };
+    float rcx[kFoldPer], rcy[kFoldPer], ra[kFoldPer];
+    auto prefetch = [&](uint32_t c0) {                  // global -> registers, coalesced over the warp
+#pragma unroll
+        for (int j = 0; j < kFoldPer; ++j) {
+            const uint32_t i = c0 + j * 32 + lane;
+            if (i < hi) { rcx[j] = __ldcs(&vals[i].cx); rcy[j] = __ldcs(&vals[i].cy); ra[j] = __ldcs(&vals[i].a); }
+        }
+    };
     float4 d = has ? flow[t] : make_float4(0.f, 0.f, 0.f, 0.f);
     FoldTerm *term = s_term[warp];
     float *om = s_om[warp];
-    for (uint32_t c0 = lo; c0 < hi; c0 += kFoldChunk) {
+    uint32_t c0 = next_chunk(lo);
+    prefetch(c0);
+    while (c0 < hi) {
         const uint32_t c1 = min(c0 + static_cast<uint32_t>(kFoldChunk), hi);
-#pragma unroll
-        for (int j = 0; j < kFoldChunk / 32; ++j) {
-            const uint32_t i = c0 + j * 32 + lane;
-            if (i < c1) {
-                const float cx = __ldcs(&vals[i].cx), cy = __ldcs(&vals[i].cy), a = __ldcs(&vals[i].a);
-                FoldTerm tm;
-                tm.tx = __fmul_rn(cx, a);
-                tm.ty = __fmul_rn(cy, a);
-                tm.tz = __fmul_rn(time, a);
-                tm.tw = __fmul_rn(a, a);
-                term[j * 32 + lane] = tm;
-                om[j * 32 + lane] = __fsub_rn(1.0f, a);
-            }
-        }
+        stage_terms(term, om, rcx, rcy, ra, c0, c1, lane, time);
         __syncwarp();
+        const uint32_t cn = next_chunk(c1);
+        if (cn < hi) prefetch(cn);                      // in flight while this chunk is folded
         if (has) {
-            const uint32_t b = max(se.x, c0), e = min(se.y, c1);
-            for (uint32_t i = b; i < e; ++i) {
-                const FoldTerm tm = term[i - c0];
-                const float m = om[i - c0];
-                d.x = __fadd_rn(tm.tx, __fmul_rn(d.x, m));
-                d.y = __fadd_rn(tm.ty, __fmul_rn(d.y, m));
-                d.z = __fadd_rn(tm.tz, __fmul_rn(d.z, m));
-                d.w = __fadd_rn(tm.tw, __fmul_rn(d.w, m));
-            }
+            const uint32_t b_abs = max(se.x, c0), e_abs = min(se.y, c1);
+            if (b_abs < e_abs) fold_terms(d, term, om, b_abs - c0, e_abs - c0);
         }
         __syncwarp();
+        c0 = cn;
     }
     if (has) flow[t] = d;
+}
+
+// One warp per hot texel: all lanes load and pre-multiply a chunk, lane 0 runs the blend chain
+// while the next chunk is already in flight.  Persistent over the worklist.
+__global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(float4 *__restrict__ flow, const uint2 *__restrict__ seg,
+                                                                     const FragVal *__restrict__ vals, float time,
+                                                                     const uint32_t *__restrict__ hot_count,
+                                                                     const uint32_t *__restrict__ hot_list) {
+    __shared__ FoldTerm s_term[kFoldWarps][2][kFoldChunk];
+    __shared__ float s_om[kFoldWarps][2][kFoldChunk];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_hot = *hot_count;
+    const uint32_t n_warps = gridDim.x * kFoldWarps;
+    for (uint32_t w = blockIdx.x * kFoldWarps + warp; w < n_hot; w += n_warps) {
+        const uint32_t t = hot_list[w];
+        const uint2 se = seg[t];
+        float4 d = flow[t];
+        float rcx[kFoldPer], rcy[kFoldPer], ra[kFoldPer];
+        auto prefetch = [&](uint32_t c0) {
+#pragma unroll
+            for (int j = 0; j < kFoldPer; ++j) {
+                const uint32_t i = c0 + j * 32 + lane;
+                if (i < se.y) { rcx[j] = __ldcs(&vals[i].cx); rcy[j] = __ldcs(&vals[i].cy); ra[j] = __ldcs(&vals[i].a); }
+            }
+        };
+        prefetch(se.x);
+        int buf = 0;
+        for (uint32_t c0 = se.x; c0 < se.y; c0 += kFoldChunk, buf ^= 1) {
+            const uint32_t c1 = min(c0 + static_cast<uint32_t>(kFoldChunk), se.y);
+            stage_terms(s_term[warp][buf], s_om[warp][buf], rcx, rcy, ra, c0, c1, lane, time);
+            __syncwarp();
+            if (c1 < se.y) prefetch(c1);
+            if (lane == 0) fold_terms(d, s_term[warp][buf], s_om[warp][buf], 0u, c1 - c0);
+        }
+        if (lane == 0) flow[t] = d;
+        __syncwarp();
+    }
 }
 
 // Full-grid alpha-over of an RGBA layer (L4 inputs drawn into the flow FBO).

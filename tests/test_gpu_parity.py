@@ -279,3 +279,41 @@ def test_sharded_contexts_equal_single(T, oracle):
         assert_bits_equal(flow, sim.flow, f"sharded flow {k}")
         got = np.concatenate([t.particles.buffers[0].download() for t in ts], 0)
         assert_bits_equal(got, sim.cur, f"sharded state {k}")
+
+
+def test_opaque_cut_is_exact(T, oracle):
+    """The fold starts at the last alpha == 1 fragment of a texel.  That must not change a single
+    bit -- including for texels that already hold Inf / NaN (which the blend can never heal)."""
+    R, G = 64, 16
+    t = make(T, R, G, state={"speedLimit": 0.01})
+    O = oracle
+    rng = np.random.default_rng(3)
+    cur = np.zeros((R, R, 4), np.float32)
+    cur[..., 0:2] = rng.uniform(-0.9, 0.9, (R, R, 2))
+    speed = rng.choice([0.002, 0.01, 0.0100001, 0.02, 0.05], size=(R, R)).astype(np.float32)   # many at/over the limit
+    ang = rng.uniform(0, 2 * np.pi, (R, R))
+    cur[..., 2] = speed * np.cos(ang)
+    cur[..., 3] = speed * np.sin(ang)
+    prev = cur.copy()
+    prev[..., 0:2] -= 8 * cur[..., 2:4]              # lines of 0..3 texels
+    prev[..., 2:4] = cur[..., 2:4]                   # both vertices get the same alpha
+    flow0 = rng.normal(0, 0.01, (G, G, 4)).astype(np.float32)
+    flow0[2, 3] = np.inf
+    flow0[5, 5, 0] = -np.inf
+    flow0[7, 1] = np.nan
+    flow0[9, 9, 2] = np.nan
+    flow0[11:13] = 0.0
+    t.particles.buffers[0].upload(cur)
+    t.particles.buffers[1].upload(prev)
+    t.flow.upload(flow0)
+    sim = OracleSim(O, R, G, G, oracle_params(O, t))
+    sim.cur, sim.prev, sim.flow = cur.copy(), prev.copy(), flow0.copy()
+    for k in range(3):
+        t.timer.tick()
+        t.draw()
+        n = sim.draw(np.float32(t.timer.time))
+        assert t.particles.stats()["last_fragments"] == n
+        got = t.flow.download()
+        assert_bits_equal(got, sim.flow, f"flow after draw {k}")
+    assert (sim.flow[..., 3] == 1.0).sum() > 20, "the case must actually contain opaque fragments"
+    assert np.isnan(sim.flow).any()
