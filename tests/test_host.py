@@ -1,0 +1,122 @@
+"""CPU tests of the host layer: the JS-mirror classes, the C-ABI library's exported symbols, and the
+fail-loudly behaviour without a GPU."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The .so loads without a GPU and exports exactly what include/tendrils_b200.h declares."""
+    from tendrils_b200 import _native as N
+    from tendrils_b200 import build as B
+    B.build()
+    hdr = open(os.path.join(ROOT, "include", "tendrils_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*(tb_\w+)\s*\(", hdr, re.M))
+    assert declared == set(N.SYMBOLS), (declared ^ set(N.SYMBOLS))
+    lib = ctypes.CDLL(N.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert N.load().tb_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import tendrils_b200 as T
+    t = T.Tendrils(T.Device(64, 64))
+    with pytest.raises(T.TendrilsError, match="no CUDA device"):
+        t.setup(32)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under tendrils_b200/ may import or load it."""
+    pkg = os.path.join(ROOT, "tendrils_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+
+
+def test_timer_mirrors_src_timer_js():
+    from tendrils_b200 import Timer, defaults
+    t = defaults()["timer"]
+    assert t.step == 1000 / 60 and t.time == 0 and t.dt == 0
+    for k in range(1, 6):
+        t.tick()
+        assert t.dt == 1000 / 60
+        assert t.time == pytest.approx(k * 1000 / 60, rel=0, abs=1e-9)
+    # f64 accumulation, as in JS: time after 3 ticks is ((0+s)+s)+s, not 3*s rounded differently
+    s = 1000 / 60
+    assert t.time == ((((s + s) + s) + s) + s)
+    t.paused = True
+    before = t.time
+    t.tick()
+    assert t.time == before and t.dt == 0
+    # loop / end (src/timer.js:43-55; the demo sets end = 600000, loop = true)
+    u = Timer(0, 0); u.step = 400.0; u.end = 1000.0; u.loop = True
+    for _ in range(3):
+        u.tick()
+    assert u.time == math.fmod(1200.0, 1000.0)
+    v = Timer(0, 0); v.step = 400.0; v.end = 1000.0
+    for _ in range(3):
+        v.tick()
+    assert v.time == 1000.0 and v.paused
+    w = Timer(now=5000.0)
+    assert w.time == 0 and w.since == 5000.0
+    w.tick(now=5100.0)
+    assert w.time == 100.0 and w.dt == 100.0
+
+
+def test_aspect_mirrors_gl_matrix_storage():
+    from tendrils_b200.aspect import aspect, coverAspect, f32vec2
+    vs = [0, 0]
+    coverAspect(vs, [1000, 500])                 # plain Array: doubles (src/index.js:139,398)
+    assert vs == [1.0, (1 / 500) * 1000]
+    j = aspect(f32vec2(), [1000, 1000], 2)       # Float32Array: rounds at every store (spawn/pixels/index.js:43,55)
+    assert j.dtype == np.float32 and j[0] == np.float32(np.float32(1 / 1000) * 2)
+
+
+def test_shard_columns_partition():
+    from tendrils_b200 import shard_columns
+    for width, world in [(4096, 1), (4096, 8), (10, 3), (7, 7), (32768, 8)]:
+        blocks = [shard_columns(width, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == width
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))          # contiguous, in rank order
+        sizes = [b - a for a, b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_defaults_match_reference_state():
+    """src/index.js:29-57"""
+    from tendrils_b200 import defaults
+    s = defaults()["state"]
+    want = dict(rootNum=512, damping=0.043, speedLimit=0.01, forceWeight=0.016, varyForce=-0.1, flowWeight=1,
+                varyFlow=0.2, noiseWeight=0.002, varyNoise=0.3, flowDecay=0.005, flowWidth=5, noiseScale=2.125,
+                varyNoiseScale=0.5, noiseSpeed=0.00025, varyNoiseSpeed=0.1, target=0, varyTarget=1)
+    for k, v in want.items():
+        assert s[k] == v, k
+
+
+def test_custom_shaders_are_rejected():
+    import tendrils_b200 as T
+    with pytest.raises(T.TendrilsError, match="custom logic shaders"):
+        T.Tendrils(T.Device(8, 8), {"logicShader": "void main(){}"})
+
+
+def test_pixel_spawner_uniforms():
+    from tendrils_b200.spawn import PixelSpawner
+    from tendrils_b200.spawn import pixels as PX
+    sp = PixelSpawner(None, {"shader": PX.bestSampleFrag, "buffer": np.zeros((2, 2, 4), np.float32)})
+    u = sp.update({"viewRes": [1024, 512]})
+    assert u["speed"] == 1 and u["bias"] == 1 and list(u["spawnSize"]) == [1, 1]
+    assert u["jitter"][0] == np.float32(np.float32(1 / 1024) * 2) and u["jitter"][1] == np.float32(np.float32(1 / 512) * 2)
+    m = PX.mat3_scale(PX.mat3_identity(), [-1, 1])
+    assert list(m) == [-1, 0, 0, 0, 1, 0, 0, 0, 1]

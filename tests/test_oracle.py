@@ -1,0 +1,198 @@
+"""CPU tests of the oracle (oracle/tendrils_oracle.c): golden vectors, analytic checks of the
+restated arithmetic, and the structural facts of the reference the survey records (D6 etc.)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import assert_bits_equal, synthetic_image
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "oracle_v1.npz")
+DT = 1000 / 60
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_sin_cos_accuracy_and_golden(oracle, gold):
+    x = gold["sin_in"]
+    s = np.array([oracle.sin(v) for v in x], np.float32)
+    c = np.array([oracle.cos(v) for v in x], np.float32)
+    assert_bits_equal(s, gold["sin_out"], "sin golden")
+    assert_bits_equal(c, gold["cos_out"], "cos golden")
+    # TSIN-1 accuracy: a few ulp of the true value on the range the shaders use
+    assert np.max(np.abs(s - np.sin(x.astype(np.float64)))) < 4e-7
+    assert np.max(np.abs(c - np.cos(x.astype(np.float64)))) < 4e-7
+    assert np.isnan(oracle.sin(np.float32(1e6))) and np.isnan(oracle.cos(float("nan")))
+    assert oracle.sin(0.0) == 0.0 and oracle.cos(0.0) == 1.0
+
+
+def test_random_golden_and_range(oracle, gold):
+    r = np.array([oracle.random(*c) for c in gold["random_in"]], np.float32)
+    assert_bits_equal(r, gold["random_out"], "glsl-random golden")
+    assert (r >= 0).all() and (r < 1).all()
+    assert len(np.unique(r)) > 55          # it is a hash, not a constant
+
+
+def test_snoise_golden_and_range(oracle, gold):
+    out = np.array([oracle.snoise3(*v) for v in gold["snoise_in"]], np.float32)
+    assert_bits_equal(out, gold["snoise_out"], "snoise golden")
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-50, 50, (4000, 3)).astype(np.float32)
+    vals = np.array([oracle.snoise3(*p) for p in pts])
+    assert np.abs(vals).max() <= 1.0 + 1e-4 and np.abs(vals).max() > 0.5
+    assert abs(vals.mean()) < 0.05
+    # continuity (it is a smooth noise): tiny step, tiny change
+    a = oracle.snoise3(0.3, 0.7, 1.1)
+    b = oracle.snoise3(0.3 + 1e-4, 0.7, 1.1)
+    assert abs(a - b) < 1e-2
+    # Ashima's simplex noise is not zero at the origin: the well-known value of snoise(vec3(0.0)) is -0.41219...
+    assert abs(oracle.snoise3(0.0, 0.0, 0.0) + 0.412199) < 1e-5
+
+
+@pytest.mark.parametrize("R,G,steps", [(8, 16, 1), (8, 16, 10), (16, 16, 100), (64, 64, 10)])
+def test_simulation_golden(oracle, gold, R, G, steps):
+    O = oracle
+    P = O.make_params()
+    cur, prev = O.spawn_ball(R, R, 0.3, 0.005), O.spawn_init(R, R)
+    targets, flow = np.zeros((R, R, 4), np.float32), np.zeros((G, G, 4), np.float32)
+    t, frags = DT, []
+    for _ in range(steps):
+        t += DT
+        new = O.integrate(P, cur, targets, flow, np.float32(t), np.float32(DT))
+        prev, cur = cur, new
+        frags.append(O.splat(P, cur, prev, flow, np.float32(t)))
+    tag = f"sim_R{R}_G{G}_n{steps}"
+    assert_bits_equal(cur, gold[tag + "_cur"], "state")
+    assert_bits_equal(prev, gold[tag + "_prev"], "previous")
+    assert_bits_equal(flow, gold[tag + "_flow"], "flow")
+    assert list(frags) == list(gold[tag + "_frags"])
+
+
+def test_spawner_golden(oracle, gold):
+    O = oracle
+    assert_bits_equal(O.spawn_ball(16, 16, 1.0, 0.0), gold["ball_R16_r1_s0"], "ball r1")
+    assert_bits_equal(O.spawn_ball(16, 16, 0.3, 0.005), gold["ball_R16_r03_s005"], "ball")
+    img = gold["image_24x20"]
+    assert_bits_equal(img, synthetic_image(24, 20), "synthetic image")
+    S = O.make_spawn_pixels(spawnSize=(1, 1), jitter=(np.float32(2 / 32), np.float32(2 / 32)), speed=0.3, bias=1.0,
+                            spawnMatrix=(-1, 0, 0, 0, 1, 0, 0, 0, 1))
+    assert_bits_equal(O.spawn_pixels_direct(S, 16, 16, img, np.float32(3 * DT)), gold["direct_R16"], "direct")
+    state = O.spawn_ball(16, 16, 0.5, 0.004)
+    for v in O.SAMPLE_VARIANTS:
+        assert_bits_equal(O.spawn_pixels_sample(S, v, state, img, np.float32(5 * DT)), gold[f"sample_{v}_R16"], v)
+
+
+def test_ball_spawn_geometry(oracle):
+    b = oracle.spawn_ball(64, 64, 0.3, 0.005)
+    assert np.hypot(b[..., 0], b[..., 1]).max() <= 0.3 * (1 + 1e-6)
+    assert np.hypot(b[..., 2], b[..., 3]).max() <= 0.005 * (1 + 1e-6)
+    # same output on every call: the hash has no time or seed input (src/spawn/ball/index.frag:11-19)
+    assert np.array_equal(b, oracle.spawn_ball(64, 64, 0.3, 0.005))
+    # ball/index.js defaults: radius 1, speed 0 -> zero velocity
+    assert (oracle.spawn_ball(8, 8)[..., 2:] == 0).all()
+
+
+@pytest.mark.parametrize("R,proper,degenerate,reversed_", [(8, 4, 3, 1), (512, 256, 255, 1), (2048, 1024, 1023, 1),
+                                                           (4096, 2049, 2046, 1)])
+def test_vertex_table_D6(oracle, gold, R, proper, degenerate, reversed_):
+    """only ~half of the rows draw a prev->cur segment; the rest are zero-length,
+    the last row is reversed.  Counts evaluated in float32 exactly as the shader does."""
+    row, cur = oracle.vertex_table(R)
+    if f"vtx_row_{R}" in gold:
+        assert np.array_equal(row, gold[f"vtx_row_{R}"]) and np.array_equal(cur, gold[f"vtx_cur_{R}"])
+    ra, rb, ca, cb = row[0::2], row[1::2], cur[0::2], cur[1::2]
+    assert (ra == np.arange(R)).all()
+    assert (rb == np.arange(R)).all()               # the odd vertex of the last row clamps back onto row R-1
+    n_proper = int(((ca == 0) & (cb == 1)).sum())
+    n_deg = int((ca == cb).sum())
+    n_rev = int(((ca == 1) & (cb == 0)).sum())
+    assert (n_proper, n_deg, n_rev) == (proper, degenerate, reversed_)
+    assert ca[R - 1] == 1 and cb[R - 1] == 0
+    assert (oracle.column_table(R) == np.arange(R)).all()
+
+
+def test_integrate_semantics(oracle):
+    O = oracle
+    R, G = 8, 8
+    P = O.make_params()
+    st = O.spawn_ball(R, R, 0.5, 0.004)
+    st[0, 0] = (-1e6, -1e6, 0.25, -0.5)          # inert: passes through untouched, velocity included
+    st[0, 1] = (0.1, 0.2, 0.0, 0.0)              # Q2: at rest and force-free -> 0/0
+    targets, flow = np.zeros((R, R, 4), np.float32), np.zeros((G, G, 4), np.float32)
+    P0 = O.make_params(noiseWeight=0.0)
+    out = O.integrate(P0, st, targets, flow, np.float32(DT), np.float32(DT))
+    assert tuple(out[0, 0]) == (-1e6, -1e6, 0.25, -0.5)
+    assert np.isnan(out[0, 1]).all()
+    # damping only: vel' = vel*damping*dt, clamped; pos' = pos + vel'
+    v = st[3, 3, 2:4]
+    want = (v * np.float32(0.043)) * np.float32(DT)
+    assert np.allclose(out[3, 3, 2:4], want, rtol=1e-6)
+    assert np.allclose(out[3, 3, 0:2], st[3, 3, 0:2] + out[3, 3, 2:4], rtol=1e-6)
+    # speed limit
+    st2 = st.copy(); st2[..., 2:4] *= 100
+    out2 = O.integrate(P, st2, targets, flow, np.float32(DT), np.float32(DT))
+    sp = np.hypot(out2[1:, :, 2], out2[1:, :, 3])
+    assert sp.max() <= 0.01 * (1 + 1e-6)
+    # the flow gather: a uniform rightward flow accelerates everything to the right
+    flow[..., 0] = 0.01; flow[..., 2] = DT; flow[..., 3] = 1
+    out3 = O.integrate(P0, st, targets, flow, np.float32(DT), np.float32(DT))
+    assert (out3[1:, :, 2] > out[1:, :, 2]).all()
+    # ... and has fully decayed 1/flowDecay = 200 ms later (src/flow/get.glsl:3-5)
+    out4 = O.integrate(P0, st, targets, flow, np.float32(DT + 200.5), np.float32(DT))
+    assert_bits_equal(out4[1:], O.integrate(P0, st, targets, np.zeros_like(flow), np.float32(DT + 200.5), np.float32(DT))[1:], "decayed flow")
+
+
+def test_splat_raster_rules(oracle):
+    """RASTER-1: centre-sampled major axis, half-open towards the second vertex; ordered over-blend."""
+    O = oracle
+    R, G = 8, 8
+    P = O.make_params(speedLimit=1.0)
+    cur, prev = O.spawn_init(R, R), O.spawn_init(R, R)
+    # particle (0,0): row 0 is a proper prev->cur pair.  A horizontal line from x=1.25 to x=4.75 px at y=2.5 px
+    to_ndc = lambda px: px / (G / 2) - 1.0
+    prev[0, 0] = (to_ndc(1.25), to_ndc(2.5), 0.5, 0.0)
+    cur[0, 0] = (to_ndc(4.75), to_ndc(2.5), 0.5, 0.0)
+    flow = np.zeros((G, G, 4), np.float32)
+    n = O.splat(P, cur, prev, flow, np.float32(100.0))
+    hit = np.argwhere(flow[..., 3] != 0)
+    assert n == 4 and [tuple(h) for h in hit] == [(2, 1), (2, 2), (2, 3), (2, 4)]   # centres 1.5 .. 4.5 lie in [1.25, 4.75)
+    a = np.float32(0.5)                                                      # alpha = |vel|/speedLimit
+    assert_bits_equal(flow[2, 2], np.array([0.5 * a, 0, 100.0 * a, a * a], np.float32), "blend onto zero")
+    # zero-length and inert primitives draw nothing
+    flow2 = np.zeros_like(flow)
+    prev[0, 0] = cur[0, 0]
+    assert O.splat(P, cur, prev, flow2, np.float32(1.0)) == 0
+    # a later primitive of the same texel blends OVER the earlier one (order = x*R + k)
+    prev[0, 0] = (to_ndc(2.25), to_ndc(2.5), 1.0, 0.0); cur[0, 0] = (to_ndc(2.75), to_ndc(2.5), 1.0, 0.0)
+    prev[1, 0] = (to_ndc(2.25), to_ndc(2.5), 0.0, 0.25); cur[1, 0] = (to_ndc(2.75), to_ndc(2.5), 0.0, 0.25)
+    flow3 = np.zeros_like(flow)
+    assert O.splat(P, cur, prev, flow3, np.float32(7.0)) == 2
+    first = np.array([1.0, 0.0, 7.0, 1.0], np.float32)                       # alpha 1: overwrites
+    second = np.array([0.0, 0.25, 7.0, 0.25], np.float32)
+    want = second * np.float32(0.25) + first * np.float32(0.75)
+    assert_bits_equal(flow3[2, 2], want, "ordered over-blend")
+
+
+def test_splat_mt_and_sharded_equal_serial(oracle):
+    O = oracle
+    R, G = 64, 32
+    P = O.make_params()
+    cur, prev = O.spawn_ball(R, R, 0.4, 0.005), O.spawn_init(R, R)
+    targets = np.zeros((R, R, 4), np.float32)
+    f_serial, f_mt, f_shard = (np.zeros((G, G, 4), np.float32) for _ in range(3))
+    t = DT
+    for _ in range(8):
+        t += DT
+        new = O.integrate(P, cur, targets, f_serial, np.float32(t), np.float32(DT))
+        prev, cur = cur, new
+        n = O.splat(P, cur, prev, f_serial, np.float32(t))
+        assert O.splat(P, cur, prev, f_mt, np.float32(t), mt=True) == n
+        m = 0
+        for cols in ((0, 20), (20, 21), (21, 64)):          # column shards folded in order = the full draw
+            m += O.splat(P, cur, prev, f_shard, np.float32(t), cols=cols)
+        assert m == n
+        assert_bits_equal(f_mt, f_serial, "mt splat")
+        assert_bits_equal(f_shard, f_serial, "sharded splat")
