@@ -8,7 +8,7 @@ N > 1 is launched by torchrun (one rank per GPU); rank 0 prints ONE JSON line.
 Workload (BASELINE.json): at N = 1 `configs[2]` -- 4096x4096 particles, 1024x1024 flow grid with
 flowDecay + trail splat, image-pixel (best-sample) respawn every 60th step -- which is the
 configuration the metric's target (">= 70 % of HBM roofline ... at 16M particles on 1 B200") is
-quoted on; at N > 1 `configs[3]`, the same per GPU (weak scaling, global texture 4096N x 4096).
+quoted on; at N > 1 `configs[3]`, the same per GPU (weak scaling, global texture 4096 x 4096N).
 
 A "step" = Tendrils.step() + the flow half of Tendrils.draw() (+ the respawn pass when due).
 `value` counts inputs resident in HBM; `e2e` re-measures with the particle state crossing
@@ -119,7 +119,9 @@ def build_sim(wl, rank, world, local_rank, group):
     from tendrils_b200.spawn.pixels import bestSampleFrag, mat3_identity, mat3_scale, pixelsFrag
     R, G = wl["R"], wl["G"]
     t = T.Tendrils(T.Device(G, G, device=local_rank, rank=rank, world_size=world, group=group))
-    t.setup([R * world, R])
+    # N ranks: one R x (R*N) texture sharded by columns (R/N columns x R*N rows = R^2 particles per rank).
+    # Widening instead (R*N x R) would leave the exact 1:1 vertex->column range of the reference's LUT.
+    t.setup([R, R * world])
     t.resize()
     first = spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}})  # src/demo.main.js:1402-1405
     sp = None
@@ -342,7 +344,13 @@ def main():
         if world == 1 and args.gpus > 1:
             sys.exit("bench.py: --gpus N > 1 must be launched with torchrun (one rank per GPU)")
     wl = WORKLOADS[args.workload]
+    # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. NCCL's version
+    # banner) is sent to stderr while the benchmark runs
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     out = run_reference(args, wl, rank, world) if args.impl == "reference" else run_ours(args, wl, rank, world, local_rank)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if out is not None:
         print(json.dumps(out), flush=True)
 

@@ -229,6 +229,9 @@ int collect(tb_ctx *c, float time) {
     c->collect_time = time;
     c->collected = false;
     c->last_frags = 0;
+    // splat timing: from the start of the collect to the end of the fold (in a sharded run this
+    // includes waiting for the grid from the previous rank)
+    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][0], c->stream));
     *c->h_total = 0;
     if (threads > 0) {
         TB_CUDA(c, cudaMemsetAsync(c->prim_off, 0, (threads + 1) * sizeof(uint32_t), c->stream));
@@ -272,6 +275,8 @@ int fold(tb_ctx *c) {
             c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 1);
         if (int r = check_launch(c, "k_splat_fold_hot")) return r;
     }
+    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
+    c->ev_count[1] += 1;
     c->collected = false;
     return TB_OK;
 }
@@ -461,13 +466,8 @@ int tb_splat_fold(tb_ctx *c) {
 int tb_splat_flow(tb_ctx *c, float time) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
-    cudaEvent_t *ev = c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots];
-    TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
     if (int r = collect(c, time)) return r;
-    if (int r = fold(c)) return r;
-    TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
-    c->ev_count[1] += 1;
-    return TB_OK;
+    return fold(c);
 }
 
 int tb_reset(tb_ctx *c) {
