@@ -172,10 +172,12 @@ int tb_stream(tb_ctx *ctx, void **cuda_stream);
 int tb_sync(tb_ctx *ctx);
 /* counters since creation: kernels launched by this library, fragments blended by the last splat */
 int tb_stats(tb_ctx *ctx, int64_t *kernel_launches, int64_t *last_fragments);
-/* CUDA-event timing, recorded on the context's stream around every integrate launch and every
- * tb_splat_flow: number of timed calls since the last reset (at most 512 are kept) and their
- * summed device time in milliseconds.  Synchronises the stream.  reset != 0 restarts the count. */
-int tb_timing(tb_ctx *ctx, int reset, int64_t *n_integrate, float *integrate_ms, int64_t *n_splat, float *splat_ms);
+/* CUDA-event timing: number of timed calls since the last reset (at most 512 are kept) and their
+ * summed device time in milliseconds, for (1) the integrate launch on the main stream, (2) the flow
+ * splat (collect start to fold end) and (3) the noise launch on the side stream when tb_step overlaps
+ * it with the previous splat (its time then hides under (2)).  Synchronises.  reset != 0 restarts. */
+int tb_timing(tb_ctx *ctx, int reset, int64_t *n_integrate, float *integrate_ms, int64_t *n_splat, float *splat_ms,
+              int64_t *n_noise, float *noise_ms);
 
 #ifdef __cplusplus
 }

@@ -62,7 +62,8 @@ SYMBOLS = {
     "tb_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "tb_sync": (C.c_int, [_ctx]),
     "tb_stats": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "tb_timing": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_int64), _fp, C.POINTER(C.c_int64), _fp]),
+    "tb_timing": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_int64), _fp, C.POINTER(C.c_int64), _fp,
+                            C.POINTER(C.c_int64), _fp]),
 }
 
 _lib = None

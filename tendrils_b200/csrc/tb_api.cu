@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -28,6 +29,12 @@ struct tb_ctx {
     int W = 0, H = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;            // low priority: noise of the next step under the previous splat
+    cudaEvent_t ev_state = nullptr;         // last write to the state buffers (main stream)
+    cudaEvent_t ev_noise = nullptr;         // noise kernel done (side stream)
+    float2 *wander = nullptr;
+    bool splat_since_step = false;          // something HBM-bound is queued that the noise can hide under
+    bool overlap = true;
 
     float4 *buf[2] = {nullptr, nullptr};   // [0] current, [1] previous (src/particles.js:128)
     float4 *targets = nullptr;
@@ -65,8 +72,8 @@ struct tb_ctx {
 
     // CUDA-event timing rings: [class][slot][begin/end]; class 0 = integrate, 1 = flow splat
     static constexpr int kTimingSlots = 512;
-    cudaEvent_t ev_ring[2][kTimingSlots][2] = {};
-    int64_t ev_count[2] = {0, 0};
+    cudaEvent_t ev_ring[3][kTimingSlots][2] = {};   // 0 integrate (main stream), 1 flow splat, 2 noise (side stream)
+    int64_t ev_count[3] = {0, 0, 0};
 
     tb_state state{};
     bool have_state = false;
@@ -229,6 +236,7 @@ int collect(tb_ctx *c, float time) {
     c->collect_time = time;
     c->collected = false;
     c->last_frags = 0;
+    c->splat_since_step = true;
     // splat timing: from the start of the collect to the end of the fold (in a sharded run this
     // includes waiting for the grid from the previous rank)
     TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][0], c->stream));
@@ -290,7 +298,10 @@ float4 *spawn_out(tb_ctx *c, tb_target target) {
 }
 
 int after_targets_write(tb_ctx *c, tb_target target) {
-    if (target != TB_TARGET_TARGETS) return TB_OK;
+    if (target != TB_TARGET_TARGETS) {
+        TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));     // the state buffers changed
+        return TB_OK;
+    }
     TB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
     k_check_finite<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(c->targets, c->n_local, c->d_flag);
     if (int r = check_launch(c, "k_check_finite")) return r;
@@ -341,12 +352,29 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
         return code;
     };
 #define TB_TRY(expr) do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) { c->err = std::string(#expr) + ": " + cudaGetErrorString(e2_); return bail(TB_ERR_CUDA); } } while (0)
-    TB_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    TB_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    TB_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+    {
+        const char *sp = std::getenv("TB_SIDE_PRIO");     // experiment knob: "equal" | "high" (default low)
+        int prio = prio_lo;
+        if (sp && std::string(sp) == "equal") prio = prio_hi;
+        if (sp && std::string(sp) == "high") { prio = prio_hi; prio_hi = prio_lo; }
+        if (sp && std::string(sp) == "high") {
+            TB_TRY(cudaStreamDestroy(c->stream));
+            TB_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_lo));
+        }
+        TB_TRY(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio));
+    }
+    TB_TRY(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
+    TB_TRY(cudaEventCreateWithFlags(&c->ev_noise, cudaEventDisableTiming));
+    c->overlap = std::getenv("TB_NO_OVERLAP") == nullptr;
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));
     TB_TRY(cudaMalloc(&c->buf[1], bytes));
     TB_TRY(cudaMalloc(&c->targets, bytes));
+    TB_TRY(cudaMalloc(&c->wander, static_cast<size_t>(c->n_local) * sizeof(float2)));
     TB_TRY(cudaMemsetAsync(c->targets, 0, bytes, c->stream));       // FBO textures start zeroed
     TB_TRY(cudaMemsetAsync(c->buf[0], 0, bytes, c->stream));
     TB_TRY(cudaMemsetAsync(c->buf[1], 0, bytes, c->stream));
@@ -354,7 +382,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     TB_TRY(cudaMallocHost(&c->h_flag, sizeof(int)));
     TB_TRY(cudaMallocHost(&c->h_total, sizeof(uint32_t)));
     TB_TRY(cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming));
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
             for (int j = 0; j < 2; ++j) TB_TRY(cudaEventCreate(&c->ev_ring[k][i][j]));
     const std::vector<PairEntry> pairs = build_pairs(PH);
@@ -382,6 +410,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
 int tb_destroy(tb_ctx *c) {
     if (!c) return TB_OK;
     cudaSetDevice(c->device);
+    if (c->side) cudaStreamSynchronize(c->side);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
     cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off);
@@ -390,10 +419,14 @@ int tb_destroy(tb_ctx *c) {
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_total) cudaFreeHost(c->h_total);
     if (c->ev_total) cudaEventDestroy(c->ev_total);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
             for (int j = 0; j < 2; ++j)
                 if (c->ev_ring[k][i][j]) cudaEventDestroy(c->ev_ring[k][i][j]);
+    if (c->ev_state) cudaEventDestroy(c->ev_state);
+    if (c->ev_noise) cudaEventDestroy(c->ev_noise);
+    if (c->side) cudaStreamDestroy(c->side);
+    cudaFree(c->wander);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return TB_OK;
@@ -433,8 +466,8 @@ int tb_step(tb_ctx *c, float time, float dt) {
     A.targets = c->targets;
     A.flow = c->flow;
     A.PW = c->PW; A.PH = c->PH; A.W = c->W; A.H = c->H;
-    A.p0 = static_cast<long long>(c->col0) * c->PH;
-    A.n = c->n_local;
+    A.col0 = c->col0;
+    A.cols = c->col1 - c->col0;
     A.time = time; A.dt = dt;
     // The target / noise terms are exactly +-0 for every finite particle when their weight is 0
     // and the variances are tame; the kernel still takes the full path for wild positions.
@@ -443,11 +476,41 @@ int tb_step(tb_ctx *c, float time, float dt) {
                     tame(S.varyNoiseScale, 1e6f) && tame(S.noiseSpeed, 1e6f) && tame(S.varyNoiseSpeed, 1e6f) &&
                     tame(time, 1e9f) && tame(dt, 1e6f));
     cudaEvent_t *ev = c->ev_ring[0][c->ev_count[0] % tb_ctx::kTimingSlots];
-    TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
-    k_integrate<<<blocks_for(A.n, 256), 256, 0, c->stream>>>(A);
-    if (int r = check_launch(c, "k_integrate")) return r;
+    auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    A.pow2_res = is_pow2(c->PW) && is_pow2(c->PH) && static_cast<long long>(c->PW) * c->PH <= (1LL << 40);
+    A.inv_resx = 1.0f / static_cast<float>(c->PW);
+    A.inv_resy = 1.0f / static_cast<float>(c->PH);
+    A.inv_n = 1.0f / (static_cast<float>(c->PW) * static_cast<float>(c->PH));
+    static const bool scalar_noise = std::getenv("TB_SCALAR_NOISE") != nullptr;    // A/B switch for profiling
+    A.packed_noise = scalar_noise ? 0 : 1;
+    A.pk.one = 1.0f; A.pk.neg_one = -1.0f; A.pk.neg_zero = -0.0f;
+    A.wander = c->wander;
+    const dim3 grid(blocks_for(c->PH, 256), static_cast<unsigned>(A.cols));
+    if (A.use_noise && c->overlap && c->splat_since_step) {
+        // The noise does not read the flow grid: evaluate it on the low-priority side stream, where it
+        // runs under the previous step's sort + fold still queued on the main stream; the rest of the
+        // shader follows on the main stream.  The side stream only waits for the state to be final.
+        cudaEvent_t *evn = c->ev_ring[2][c->ev_count[2] % tb_ctx::kTimingSlots];
+        TB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_state, 0));
+        TB_CUDA(c, cudaEventRecord(evn[0], c->side));
+        k_integrate<kNoise><<<grid, 256, 0, c->side>>>(A);
+        if (int r = check_launch(c, "k_integrate<noise>")) return r;
+        TB_CUDA(c, cudaEventRecord(evn[1], c->side));
+        TB_CUDA(c, cudaEventRecord(c->ev_noise, c->side));
+        c->ev_count[2] += 1;
+        TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_noise, 0));
+        TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
+        k_integrate<kFinish><<<grid, 256, 0, c->stream>>>(A);
+        if (int r = check_launch(c, "k_integrate<finish>")) return r;
+    } else {
+        TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
+        k_integrate<kFused><<<grid, 256, 0, c->stream>>>(A);
+        if (int r = check_launch(c, "k_integrate")) return r;
+    }
     TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     c->ev_count[0] += 1;
+    c->splat_since_step = false;
     return TB_OK;
 }
 
@@ -477,6 +540,7 @@ int tb_reset(tb_ctx *c) {
         k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(c->buf[b], c->n_local);
         if (int r = check_launch(c, "k_spawn_init")) return r;
     }
+    TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     return TB_OK;
 }
 
@@ -587,9 +651,11 @@ int tb_upload(tb_ctx *c, tb_buffer which, const float *host, int64_t n_floats) {
     float4 *dst; int64_t n;
     if (int r = buffer_of(c, which, &dst, &n)) return r;
     TB_REQUIRE(c, n == n_floats, "tb_upload: size mismatch");
+    TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaMemcpyAsync(dst, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (which == TB_BUF_TARGETS) return after_targets_write(c, TB_TARGET_TARGETS);
+    TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     return TB_OK;
 }
 
@@ -649,6 +715,7 @@ int tb_stream(tb_ctx *c, void **cuda_stream) {
 int tb_sync(tb_ctx *c) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
 }
@@ -660,13 +727,15 @@ int tb_stats(tb_ctx *c, int64_t *kernel_launches, int64_t *last_fragments) {
     return TB_OK;
 }
 
-int tb_timing(tb_ctx *c, int reset, int64_t *n_integrate, float *integrate_ms, int64_t *n_splat, float *splat_ms) {
+int tb_timing(tb_ctx *c, int reset, int64_t *n_integrate, float *integrate_ms, int64_t *n_splat, float *splat_ms,
+              int64_t *n_noise, float *noise_ms) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
-    int64_t *n_out[2] = {n_integrate, n_splat};
-    float *ms_out[2] = {integrate_ms, splat_ms};
-    for (int k = 0; k < 2; ++k) {
+    int64_t *n_out[3] = {n_integrate, n_splat, n_noise};
+    float *ms_out[3] = {integrate_ms, splat_ms, noise_ms};
+    for (int k = 0; k < 3; ++k) {
         const int64_t n = std::min<int64_t>(c->ev_count[k], tb_ctx::kTimingSlots);
         double total = 0.0;
         for (int64_t i = 0; i < n; ++i) {

@@ -3,6 +3,7 @@
 #pragma once
 
 #include "tb_math.cuh"
+#include "tb_noise2.cuh"
 #include "../../include/tendrils_b200.h"
 
 namespace tb {
@@ -33,41 +34,82 @@ struct IntegrateArgs {
     float4 *__restrict__ out;
     const float4 *__restrict__ targets;
     const float4 *__restrict__ flow;
+    float2 *__restrict__ wander;           // the two noise values per particle (split launch only)
     int PW, PH, W, H;
-    long long p0;          // global index of the first local particle (col0*PH)
-    long long n;           // local particle count
+    int col0, cols;        // first global column, local columns
     float time, dt;
     int use_targets;       // 0: the target term is provably +-0 for every finite particle
     int use_noise;         // 0: the noise term is provably +-0 for every finite particle
+    int packed_noise;      // 1: evaluate the two simplex noises on the packed FP32 pipe (tb_noise2.cuh)
+    int pow2_res;          // 1: PW and PH are powers of two: x/res == x*(1/res) exactly
+    float inv_resx, inv_resy, inv_n;
+    PackedConsts pk;       // 1, -1, -0 (opaque to the compiler on purpose)
 };
 
 // a3: src/logic.frag:45-101.  One thread per particle, 16 B in / 16 B out, flow gather via L2.
-__global__ void __launch_bounds__(256) k_integrate(const IntegrateArgs A) {
-    const long long l = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (l >= A.n) return;
+#ifndef TB_INTEGRATE_MIN_BLOCKS
+#define TB_INTEGRATE_MIN_BLOCKS 5
+#endif
+
+// logic.frag:45-101 comes in three launch shapes sharing one body:
+//   kFused    the whole shader in one pass (16 B in, 16 B out, one 16 B L2 gather);
+//   kNoise    only the two simplex noises (logic.frag:57-68) -> `wander` (8 B/particle).  They do not
+//             depend on the flow grid, so tb_step runs this on a side stream while the PREVIOUS
+//             step's flow splat (sort + fold, HBM-bound) still occupies the main stream;
+//   kFinish   everything else, reading `wander` back (logic.frag:71-100).
+// The arithmetic is the same expression tree in every shape: results are bit-identical.
+enum IntegrateMode { kFused = 0, kNoise = 1, kFinish = 2 };
+
+// Grid: x = 256-thread tiles along a texture column (y), y = local column.  No integer division.
+template <int MODE>
+__global__ void __launch_bounds__(256, TB_INTEGRATE_MIN_BLOCKS) k_integrate(const IntegrateArgs A) {
+    const int y = blockIdx.x * 256 + threadIdx.x;
+    if (y >= A.PH) return;
+    const long long l = static_cast<long long>(blockIdx.y) * A.PH + y;
     const float4 st = __ldcs(A.in + l);
     float posx = st.x, posy = st.y, velx = st.z, vely = st.w;
     if (!(posx != kInert || posy != kInert)) {
-        __stcs(A.out + l, st);
+        if (MODE != kNoise) __stcs(A.out + l, st);
         return;
     }
-    const long long p = A.p0 + l;
-    const int x = static_cast<int>(p / A.PH);
-    const int y = static_cast<int>(p - static_cast<long long>(x) * A.PH);
+    const int x = A.col0 + static_cast<int>(blockIdx.y);
     const float resx = static_cast<float>(A.PW), resy = static_cast<float>(A.PH);
     const float fcx = __fadd_rn(static_cast<float>(x), 0.5f), fcy = __fadd_rn(static_cast<float>(y), 0.5f);
-    const float uvx = __fdiv_rn(fcx, resx), uvy = __fdiv_rn(fcy, resy);
-    const float i = __fdiv_rn(__fadd_rn(fcx, __fmul_rn(fcy, resx)), __fmul_rn(resx, resy));
+    float uvx, uvy, i;
+    if (A.pow2_res) {      // dividing by a power of two is the same rounding as multiplying by its reciprocal
+        uvx = __fmul_rn(fcx, A.inv_resx);
+        uvy = __fmul_rn(fcy, A.inv_resy);
+        i = __fmul_rn(__fadd_rn(fcx, __fmul_rn(fcy, resx)), A.inv_n);
+    } else {
+        uvx = __fdiv_rn(fcx, resx);
+        uvy = __fdiv_rn(fcy, resy);
+        i = __fdiv_rn(__fadd_rn(fcx, __fmul_rn(fcy, resx)), __fmul_rn(resx, resy));
+    }
     const tb_state &S = A.S;
 
     const bool tame = fabsf(posx) < 1.0e6f && fabsf(posy) < 1.0e6f;
     float wx = 0.0f, wy = 0.0f;
-    if (A.use_noise || !tame) {
+    if (MODE == kFinish) {
+        const float2 w = __ldcs(A.wander + l);
+        wx = w.x;
+        wy = w.y;
+    } else if (A.use_noise || !tame) {
         const float ns = vary(S.noiseScale, i, S.varyNoiseScale);
         const float npx = __fmul_rn(posx, ns), npy = __fmul_rn(posy, ns);
         const float noiseTime = __fmul_rn(A.time, vary(S.noiseSpeed, i, S.varyNoiseSpeed));
-        wx = snoise3(npx, npy, __fadd_rn(uvx, noiseTime));
-        wy = snoise3(npx, npy, __fadd_rn(__fadd_rn(uvy, noiseTime), 1234.5678f));
+        const float za = __fadd_rn(uvx, noiseTime), zb = __fadd_rn(__fadd_rn(uvy, noiseTime), 1234.5678f);
+        // the packed path relies on lattice coordinates being exact integers below 2^24
+        const bool lattice_ok = fabsf(npx) < 2.0e6f && fabsf(npy) < 2.0e6f && fabsf(za) < 2.0e6f && fabsf(zb) < 2.0e6f;
+        if (A.packed_noise && lattice_ok) {
+            snoise3_pair(A.pk, npx, npy, za, zb, wx, wy);
+        } else {
+            wx = snoise3(npx, npy, za);
+            wy = snoise3(npx, npy, zb);
+        }
+    }
+    if (MODE == kNoise) {
+        __stcs(A.wander + l, make_float2(wx, wy));
+        return;
     }
 
     // flowAtScreenPos (flow/flow-at-screen-pos.glsl:13-27) with levels = stride = 1

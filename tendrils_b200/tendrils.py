@@ -270,10 +270,14 @@ class Particles:
         return {"kernel_launches": a.value, "last_fragments": b.value}
 
     def timing(self, reset=False):
-        """Summed CUDA-event time of the integrate launches and the flow splats since the last reset."""
-        ni, ns, mi, ms = C.c_int64(), C.c_int64(), C.c_float(), C.c_float()
-        N.check(self._ctx, self._L.tb_timing(self._ctx, int(reset), C.byref(ni), C.byref(mi), C.byref(ns), C.byref(ms)))
-        return {"n_integrate": ni.value, "integrate_ms": mi.value, "n_splat": ns.value, "splat_ms": ms.value}
+        """Summed CUDA-event time of the integrate launches, the flow splats and the side-stream noise
+        launches since the last reset."""
+        ni, ns, nn = C.c_int64(), C.c_int64(), C.c_int64()
+        mi, ms, mn = C.c_float(), C.c_float(), C.c_float()
+        N.check(self._ctx, self._L.tb_timing(self._ctx, int(reset), C.byref(ni), C.byref(mi), C.byref(ns), C.byref(ms),
+                                             C.byref(nn), C.byref(mn)))
+        return {"n_integrate": ni.value, "integrate_ms": mi.value, "n_splat": ns.value, "splat_ms": ms.value,
+                "n_noise": nn.value, "noise_ms": mn.value}
 
     def dispose(self):                                                  # src/particles.js:168-169 (@todo there)
         if getattr(self, "_ctx", None):
