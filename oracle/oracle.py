@@ -98,6 +98,8 @@ def lib():
         L.or_splat.restype = C.c_longlong
         L.or_splat.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int,
                                _fp, _fp, _fp, C.c_int, C.c_int, C.c_float]
+        L.or_flow_vertex.restype = C.c_int
+        L.or_flow_vertex.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_float, _fp]
         L.or_splat_mt.restype = C.c_longlong
         L.or_splat_mt.argtypes = L.or_splat.argtypes
         L.or_spawn_init.restype = None
@@ -159,6 +161,14 @@ def splat(P, cur, prev, flow, time, cols=None, mt=False):
     x0, x1 = cols or (0, PW)
     fn = lib().or_splat_mt if mt else lib().or_splat
     return fn(C.byref(P), PW, PH, x0, x1, _p(cur), _p(prev), _p(flow), W, H, f32(time))
+
+
+def flow_vertex(P, cur, prev, i, j, time):
+    """(written, [gl_Position.x, gl_Position.y, r, g, b, a]) of vertex (column i, row j) of the flow draw."""
+    PW, PH = cur.shape[:2]
+    out = np.zeros(6, np.float32)
+    ok = lib().or_flow_vertex(C.byref(P), PW, PH, int(i), int(j), _p(cur), _p(prev), f32(time), _p(out))
+    return bool(ok), out
 
 
 def spawn_init(PW, PH, cols=None):

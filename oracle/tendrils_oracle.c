@@ -1,7 +1,7 @@
 /*
  * tendrils_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
  * See tendrils_oracle.h for the contract.  PARITY UNPINNED by the reference's own tests
- * (it has none); pinned against tests/golden/glsl_*.json (reference shader text run
+ * (it has none); pinned against tests/golden/glsl_v1.npz (reference shader text run
  * through tools/glsl_interp.py) and spec/PARITY.md.
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared
@@ -256,6 +256,25 @@ static inline void flow_colour(float vx, float vy, float time, float speedLimit,
 
 static inline int finite4(const float *s) {
     return isfinite(s[0]) && isfinite(s[1]) && isfinite(s[2]) && isfinite(s[3]);
+}
+
+/* The vertex stage alone (src/flow/vert/main.vert:10-17 + stateAtFrame + apply/state.glsl), exposed so that
+ * tests can compare it with the reference's flow/index.vert run through tools/glsl_interp.py.
+ * out6 = (gl_Position.xy, color.rgba); returns 1 when gl_Position is written (state not inert). */
+int or_flow_vertex(const or_params *P, int PW, int PH, int i, int j, const float *cur, const float *prev,
+                   float time, float *out6) {
+    int *row = (int *)malloc(sizeof(int) * 2 * PH), *isc = (int *)malloc(sizeof(int) * 2 * PH);
+    int *col = (int *)malloc(sizeof(int) * PW);
+    or_vertex_table(PH, row, isc);
+    or_column_table(PW, col);
+    const float *st = (isc[j] ? cur : prev) + 4 * ((size_t)col[i] * PH + row[j]);
+    free(row); free(isc); free(col);
+    if (!(st[0] != -1000000.0f || st[1] != -1000000.0f)) return 0;
+    float c[4];
+    flow_colour(st[2], st[3], time, P->speedLimit, c);
+    out6[0] = st[0] * P->viewSize[0]; out6[1] = st[1] * P->viewSize[1];
+    out6[2] = c[0]; out6[3] = c[1]; out6[4] = c[2]; out6[5] = c[3];
+    return 1;
 }
 
 /* One fragment, blendFunc(SRC_ALPHA, ONE_MINUS_SRC_ALPHA) on all four channels

@@ -9,7 +9,7 @@
  * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this
  * path and its shaders cannot be executed in this image (no
  * Node / headless-gl / Mesa).  This oracle is pinned instead against
- *   (1) tests/golden/glsl_*.json -- outputs of the reference's OWN shader text
+ *   (1) tests/golden/glsl_v1.npz -- outputs of the reference's OWN shader text
  *       (docs/js/index.js.map, demo.js.map sourcesContent) executed by tools/glsl_interp.py, and
  *   (2) the rounding contract in spec/PARITY.md (every op is one IEEE-754 binary32
  *       operation, evaluated in GLSL source order, no FMA contraction).
@@ -71,6 +71,10 @@ void or_integrate(const or_params *P, int PW, int PH, int x0, int x1,
 void or_vertex_table(int PH, int *row_of_vertex, int *cur_of_vertex);
 /* column index sampled by vertex column i (reference particles.js:171-190 + NEAREST fetch) */
 void or_column_table(int PW, int *col_of_vertex_col);
+
+/* the vertex stage of the flow draw alone: out6 = (gl_Position.xy, color.rgba); 0 when the vertex is inert */
+int or_flow_vertex(const or_params *P, int PW, int PH, int i, int j, const float *cur, const float *prev,
+                   float time, float *out6);
 
 /* a7-a10: flow/index.vert + GL_LINES raster + ordered alpha-over blend, columns [x0,x1). */
 /* returns the number of fragments blended. */
