@@ -50,6 +50,11 @@ struct tb_ctx {
     int n_pairs = 0;
     long long n_prims = 0;                 // local primitives = columns * n_pairs
     uint32_t *prim_off = nullptr;          // n_prims+1: fragments per primitive -> exclusive offsets, [n_prims] = total
+    int32_t *row_pair = nullptr;           // per texture row: pair index | kind << 30, or -1 (fused count in k_integrate)
+    bool fuse_count = false;               // every pair reads one particle's prev/cur: the count can ride in k_integrate
+    bool count_valid = false;              // prim_off/total on the host belong to the current (state, flow shape, viewSize)
+    float count_vs[2] = {0.f, 0.f};
+    int count_wh[2] = {0, 0};
     void *scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
     uint32_t *keys[2] = {nullptr, nullptr};   // texel of each fragment (draw order / sorted)
@@ -226,6 +231,17 @@ SplatArgs splat_args(tb_ctx *c) {
     return A;
 }
 
+// exclusive scan of the per-primitive counts in place and the total to the host (async; ev_total)
+int scan_counts(tb_ctx *c) {
+    const long long threads = c->n_prims;
+    TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp, c->scan_tmp_bytes, c->prim_off, c->prim_off,
+                                             static_cast<int>(threads + 1), c->stream));
+    c->launches += 2;    // DeviceScanInitKernel + DeviceScanKernel
+    TB_CUDA(c, cudaMemcpyAsync(c->h_total, c->prim_off + threads, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaEventRecord(c->ev_total, c->stream));
+    return TB_OK;
+}
+
 // Rasterise this context's primitives into per-texel fragment segments in draw order:
 //   count per primitive -> exclusive scan -> emit in draw order (no atomics) -> stable radix
 //   sort by texel -> segment bounds.
@@ -240,17 +256,18 @@ int collect(tb_ctx *c, float time) {
     // splat timing: from the start of the collect to the end of the fold (in a sharded run this
     // includes waiting for the grid from the previous rank)
     TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][0], c->stream));
-    *c->h_total = 0;
+    if (threads <= 0) *c->h_total = 0;
     if (threads > 0) {
-        TB_CUDA(c, cudaMemsetAsync(c->prim_off, 0, (threads + 1) * sizeof(uint32_t), c->stream));
-        SplatArgs A = splat_args(c);
-        k_splat_count<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
-        if (int r = check_launch(c, "k_splat_count")) return r;
-        TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp, c->scan_tmp_bytes, c->prim_off, c->prim_off,
-                                                 static_cast<int>(threads + 1), c->stream));
-        c->launches += 2;    // DeviceScanInitKernel + DeviceScanKernel
-        TB_CUDA(c, cudaMemcpyAsync(c->h_total, c->prim_off + threads, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        TB_CUDA(c, cudaEventRecord(c->ev_total, c->stream));
+        const bool have_count = c->count_valid && c->count_wh[0] == c->W && c->count_wh[1] == c->H &&
+                                c->count_vs[0] == c->state.viewSize[0] && c->count_vs[1] == c->state.viewSize[1];
+        if (!have_count) {      // the count did not ride in k_integrate (or the draw parameters changed since)
+            TB_CUDA(c, cudaMemsetAsync(c->prim_off, 0, (threads + 1) * sizeof(uint32_t), c->stream));
+            SplatArgs A = splat_args(c);
+            k_splat_count<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
+            if (int r = check_launch(c, "k_splat_count")) return r;
+            if (int r = scan_counts(c)) return r;
+        }
+        c->count_valid = false;                                // consumed: the offsets are about to be used
         TB_CUDA(c, cudaEventSynchronize(c->ev_total));        // the sort needs the count on the host
         if (int r = ensure_frag_cap(c, *c->h_total)) return r;
         c->last_frags = *c->h_total;
@@ -293,6 +310,7 @@ int fold(tb_ctx *c) {
 // buffers[0]; explicit targets FBO -> no rotation.  `particles` is buffers[1] either way.
 float4 *spawn_out(tb_ctx *c, tb_target target) {
     if (target == TB_TARGET_TARGETS) return c->targets;
+    c->count_valid = false;
     std::swap(c->buf[0], c->buf[1]);
     return c->buf[0];
 }
@@ -368,7 +386,9 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     }
     TB_TRY(cudaEventCreateWithFlags(&c->ev_state, cudaEventDisableTiming));
     TB_TRY(cudaEventCreateWithFlags(&c->ev_noise, cudaEventDisableTiming));
-    c->overlap = std::getenv("TB_NO_OVERLAP") == nullptr;
+    // Opt-in (TB_OVERLAP=1): measured +4.7 % step throughput at cfg3, but the low-priority noise launch is
+    // time-sliced under the sort, which makes its own duration meaningless as a roofline input.
+    c->overlap = std::getenv("TB_OVERLAP") != nullptr;
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));
@@ -392,6 +412,19 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
         TB_TRY(cudaMemcpyAsync(c->pairs, pairs.data(), pairs.size() * sizeof(PairEntry), cudaMemcpyHostToDevice, c->stream));
         TB_TRY(cudaStreamSynchronize(c->stream));
     }
+    {
+        std::vector<int32_t> rp(static_cast<size_t>(PH), -1);
+        c->fuse_count = !pairs.empty();
+        for (size_t k = 0; k < pairs.size(); ++k) {
+            const int ra = pairs[k].row_a & 0x7fffffff, rb = pairs[k].row_b & 0x7fffffff;
+            const bool ca = pairs[k].row_a < 0, cb = pairs[k].row_b < 0;
+            if (ra != rb || ca == cb || k >= (1u << 30)) { c->fuse_count = false; break; }
+            rp[static_cast<size_t>(ra)] = static_cast<int32_t>(static_cast<uint32_t>(k) | ((cb ? 1u : 2u) << 30));   // 1: prev->cur, 2: cur->prev
+        }
+        TB_TRY(cudaMalloc(&c->row_pair, rp.size() * sizeof(int32_t)));
+        TB_TRY(cudaMemcpyAsync(c->row_pair, rp.data(), rp.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        TB_TRY(cudaStreamSynchronize(c->stream));
+    }
     c->n_prims = static_cast<long long>(col1 - col0) * c->n_pairs;
     if (c->n_prims >= (1LL << 31)) { c->err = "tendrils-b200: too many primitives per context"; return bail(TB_ERR_INVALID); }
     TB_TRY(cudaMalloc(&c->prim_off, (c->n_prims + 1) * sizeof(uint32_t)));
@@ -413,7 +446,7 @@ int tb_destroy(tb_ctx *c) {
     if (c->side) cudaStreamSynchronize(c->side);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
-    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off);
+    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off); cudaFree(c->row_pair);
     cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->hot); cudaFree(c->d_flag);
     for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); }
     if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -485,6 +518,12 @@ int tb_step(tb_ctx *c, float time, float dt) {
     A.packed_noise = scalar_noise ? 0 : 1;
     A.pk.one = 1.0f; A.pk.neg_one = -1.0f; A.pk.neg_zero = -0.0f;
     A.wander = c->wander;
+    const bool fuse = c->fuse_count && c->n_prims > 0;
+    A.row_pair = c->row_pair;
+    A.prim_off = fuse ? c->prim_off : nullptr;
+    A.n_pairs = c->n_pairs;
+    c->count_valid = false;
+    if (fuse) TB_CUDA(c, cudaMemsetAsync(c->prim_off, 0, (c->n_prims + 1) * sizeof(uint32_t), c->stream));
     const dim3 grid(blocks_for(c->PH, 256), static_cast<unsigned>(A.cols));
     if (A.use_noise && c->overlap && c->splat_since_step) {
         // The noise does not read the flow grid: evaluate it on the low-priority side stream, where it
@@ -511,6 +550,14 @@ int tb_step(tb_ctx *c, float time, float dt) {
     TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     c->ev_count[0] += 1;
     c->splat_since_step = false;
+    if (fuse) {
+        // the scan and the 4-byte total travel to the host now, so that the next tb_splat_flow finds the
+        // fragment count waiting instead of stalling the GPU on a round trip
+        if (int r = scan_counts(c)) return r;
+        c->count_valid = true;
+        c->count_wh[0] = c->W; c->count_wh[1] = c->H;
+        c->count_vs[0] = S.viewSize[0]; c->count_vs[1] = S.viewSize[1];
+    }
     return TB_OK;
 }
 
@@ -535,6 +582,7 @@ int tb_splat_flow(tb_ctx *c, float time) {
 
 int tb_reset(tb_ctx *c) {
     TB_REQUIRE(c, c, "null context");
+    c->count_valid = false;
     TB_CUDA(c, cudaSetDevice(c->device));
     for (int b = 0; b < 2; ++b) {
         k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(c->buf[b], c->n_local);
@@ -651,6 +699,7 @@ int tb_upload(tb_ctx *c, tb_buffer which, const float *host, int64_t n_floats) {
     float4 *dst; int64_t n;
     if (int r = buffer_of(c, which, &dst, &n)) return r;
     TB_REQUIRE(c, n == n_floats, "tb_upload: size mismatch");
+    if (which != TB_BUF_FLOW && which != TB_BUF_TARGETS) c->count_valid = false;
     TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaMemcpyAsync(dst, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -44,9 +44,59 @@ struct IntegrateArgs {
     int pow2_res;          // 1: PW and PH are powers of two: x/res == x*(1/res) exactly
     float inv_resx, inv_resy, inv_n;
     PackedConsts pk;       // 1, -1, -0 (opaque to the compiler on purpose)
+    // fused first pass of the flow splat: fragments of this particle's line, in draw order
+    const int32_t *__restrict__ row_pair;   // per row: 0xffffffff, or pair index | kind << 30 (1: prev->cur, 2: cur->prev)
+    uint32_t *__restrict__ prim_off;        // zeroed beforehand; null when the count is not fused
+    int n_pairs;
 };
 
 // a3: src/logic.frag:45-101.  One thread per particle, 16 B in / 16 B out, flow gather via L2.
+// RASTER-1 (spec/PARITY.md): GL_LINES of width 1, centre-sampled along the major axis, half-open
+// towards the second vertex, scissored to the grid.  emit(gx, gy, t) per fragment.
+template <class Emit>
+__device__ __forceinline__ void raster_line(float xa, float ya, float xb, float yb, int W, int H, Emit &&emit) {
+    const float dx = __fsub_rn(xb, xa), dy = __fsub_rn(yb, ya);
+    const float adx = fabsf(dx), ady = fabsf(dy);
+    const bool xmajor = adx >= ady;
+    // major/minor axis views
+    const float ma = xmajor ? xa : ya, mb = xmajor ? xb : yb, dm = xmajor ? dx : dy;
+    const float na = xmajor ? ya : xa, dn = xmajor ? dy : dx;
+    const int M = xmajor ? W : H, N = xmajor ? H : W;
+    if (!(fabsf(dm) > 0.0f)) return;
+    float flo = __fsub_rn(floorf(gmin(ma, mb)), 1.0f), fhi = __fadd_rn(floorf(gmax(ma, mb)), 1.0f);
+    if (flo < 0.0f) flo = 0.0f;
+    if (fhi > static_cast<float>(M - 1)) fhi = static_cast<float>(M - 1);
+    if (!(flo <= fhi)) return;
+    const int ihi = static_cast<int>(fhi);
+    for (int i = static_cast<int>(flo); i <= ihi; ++i) {
+        const float ic = __fadd_rn(static_cast<float>(i), 0.5f);
+        const bool in = (dm > 0.0f) ? (ma <= ic && ic < mb) : (mb < ic && ic <= ma);
+        if (!in) continue;
+        const float t = __fdiv_rn(__fsub_rn(ic, ma), dm);
+        const float nn = __fadd_rn(na, __fmul_rn(t, dn));
+        const float fj = floorf(nn);
+        if (!(fj >= 0.0f && fj <= static_cast<float>(N - 1))) continue;
+        const int j = static_cast<int>(fj);
+        emit(xmajor ? i : j, xmajor ? j : i, t);
+    }
+}
+
+// Loads the two vertices of pair (column, entry) and hands window coordinates + colours on.
+// window coordinates of a vertex (PARITY V3) and the cull rules V1/V2 shared by every splat pass
+__device__ __forceinline__ bool splat_vertex_ok(const float4 &s) {
+    if (!(s.x != kInert || s.y != kInert)) return false;
+    return is_finite(s.x) && is_finite(s.y) && is_finite(s.z) && is_finite(s.w);
+}
+__device__ __forceinline__ uint32_t count_fragments(const float4 &sa, const float4 &sb, float vsx, float vsy, int W, int H) {
+    if (!splat_vertex_ok(sa) || !splat_vertex_ok(sb)) return 0u;
+    const float hw = __fmul_rn(0.5f, static_cast<float>(W)), hh = __fmul_rn(0.5f, static_cast<float>(H));
+    const float xa = __fadd_rn(__fmul_rn(__fmul_rn(sa.x, vsx), hw), hw), ya = __fadd_rn(__fmul_rn(__fmul_rn(sa.y, vsy), hh), hh);
+    const float xb = __fadd_rn(__fmul_rn(__fmul_rn(sb.x, vsx), hw), hw), yb = __fadd_rn(__fmul_rn(__fmul_rn(sb.y, vsy), hh), hh);
+    uint32_t n = 0;
+    raster_line(xa, ya, xb, yb, W, H, [&](int, int, float) { ++n; });
+    return n;
+}
+
 #ifndef TB_INTEGRATE_MIN_BLOCKS
 #define TB_INTEGRATE_MIN_BLOCKS 5
 #endif
@@ -142,7 +192,17 @@ __global__ void __launch_bounds__(256, TB_INTEGRATE_MIN_BLOCKS) k_integrate(cons
     const float sc = __fdiv_rn(gmin(speed, S.speedLimit), speed);
     nvx = __fmul_rn(nvx, sc);
     nvy = __fmul_rn(nvy, sc);
-    __stcs(A.out + l, make_float4(__fadd_rn(posx, nvx), __fadd_rn(posy, nvy), nvx, nvy));
+    const float4 nst = make_float4(__fadd_rn(posx, nvx), __fadd_rn(posy, nvy), nvx, nvy);
+    __stcs(A.out + l, nst);
+    // Pass 1 of the flow splat, fused: previous and current state of this particle are both in registers.
+    if (A.prim_off != nullptr) {
+        const uint32_t rp = static_cast<uint32_t>(__ldg(A.row_pair + y));
+        if (rp != 0xffffffffu) {
+            const bool forward = (rp >> 30) == 1u;
+            const uint32_t n = count_fragments(forward ? st : nst, forward ? nst : st, S.viewSize[0], S.viewSize[1], A.W, A.H);
+            A.prim_off[static_cast<size_t>(blockIdx.y) * A.n_pairs + (rp & 0x3fffffffu)] = n;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -167,35 +227,6 @@ struct SplatArgs {
     const uint32_t *total; // device: total fragments of this collect (after the scan)
 };
 
-template <class Emit>
-__device__ __forceinline__ void raster_line(float xa, float ya, float xb, float yb, int W, int H, Emit &&emit) {
-    const float dx = __fsub_rn(xb, xa), dy = __fsub_rn(yb, ya);
-    const float adx = fabsf(dx), ady = fabsf(dy);
-    const bool xmajor = adx >= ady;
-    // major/minor axis views
-    const float ma = xmajor ? xa : ya, mb = xmajor ? xb : yb, dm = xmajor ? dx : dy;
-    const float na = xmajor ? ya : xa, dn = xmajor ? dy : dx;
-    const int M = xmajor ? W : H, N = xmajor ? H : W;
-    if (!(fabsf(dm) > 0.0f)) return;
-    float flo = __fsub_rn(floorf(gmin(ma, mb)), 1.0f), fhi = __fadd_rn(floorf(gmax(ma, mb)), 1.0f);
-    if (flo < 0.0f) flo = 0.0f;
-    if (fhi > static_cast<float>(M - 1)) fhi = static_cast<float>(M - 1);
-    if (!(flo <= fhi)) return;
-    const int ihi = static_cast<int>(fhi);
-    for (int i = static_cast<int>(flo); i <= ihi; ++i) {
-        const float ic = __fadd_rn(static_cast<float>(i), 0.5f);
-        const bool in = (dm > 0.0f) ? (ma <= ic && ic < mb) : (mb < ic && ic <= ma);
-        if (!in) continue;
-        const float t = __fdiv_rn(__fsub_rn(ic, ma), dm);
-        const float nn = __fadd_rn(na, __fmul_rn(t, dn));
-        const float fj = floorf(nn);
-        if (!(fj >= 0.0f && fj <= static_cast<float>(N - 1))) continue;
-        const int j = static_cast<int>(fj);
-        emit(xmajor ? i : j, xmajor ? j : i, t);
-    }
-}
-
-// Loads the two vertices of pair (column, entry) and hands window coordinates + colours on.
 // Threads are numbered in draw order: tid = local column * n_pairs + index of the active pair.
 template <class Body>
 __device__ __forceinline__ void splat_pair(const SplatArgs &A, Body &&body) {
