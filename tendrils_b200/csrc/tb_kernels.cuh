@@ -14,10 +14,34 @@ static constexpr float kInert = -1000000.0f;   // src/const/inert.glsl:1
 // channel is the uniform `time` at both vertices, hence constant along the line.  Fragments
 // are generated in primitive (draw) order p = x*PH + k (src/particles.js:182-186) and stably
 // sorted by texel, so the order within a texel's segment is the draw order.
+#ifndef TB_FRAG_BYTES
+#define TB_FRAG_BYTES 16
+#endif
+#if TB_FRAG_BYTES == 16
+struct __align__(16) FragVal {   // padded to 16 B: one 128-bit load/store per fragment in emit, sort and fold
+    float cx, cy;     // interpolated vel.xy
+    float a;          // interpolated alpha
+    float pad;
+};
+__device__ __forceinline__ FragVal load_frag(const FragVal *p) {
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
+    FragVal f; f.cx = v.x; f.cy = v.y; f.a = v.z; f.pad = 0.f;
+    return f;
+}
+__device__ __forceinline__ void store_frag(FragVal *p, float cx, float cy, float a) {
+    *reinterpret_cast<float4 *>(p) = make_float4(cx, cy, a, 0.f);
+}
+#else
 struct FragVal {
     float cx, cy;     // interpolated vel.xy
     float a;          // interpolated alpha
 };
+__device__ __forceinline__ FragVal load_frag(const FragVal *p) {
+    FragVal f; f.cx = __ldcs(&p->cx); f.cy = __ldcs(&p->cy); f.a = __ldcs(&p->a);
+    return f;
+}
+__device__ __forceinline__ void store_frag(FragVal *p, float cx, float cy, float a) { p->cx = cx; p->cy = cy; p->a = a; }
+#endif
 
 // Line pair k of a column: which texel row and which buffer each of its 2 vertices samples
 // (src/particles.js:171-190 seen through src/state/state-at-frame.glsl:12-22).
@@ -63,7 +87,9 @@ __device__ __forceinline__ void raster_line(float xa, float ya, float xb, float 
     const float na = xmajor ? ya : xa, dn = xmajor ? dy : dx;
     const int M = xmajor ? W : H, N = xmajor ? H : W;
     if (!(fabsf(dm) > 0.0f)) return;
-    float flo = __fsub_rn(floorf(gmin(ma, mb)), 1.0f), fhi = __fadd_rn(floorf(gmax(ma, mb)), 1.0f);
+    // Candidate columns: a superset of those whose centre i + 0.5 lies within [min, max]; the membership
+    // test below is the definition.  lo - 0.5 and hi - 0.5 are exact wherever they matter (0.5 <= v < 2^22).
+    float flo = floorf(__fsub_rn(gmin(ma, mb), 0.5f)), fhi = floorf(__fsub_rn(gmax(ma, mb), 0.5f));
     if (flo < 0.0f) flo = 0.0f;
     if (fhi > static_cast<float>(M - 1)) fhi = static_cast<float>(M - 1);
     if (!(flo <= fhi)) return;
@@ -269,15 +295,14 @@ __global__ void __launch_bounds__(256) k_splat_emit(const SplatArgs A) {
         const float ab = gmin(__fdiv_rn(glength(sb.z, sb.w), A.speedLimit), 1.0f);
         uint32_t slot = A.prim_off[tid];
         raster_line(xa, ya, xb, yb, A.W, A.H, [&](int gx, int gy, float t) {
-            FragVal f;
-            f.cx = __fadd_rn(sa.z, __fmul_rn(t, __fsub_rn(sb.z, sa.z)));
-            f.cy = __fadd_rn(sa.w, __fmul_rn(t, __fsub_rn(sb.w, sa.w)));
-            f.a = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
+            const float fcx = __fadd_rn(sa.z, __fmul_rn(t, __fsub_rn(sb.z, sa.z)));
+            const float fcy = __fadd_rn(sa.w, __fmul_rn(t, __fsub_rn(sb.w, sa.w)));
+            const float fa = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
             // bit 31 flags a fragment whose alpha is exactly 1; it rides along the sort (which only
             // looks at the texel bits) and lets the fold skip everything such a fragment overwrites
             A.keys[slot] = (static_cast<uint32_t>(gy) * static_cast<uint32_t>(A.W) + static_cast<uint32_t>(gx)) |
-                           (f.a == 1.0f ? kOpaqueBit : 0u);
-            A.vals[slot] = f;
+                           (fa == 1.0f ? kOpaqueBit : 0u);
+            store_frag(A.vals + slot, fcx, fcy, fa);
             ++slot;
         });
     });
@@ -397,7 +422,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restri
 #pragma unroll
         for (int j = 0; j < kFoldPer; ++j) {
             const uint32_t i = c0 + j * 32 + lane;
-            if (i < hi) { rcx[j] = __ldcs(&vals[i].cx); rcy[j] = __ldcs(&vals[i].cy); ra[j] = __ldcs(&vals[i].a); }
+            if (i < hi) { const FragVal f = load_frag(vals + i); rcx[j] = f.cx; rcy[j] = f.cy; ra[j] = f.a; }
         }
     };
     float4 d = has ? flow[t] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -441,7 +466,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(float4 *__re
 #pragma unroll
             for (int j = 0; j < kFoldPer; ++j) {
                 const uint32_t i = c0 + j * 32 + lane;
-                if (i < se.y) { rcx[j] = __ldcs(&vals[i].cx); rcy[j] = __ldcs(&vals[i].cy); ra[j] = __ldcs(&vals[i].a); }
+                if (i < se.y) { const FragVal f = load_frag(vals + i); rcx[j] = f.cx; rcy[j] = f.cy; ra[j] = f.a; }
             }
         };
         prefetch(se.x);
