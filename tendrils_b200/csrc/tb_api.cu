@@ -63,8 +63,9 @@ struct tb_ctx {
     size_t sort_tmp_bytes = 0;
     uint32_t frag_cap = 0;
     uint32_t *seg = nullptr;               // 2*G: [begin,end) of every texel's sorted segment
-    uint32_t *hot = nullptr;               // [0] = count, [1..G] = worklist of hot texels
+    uint32_t *hot = nullptr;               // [0] = count, [1] = cursor, [2..G+1] = worklist of hot texels
     int n_sms = 148;
+    uint32_t hot_threshold = kFoldHot;
     int key_bits = 1;
     uint32_t *h_total = nullptr;           // pinned
     cudaEvent_t ev_total = nullptr;
@@ -169,7 +170,7 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     const size_t G = static_cast<size_t>(w) * h;
     TB_CUDA(c, cudaMalloc(&c->flow, G * sizeof(float4)));
     TB_CUDA(c, cudaMalloc(&c->seg, 2 * G * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->hot, (G + 1) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->hot, (G + 2) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMemsetAsync(c->flow, 0, G * sizeof(float4), c->stream));
     c->key_bits = 1;
     while ((1ull << c->key_bits) < G) c->key_bits += 1;
@@ -281,7 +282,7 @@ int collect(tb_ctx *c, float time) {
                                                    c->vals[1], static_cast<int64_t>(F), 0, c->key_bits, c->stream));
         c->launches += 1 + (c->key_bits + 7) / 8;   // histogram + one onesweep pass per 8 key bits (+ scan, not counted)
         TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * G * sizeof(uint32_t), c->stream));
-        k_splat_bounds<<<blocks_for(F, 256), 256, 0, c->stream>>>(c->keys[1], F, c->seg);
+        k_splat_bounds<<<blocks_for((static_cast<long long>(F) + 3) / 4, 256), 256, 0, c->stream>>>(c->keys[1], F, c->seg);
         if (int r = check_launch(c, "k_splat_bounds")) return r;
     }
     c->collected = true;
@@ -294,10 +295,10 @@ int fold(tb_ctx *c) {
     if (c->last_frags > 0) {
         TB_CUDA(c, cudaMemsetAsync(c->hot, 0, sizeof(uint32_t), c->stream));
         k_splat_fold<<<blocks_for(G, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
-            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], G, c->collect_time, c->hot, c->hot + 1);
+            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], G, c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
         if (int r = check_launch(c, "k_splat_fold")) return r;
         k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
-            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 1);
+            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2);
         if (int r = check_launch(c, "k_splat_fold_hot")) return r;
     }
     TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
@@ -389,6 +390,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     // Opt-in (TB_OVERLAP=1): measured +4.7 % step throughput at cfg3, but the low-priority noise launch is
     // time-sliced under the sort, which makes its own duration meaningless as a roofline input.
     c->overlap = std::getenv("TB_OVERLAP") != nullptr;
+    if (const char *e = std::getenv("TB_FOLD_HOT")) c->hot_threshold = static_cast<uint32_t>(std::max(1, std::atoi(e)));
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));

@@ -118,6 +118,32 @@ __device__ __forceinline__ uint32_t count_fragments(const float4 &sa, const floa
     const float hw = __fmul_rn(0.5f, static_cast<float>(W)), hh = __fmul_rn(0.5f, static_cast<float>(H));
     const float xa = __fadd_rn(__fmul_rn(__fmul_rn(sa.x, vsx), hw), hw), ya = __fadd_rn(__fmul_rn(__fmul_rn(sa.y, vsy), hh), hh);
     const float xb = __fadd_rn(__fmul_rn(__fmul_rn(sb.x, vsx), hw), hw), yb = __fadd_rn(__fmul_rn(__fmul_rn(sb.y, vsy), hh), hh);
+    // Closed form when the line stays clear of the minor-axis borders: then every candidate column whose
+    // centre passes the membership test yields a fragment, interior candidates always pass (their centres
+    // lie strictly between the endpoints), and only the two end candidates need testing.  Same count as
+    // the loop, without its per-fragment division.
+    {
+        const float dx = __fsub_rn(xb, xa), dy = __fsub_rn(yb, ya);
+        const bool xmajor = fabsf(dx) >= fabsf(dy);
+        const float ma = xmajor ? xa : ya, mb = xmajor ? xb : yb, dm = xmajor ? dx : dy;
+        const float na = xmajor ? ya : xa, nb = xmajor ? yb : xb;
+        const int M = xmajor ? W : H, N = xmajor ? H : W;
+        if (!(fabsf(dm) > 0.0f)) return 0u;
+        if (gmin(na, nb) >= 1.0f && gmax(na, nb) <= static_cast<float>(N - 1)) {
+            float flo = floorf(__fsub_rn(gmin(ma, mb), 0.5f)), fhi = floorf(__fsub_rn(gmax(ma, mb), 0.5f));
+            if (flo < 0.0f) flo = 0.0f;
+            if (fhi > static_cast<float>(M - 1)) fhi = static_cast<float>(M - 1);
+            if (!(flo <= fhi)) return 0u;
+            auto member = [&](float fi) {
+                const float ic = __fadd_rn(fi, 0.5f);
+                return (dm > 0.0f) ? (ma <= ic && ic < mb) : (mb < ic && ic <= ma);
+            };
+            uint32_t n = static_cast<uint32_t>(static_cast<int>(fhi) - static_cast<int>(flo)) + 1u;
+            if (!member(flo)) --n;
+            if (fhi != flo && !member(fhi)) --n;
+            return n;
+        }
+    }
     uint32_t n = 0;
     raster_line(xa, ya, xb, yb, W, H, [&](int, int, float) { ++n; });
     return n;
@@ -316,12 +342,27 @@ __global__ void __launch_bounds__(256) k_splat_emit(const SplatArgs A) {
 // finite under this blend) -- so folding from it onto the ORIGINAL texel is exact.
 // seg is zero-filled beforehand (empty segments stay [0,0)).
 __global__ void __launch_bounds__(256) k_splat_bounds(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ seg) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t raw = keys[i], k = raw & ~kOpaqueBit;
-    const bool first = (i == 0) || ((keys[i - 1] & ~kOpaqueBit) != k);
-    if (first || (raw & kOpaqueBit)) atomicMax(&seg[2 * k], i);
-    if (i == n - 1 || (keys[i + 1] & ~kOpaqueBit) != k) seg[2 * k + 1] = i + 1;
+    // four consecutive keys per thread (one 128-bit load) plus the two neighbours
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i0 >= n) return;
+    uint32_t k[6];
+    k[0] = i0 ? keys[i0 - 1] : 0u;
+    if (i0 + 4 <= n) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(keys + i0);
+        k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+    } else {
+        for (uint32_t j = 0; j < 4; ++j) k[1 + j] = (i0 + j < n) ? keys[i0 + j] : 0u;
+    }
+    k[5] = (i0 + 4 < n) ? keys[i0 + 4] : 0u;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t i = i0 + j;
+        if (i >= n) break;
+        const uint32_t raw = k[1 + j], t = raw & ~kOpaqueBit;
+        const bool first = (i == 0) || ((k[j] & ~kOpaqueBit) != t);
+        if (first || (raw & kOpaqueBit)) atomicMax(&seg[2 * t], i);
+        if (i == n - 1 || (k[2 + j] & ~kOpaqueBit) != t) seg[2 * t + 1] = i + 1;
+    }
 }
 
 // Pass 5: ordered alpha-over fold: blendFunc(SRC_ALPHA, ONE_MINUS_SRC_ALPHA) on all four
@@ -395,7 +436,8 @@ __device__ __forceinline__ void stage_terms(FoldTerm *term, float *om, const flo
 
 __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restrict__ flow, const uint2 *__restrict__ seg,
                                                                  const FragVal *__restrict__ vals, int G, float time,
-                                                                 uint32_t *__restrict__ hot_count, uint32_t *__restrict__ hot_list) {
+                                                                 uint32_t *__restrict__ hot_count, uint32_t *__restrict__ hot_list,
+                                                                 uint32_t hot_threshold) {
     __shared__ FoldTerm s_term[kFoldWarps][kFoldChunk];
     __shared__ float s_om[kFoldWarps][kFoldChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -403,7 +445,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restri
     uint2 se = make_uint2(0u, 0u);
     if (t < G) se = seg[t];
     bool has = se.y > se.x;
-    if (has && se.y - se.x > kFoldHot) {                // hot texel: a whole warp will fold it
+    if (has && se.y - se.x > hot_threshold) {           // hot texel: a whole warp will fold it
         hot_list[atomicAdd(hot_count, 1u)] = static_cast<uint32_t>(t);
         has = false;
     }
