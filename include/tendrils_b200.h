@@ -141,6 +141,17 @@ int tb_splat_flow(tb_ctx *ctx, float time);
 int tb_splat_collect(tb_ctx *ctx, float time);
 int tb_splat_fold(tb_ctx *ctx);
 
+/* The ordered fold of a column-sharded run over peer memory (one process per GPU, one node).  Every rank
+ * exports IPC handles of its flow grid / inbox / flags (tb_ring_export, tb_ring_handle_bytes() bytes), the host
+ * layer exchanges them (any transport), and each rank maps those of rank+1 (tb_ring_connect).  After
+ * tb_splat_collect, tb_splat_fold_ring folds chunk by chunk: wait for the previous rank's chunk, blend this
+ * rank's fragments onto it, write the result straight into the next rank's inbox over NVLink; the last rank's
+ * result is the new grid and travels once around the ring.  Must be redone after tb_resize_flow. */
+int64_t tb_ring_handle_bytes(void);
+int tb_ring_export(tb_ctx *ctx, void *handles_out, int64_t n_bytes);
+int tb_ring_connect(tb_ctx *ctx, int32_t rank, int32_t world, const void *next_rank_handles, int64_t n_bytes);
+int tb_splat_fold_ring(tb_ctx *ctx);
+
 /* Tendrils.spawn(cpuFn) with the default initSpawner: fills ALL buffers
  * (src/index.js:425-429, src/particles.js:94-117, src/spawn/init/cpu.js:3-8). */
 int tb_reset(tb_ctx *ctx);

@@ -66,6 +66,20 @@ struct tb_ctx {
     uint32_t *hot = nullptr;               // [0] = count, [1] = cursor, [2..G+1] = worklist of hot texels
     int n_sms = 148;
     uint32_t hot_threshold = kFoldHot;
+
+    // sharded ring fold over peer memory (tb_ring_*): my inbox + flags, the next rank's mapped over NVLink
+    static constexpr int kRingMaxChunks = 64;
+    int ring_chunks = 16;
+    int ring_rank = 0, ring_world = 1;
+    float4 *inbox = nullptr;               // the previous rank writes its folded chunks here
+    uint32_t *ring_flags = nullptr;        // [0..C): inbox chunk ready (epoch), [C..2C): final chunk in my grid (epoch)
+    uint32_t *ring_hot_counts = nullptr;   // per chunk hot-texel counters
+    float4 *next_inbox = nullptr, *next_flow = nullptr;
+    uint32_t *next_flags = nullptr;
+    bool ring_connected = false;
+    uint32_t ring_epoch = 0;
+    cudaStream_t ring_stream = nullptr;    // forwards final chunks around the ring
+    cudaEvent_t ev_ring_fwd = nullptr, ev_ring_begin = nullptr;
     int key_bits = 1;
     uint32_t *h_total = nullptr;           // pinned
     cudaEvent_t ev_total = nullptr;
@@ -160,7 +174,10 @@ bool columns_are_identity(int PW) {
     return true;
 }
 
+int ring_release(tb_ctx *c);
+
 int alloc_flow(tb_ctx *c, int w, int h) {
+    ring_release(c);
     TB_REQUIRE(c, w >= 1 && h >= 1 && static_cast<long long>(w) * h < (1LL << 31), "flow grid dimensions out of bounds");
     if (c->flow) cudaFree(c->flow);
     if (c->seg) cudaFree(c->seg);
@@ -293,12 +310,15 @@ int fold(tb_ctx *c) {
     TB_REQUIRE(c, c->collected, "tb_splat_fold without a preceding tb_splat_collect");
     const int G = c->W * c->H;
     if (c->last_frags > 0) {
+        FoldIO io{};
+        io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
+        io.t_begin = 0; io.t_end = G; io.copy_all = 0;
         TB_CUDA(c, cudaMemsetAsync(c->hot, 0, sizeof(uint32_t), c->stream));
         k_splat_fold<<<blocks_for(G, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
-            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], G, c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
+            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
         if (int r = check_launch(c, "k_splat_fold")) return r;
         k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
-            c->flow, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2);
+            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2);
         if (int r = check_launch(c, "k_splat_fold_hot")) return r;
     }
     TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
@@ -334,7 +354,153 @@ bool tame(float v, float lim) { return std::isfinite(v) && std::fabs(v) < lim; }
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Sharded ring fold over peer memory
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct RingHandles {                 // what tb_ring_export hands to the neighbour (3 x 64 bytes + sizes)
+    cudaIpcMemHandle_t flow, inbox, flags;
+    int32_t w, h, chunks, pad;
+};
+
+int ring_release(tb_ctx *c) {
+    if (c->next_inbox) cudaIpcCloseMemHandle(c->next_inbox);
+    if (c->next_flow) cudaIpcCloseMemHandle(c->next_flow);
+    if (c->next_flags) cudaIpcCloseMemHandle(c->next_flags);
+    c->next_inbox = c->next_flow = nullptr;
+    c->next_flags = nullptr;
+    c->ring_connected = false;
+    return TB_OK;
+}
+
+// The ordered fold of a column-sharded run, chunk by chunk:
+//   rank r waits for chunk k of its inbox (rank 0: reads its own grid), folds its fragments onto it and
+//   writes the result straight into rank r+1's inbox over NVLink, then raises that rank's flag;
+//   the last rank's result is final: it goes to its own grid and to rank 0's, and travels on around the
+//   ring (ring_stream) so that every rank ends the step with the same grid.
+// Fold order = rank order = primitive order, so the result equals the single-GPU fold bit for bit.
+int ring_fold(tb_ctx *c) {
+    TB_REQUIRE(c, c->collected, "tb_splat_fold_ring without a preceding tb_splat_collect");
+    TB_REQUIRE(c, c->ring_connected, "tb_ring_connect must be called first");
+    const int G = c->W * c->H, C = c->ring_chunks;
+    const int r = c->ring_rank, P = c->ring_world;
+    const bool first = r == 0, last = r == P - 1;
+    const uint32_t epoch = ++c->ring_epoch;
+    const int per = ((G + C - 1) / C + 127) / 128 * 128;                 // texels per chunk, CTA aligned
+    uint32_t *in_flag = c->ring_flags, *fin_flag = c->ring_flags + C;
+    TB_CUDA(c, cudaMemsetAsync(c->ring_hot_counts, 0, C * sizeof(uint32_t), c->stream));
+    if (c->last_frags == 0)   // no fragments on this rank: collect() left the segments of an earlier draw behind
+        TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * static_cast<size_t>(G) * sizeof(uint32_t), c->stream));
+    TB_CUDA(c, cudaEventRecord(c->ev_ring_begin, c->stream));
+    TB_CUDA(c, cudaStreamWaitEvent(c->ring_stream, c->ev_ring_begin, 0));
+    for (int k = 0; k < C; ++k) {
+        const int t0 = std::min(G, k * per), t1 = std::min(G, (k + 1) * per);
+        if (t0 >= t1) continue;
+        FoldIO io{};
+        io.src = first ? c->flow : c->inbox;
+        io.dst = last ? c->flow : c->next_inbox;
+        io.dst2 = (last && P > 1) ? c->next_flow : nullptr;             // rank 0's grid
+        io.t_begin = t0; io.t_end = t1; io.copy_all = 1;
+        if (!first) {
+            k_ring_wait<<<1, 1, 0, c->stream>>>(in_flag + k, epoch);
+            if (int e = check_launch(c, "k_ring_wait")) return e;
+        }
+        k_splat_fold<<<blocks_for(t1 - t0, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
+            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2,
+            c->last_frags > 0 ? c->hot_threshold : 0xffffffffu);
+        if (int e = check_launch(c, "k_splat_fold")) return e;
+        k_splat_fold_hot<<<c->n_sms, kFoldWarps * 32, 0, c->stream>>>(
+            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2);
+        if (int e = check_launch(c, "k_splat_fold_hot")) return e;
+        // chunk k of the next rank's inbox (or, from the last rank, of rank 0's grid) is complete
+        k_ring_signal<<<1, 1, 0, c->stream>>>(last ? c->next_flags + C + k : c->next_flags + k, epoch);
+        if (int e = check_launch(c, "k_ring_signal")) return e;
+    }
+    // final chunks travel 0 -> 1 -> ... -> P-2 (the last rank already has them)
+    if (!last) {
+        for (int k = 0; k < C; ++k) {
+            const int t0 = std::min(G, k * per), t1 = std::min(G, (k + 1) * per);
+            if (t0 >= t1) continue;
+            k_ring_wait<<<1, 1, 0, c->ring_stream>>>(fin_flag + k, epoch);
+            if (int e = check_launch(c, "k_ring_wait")) return e;
+            if (r < P - 2) {
+                TB_CUDA(c, cudaMemcpyAsync(c->next_flow + t0, c->flow + t0, static_cast<size_t>(t1 - t0) * sizeof(float4),
+                                           cudaMemcpyDeviceToDevice, c->ring_stream));
+                k_ring_signal<<<1, 1, 0, c->ring_stream>>>(c->next_flags + C + k, epoch);
+                if (int e = check_launch(c, "k_ring_signal")) return e;
+            }
+        }
+        TB_CUDA(c, cudaEventRecord(c->ev_ring_fwd, c->ring_stream));
+        TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_ring_fwd, 0));    // the next integrate reads the final grid
+    }
+    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
+    c->ev_count[1] += 1;
+    c->collected = false;
+    return TB_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
+int tb_ring_export(tb_ctx *c, void *out, int64_t n_bytes) {
+    TB_REQUIRE(c, c && out, "null argument");
+    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(RingHandles)), "tb_ring_export: buffer must be tb_ring_handle_bytes() long");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const size_t G = static_cast<size_t>(c->W) * c->H;
+    if (const char *e = std::getenv("TB_RING_CHUNKS")) c->ring_chunks = std::max(1, std::min<int>(tb_ctx::kRingMaxChunks, std::atoi(e)));
+    const int C = c->ring_chunks;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    ring_release(c);
+    if (c->inbox) cudaFree(c->inbox);
+    if (c->ring_flags) cudaFree(c->ring_flags);
+    if (c->ring_hot_counts) cudaFree(c->ring_hot_counts);
+    c->inbox = nullptr; c->ring_flags = nullptr; c->ring_hot_counts = nullptr;
+    TB_CUDA(c, cudaMalloc(&c->inbox, G * sizeof(float4)));
+    TB_CUDA(c, cudaMalloc(&c->ring_flags, 2 * C * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->ring_hot_counts, C * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMemset(c->ring_flags, 0, 2 * C * sizeof(uint32_t)));
+    c->ring_epoch = 0;
+    if (!c->ring_stream) {
+        TB_CUDA(c, cudaStreamCreateWithFlags(&c->ring_stream, cudaStreamNonBlocking));
+        TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_ring_fwd, cudaEventDisableTiming));
+        TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_ring_begin, cudaEventDisableTiming));
+    }
+    RingHandles hnd{};
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flow, c->flow));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.inbox, c->inbox));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flags, c->ring_flags));
+    hnd.w = c->W; hnd.h = c->H; hnd.chunks = C;
+    std::memcpy(out, &hnd, sizeof(hnd));
+    return TB_OK;
+}
+
+int64_t tb_ring_handle_bytes(void) { return static_cast<int64_t>(sizeof(RingHandles)); }
+
+int tb_ring_connect(tb_ctx *c, int32_t rank, int32_t world, const void *next_rank_handles, int64_t n_bytes) {
+    TB_REQUIRE(c, c && next_rank_handles, "null argument");
+    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(RingHandles)), "tb_ring_connect: bad handle size");
+    TB_REQUIRE(c, world >= 2 && rank >= 0 && rank < world, "tb_ring_connect: bad rank/world");
+    TB_REQUIRE(c, c->inbox != nullptr, "tb_ring_export must be called before tb_ring_connect");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    RingHandles hnd;
+    std::memcpy(&hnd, next_rank_handles, sizeof(hnd));
+    TB_REQUIRE(c, hnd.w == c->W && hnd.h == c->H && hnd.chunks == c->ring_chunks, "tb_ring_connect: the next rank's flow grid has another shape");
+    ring_release(c);
+    TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_flow), hnd.flow, cudaIpcMemLazyEnablePeerAccess));
+    TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_inbox), hnd.inbox, cudaIpcMemLazyEnablePeerAccess));
+    TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_flags), hnd.flags, cudaIpcMemLazyEnablePeerAccess));
+    c->ring_rank = rank; c->ring_world = world;
+    c->ring_connected = true;
+    return TB_OK;
+}
+
+int tb_splat_fold_ring(tb_ctx *c) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    return ring_fold(c);
+}
 
 int tb_abi_version(void) { return TB_ABI_VERSION; }
 
@@ -458,6 +624,11 @@ int tb_destroy(tb_ctx *c) {
         for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
             for (int j = 0; j < 2; ++j)
                 if (c->ev_ring[k][i][j]) cudaEventDestroy(c->ev_ring[k][i][j]);
+    ring_release(c);
+    cudaFree(c->inbox); cudaFree(c->ring_flags); cudaFree(c->ring_hot_counts);
+    if (c->ring_stream) { cudaStreamSynchronize(c->ring_stream); cudaStreamDestroy(c->ring_stream); }
+    if (c->ev_ring_fwd) cudaEventDestroy(c->ev_ring_fwd);
+    if (c->ev_ring_begin) cudaEventDestroy(c->ev_ring_begin);
     if (c->ev_state) cudaEventDestroy(c->ev_state);
     if (c->ev_noise) cudaEventDestroy(c->ev_noise);
     if (c->side) cudaStreamDestroy(c->side);

@@ -434,20 +434,39 @@ __device__ __forceinline__ void stage_terms(FoldTerm *term, float *om, const flo
     }
 }
 
-__global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restrict__ flow, const uint2 *__restrict__ seg,
-                                                                 const FragVal *__restrict__ vals, int G, float time,
+// Where a fold launch reads and writes texels.  Single GPU: src = dst = the flow grid, the whole grid.
+// Sharded ring (tb_splat_fold_ring): one launch per grid chunk; src is this rank's inbox (rank 0: its own
+// grid), dst the NEXT rank's inbox mapped over NVLink (last rank: its own grid, dst2 = rank 0's grid), and
+// because src != dst every texel of the chunk is written, touched or not.
+struct FoldIO {
+    const float4 *src;
+    float4 *dst;
+    float4 *dst2;
+    int t_begin, t_end;
+    int copy_all;
+};
+
+__global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(const FoldIO io, const uint2 *__restrict__ seg,
+                                                                 const FragVal *__restrict__ vals, float time,
                                                                  uint32_t *__restrict__ hot_count, uint32_t *__restrict__ hot_list,
                                                                  uint32_t hot_threshold) {
     __shared__ FoldTerm s_term[kFoldWarps][kFoldChunk];
     __shared__ float s_om[kFoldWarps][kFoldChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = (blockIdx.x * kFoldWarps + warp) * 32 + lane;
+    const int t = io.t_begin + (blockIdx.x * kFoldWarps + warp) * 32 + lane;
     uint2 se = make_uint2(0u, 0u);
-    if (t < G) se = seg[t];
+    if (t < io.t_end) se = seg[t];
     bool has = se.y > se.x;
+    bool hot = false;
     if (has && se.y - se.x > hot_threshold) {           // hot texel: a whole warp will fold it
         hot_list[atomicAdd(hot_count, 1u)] = static_cast<uint32_t>(t);
         has = false;
+        hot = true;
+    }
+    if (io.copy_all && t < io.t_end && !has && !hot) {  // untouched texel: carry it over to the next buffer
+        const float4 v = io.src[t];
+        io.dst[t] = v;
+        if (io.dst2) io.dst2[t] = v;
     }
     // Segments are stored in texel order, so the warp's fragments lie in [lo, hi); fragments
     // overwritten by an opaque one (k_splat_bounds) and hot texels leave gaps between the lanes' ranges.
@@ -467,7 +486,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restri
             if (i < hi) { const FragVal f = load_frag(vals + i); rcx[j] = f.cx; rcy[j] = f.cy; ra[j] = f.a; }
         }
     };
-    float4 d = has ? flow[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 d = has ? io.src[t] : make_float4(0.f, 0.f, 0.f, 0.f);
     FoldTerm *term = s_term[warp];
     float *om = s_om[warp];
     uint32_t c0 = next_chunk(lo);
@@ -485,12 +504,15 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(float4 *__restri
         __syncwarp();
         c0 = cn;
     }
-    if (has) flow[t] = d;
+    if (has) {
+        io.dst[t] = d;
+        if (io.dst2) io.dst2[t] = d;
+    }
 }
 
 // One warp per hot texel: all lanes load and pre-multiply a chunk, lane 0 runs the blend chain
 // while the next chunk is already in flight.  Persistent over the worklist.
-__global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(float4 *__restrict__ flow, const uint2 *__restrict__ seg,
+__global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(const FoldIO io, const uint2 *__restrict__ seg,
                                                                      const FragVal *__restrict__ vals, float time,
                                                                      const uint32_t *__restrict__ hot_count,
                                                                      const uint32_t *__restrict__ hot_list) {
@@ -502,7 +524,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(float4 *__re
     for (uint32_t w = blockIdx.x * kFoldWarps + warp; w < n_hot; w += n_warps) {
         const uint32_t t = hot_list[w];
         const uint2 se = seg[t];
-        float4 d = flow[t];
+        float4 d = io.src[t];
         float rcx[kFoldPer], rcy[kFoldPer], ra[kFoldPer];
         auto prefetch = [&](uint32_t c0) {
 #pragma unroll
@@ -520,9 +542,25 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(float4 *__re
             if (c1 < se.y) prefetch(c1);
             if (lane == 0) fold_terms(d, s_term[warp][buf], s_om[warp][buf], 0u, c1 - c0);
         }
-        if (lane == 0) flow[t] = d;
+        if (lane == 0) {
+            io.dst[t] = d;
+            if (io.dst2) io.dst2[t] = d;
+        }
         __syncwarp();
     }
+}
+
+// Gates of the sharded ring fold: flags carry the step number ("epoch") and live in memory the
+// neighbouring rank maps over NVLink.  A kernel boundary orders the peer stores of the preceding fold
+// launch before the signal; the fence makes them visible system-wide first.
+__global__ void k_ring_wait(const uint32_t *flag, uint32_t epoch) {
+    const volatile uint32_t *f = flag;
+    while (*f < epoch) __nanosleep(200);
+    __threadfence_system();
+}
+__global__ void k_ring_signal(uint32_t *peer_flag, uint32_t epoch) {
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(peer_flag) = epoch;
 }
 
 // Full-grid alpha-over of an RGBA layer (L4 inputs drawn into the flow FBO).

@@ -38,6 +38,18 @@ def _global_rank(group, group_rank):
     return dist.get_global_rank(group, group_rank)
 
 
+def exchange_ring_handles(mine: bytes, rank, world_size, group, device):
+    """all-gather the ranks' IPC handle blobs and return the one of rank+1 (the ring successor)."""
+    import torch
+    import torch.distributed as dist
+    use_cuda = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", device) if use_cuda else torch.device("cpu")
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+    out = [torch.empty_like(t) for _ in range(world_size)]
+    dist.all_gather(out, t, group=group)
+    return bytes(out[(rank + 1) % world_size].cpu().tolist())
+
+
 class _CudaArray:
     def __init__(self, ptr, n_floats):
         self.__cuda_array_interface__ = {

@@ -27,13 +27,17 @@ class Device:
     rank/world_size describe a column-sharded multi-GPU run (one process per GPU); group is the
     torch.distributed process group used for the ordered flow exchange."""
 
-    def __init__(self, width=1, height=1, device=0, rank=0, world_size=1, group=None):
+    def __init__(self, width=1, height=1, device=0, rank=0, world_size=1, group=None, ring=None):
         self.drawingBufferWidth = int(width)
         self.drawingBufferHeight = int(height)
         self.device = int(device)
         self.rank = int(rank)
         self.world_size = int(world_size)
         self.group = group
+        # how the ordered flow fold travels between ranks: "peer" = CUDA IPC peer memory over NVLink
+        # (one node), "dist" = torch.distributed send/recv/broadcast
+        import os
+        self.ring = ring or os.environ.get("TB_RING", "peer")
 
 
 class Shader:
@@ -153,6 +157,7 @@ class Particles:
         self.render = params["render"]
         self.col0, self.col1 = shard_columns(self.shape[0], gl.rank, gl.world_size)
         self.flow_shape = [1, 1]
+        self._ring_ready = False
         self._L = N.load()
         cfg = N.TbConfig(self.shape[0], self.shape[1], self.col0, self.col1, 1, 1, gl.device, 0)
         ctx = C.c_void_p()
@@ -186,6 +191,7 @@ class Particles:
     def _resize_flow(self, w, h):
         N.check(self._ctx, self._L.tb_resize_flow(self._ctx, w, h))
         self.flow_shape = [w, h]
+        self._ring_ready = False          # new allocation: the IPC handles must be exchanged again
 
     def step(self, update, buffer=None):                                # src/particles.js:123-145
         """Runs `self.logic` once over the state texture.  buffer=None rotates the ping-pong
@@ -243,12 +249,33 @@ class Particles:
         N.check(ctx, L.tb_set_state(ctx, C.byref(st)))
         if gl.world_size == 1:
             N.check(ctx, L.tb_splat_flow(ctx, float(u["time"])))
+            return
+        N.check(ctx, L.tb_splat_collect(ctx, float(u["time"])))
+        if gl.ring == "peer":
+            # the ordered fold over peer memory: chunks travel rank to rank inside the fold kernels' own stores
+            self._ensure_ring()
+            N.check(ctx, L.tb_splat_fold_ring(ctx))
         else:
+            # same protocol over torch.distributed send/recv/broadcast (NCCL or gloo): slower, but needs no IPC
             from .multi_gpu import ordered_ring_fold
-            N.check(ctx, L.tb_splat_collect(ctx, float(u["time"])))
             ordered_ring_fold(gl.rank, gl.world_size, gl.group,
                               fold=lambda: N.check(ctx, L.tb_splat_fold(ctx)),
                               flow_tensor=self._flow_tensor, stream=self.stream_handle())
+
+    def _ensure_ring(self):
+        """Exchange CUDA IPC handles of (flow grid, inbox, flags) once per flow-grid allocation and map the
+        next rank's.  torch.distributed is only the courier of 208 bytes per rank."""
+        if self._ring_ready:
+            return
+        from .multi_gpu import exchange_ring_handles
+        L, ctx, gl = self._L, self._ctx, self.gl
+        nbytes = L.tb_ring_handle_bytes()
+        mine = (C.c_ubyte * nbytes)()
+        N.check(ctx, L.tb_ring_export(ctx, mine, nbytes))
+        nxt = exchange_ring_handles(bytes(mine), gl.rank, gl.world_size, gl.group, gl.device)
+        buf = (C.c_ubyte * nbytes).from_buffer_copy(nxt)
+        N.check(ctx, L.tb_ring_connect(ctx, gl.rank, gl.world_size, buf, nbytes))
+        self._ring_ready = True
 
     # -- plumbing ------------------------------------------------------------------------
     def stream_handle(self) -> int:

@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, R, G, steps, out_dir):
+def _worker(rank, world, port, R, G, steps, out_dir, ring):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -24,7 +24,7 @@ def _worker(rank, world, port, R, G, steps, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import tendrils_b200 as T
     from tendrils_b200.spawn import spawnBall
-    t = T.Tendrils(T.Device(G, G, device=rank, rank=rank, world_size=world, group=dist.group.WORLD))
+    t = T.Tendrils(T.Device(G, G, device=rank, rank=rank, world_size=world, group=dist.group.WORLD, ring=ring))
     t.setup(R); t.resize()
     spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}}).spawn(t)
     for _ in range(steps):
@@ -35,13 +35,14 @@ def _worker(rank, world, port, R, G, steps, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_ring_equals_oracle(oracle, tmp_path):
+@pytest.mark.parametrize("ring", ["peer", "dist"])
+def test_two_gpu_ring_equals_oracle(oracle, tmp_path, ring):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     world, R, G, steps = 2, 96, 64, 8
-    mp.spawn(_worker, args=(world, _free_port(), R, G, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), R, G, steps, str(tmp_path), ring), nprocs=world, join=True)
     O = oracle
     DT = 1000 / 60
     P = O.make_params()

@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     from tendrils_b200 import build as B
     B.build()
     hdr = open(os.path.join(ROOT, "include", "tendrils_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char \*)\s*(tb_\w+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^(?:int64_t|int|const char \*)\s*(tb_\w+)\s*\(", hdr, re.M))
     assert declared == set(N.SYMBOLS), (declared ^ set(N.SYMBOLS))
     lib = ctypes.CDLL(N.lib_path())
     for name in declared:
