@@ -222,6 +222,11 @@ def run_ours(args, wl, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = None
+    try:        # DRAM bytes of one k_integrate launch from the committed ncu --set full capture of this workload
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("k_integrate")
+    except Exception:
+        pass
     ab = algorithmic_bytes(n_local, grid)
     fin_us = 1e3 * tm["integrate_ms"] / max(tm["n_integrate"], 1)      # main-stream launch (fused, or the finish half)
     noise_us = 1e3 * tm["noise_ms"] / max(tm["n_integrate"], 1)        # side-stream noise launch, hidden under the splat
@@ -245,7 +250,7 @@ def run_ours(args, wl, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_integrate (logic.frag: noise launch + finish launch, device time summed)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": dom_us,
                      "integrate_us": int_us, "integrate_main_stream_us": fin_us, "integrate_noise_side_stream_us": noise_us,
                      "splat_us": spl_us,

@@ -152,6 +152,24 @@ int tb_ring_export(tb_ctx *ctx, void *handles_out, int64_t n_bytes);
 int tb_ring_connect(tb_ctx *ctx, int32_t rank, int32_t world, const void *next_rank_handles, int64_t n_bytes);
 int tb_splat_fold_ring(tb_ctx *ctx);
 
+/* Band exchange for column-sharded runs (the scalable form of the ordered fold): the grid is cut into one band
+ * of texels per rank; every rank sends each band's slice of its sorted fragments to the band's owner (an
+ * all-to-all the host layer performs on the device pointers below), folds the pieces it received in source-rank
+ * order = draw order onto its band (tb_splat_fold_piece), and the bands are all-gathered.  No rank waits for
+ * another rank's fold; the result equals the single-GPU fold bit for bit.
+ *   tb_splat_band_offsets      after tb_splat_collect: index in this rank's sorted fragment array where each
+ *                              band starts (n_bands+1 values; synchronises)
+ *   tb_splat_exchange_buffers  device pointers: what to send (sorted keys u32 / values of *val_bytes bytes each)
+ *                              and where to receive recv_items items (grown on demand)
+ *   tb_splat_fold_piece        blend items [piece_offset, +piece_items) of the receive buffers onto texels
+ *                              [t_begin, t_end) of the flow grid
+ *   tb_splat_exchange_done     end of the draw (timing, state) */
+int tb_splat_band_offsets(tb_ctx *ctx, int32_t n_bands, int32_t band_texels, int64_t *host_offsets);
+int tb_splat_exchange_buffers(tb_ctx *ctx, int64_t recv_items, void **send_keys, void **send_vals, void **recv_keys,
+                              void **recv_vals, int32_t *val_bytes);
+int tb_splat_fold_piece(tb_ctx *ctx, int64_t piece_offset, int64_t piece_items, int32_t t_begin, int32_t t_end);
+int tb_splat_exchange_done(tb_ctx *ctx);
+
 /* Tendrils.spawn(cpuFn) with the default initSpawner: fills ALL buffers
  * (src/index.js:425-429, src/particles.js:94-117, src/spawn/init/cpu.js:3-8). */
 int tb_reset(tb_ctx *ctx);

@@ -53,6 +53,11 @@ SYMBOLS = {
     "tb_ring_export": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "tb_ring_connect": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "tb_splat_fold_ring": (C.c_int, [_ctx]),
+    "tb_splat_band_offsets": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "tb_splat_exchange_buffers": (C.c_int, [_ctx, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "tb_splat_fold_piece": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "tb_splat_exchange_done": (C.c_int, [_ctx]),
     "tb_reset": (C.c_int, [_ctx]),
     "tb_spawn_init": (C.c_int, [_ctx, C.c_int]),
     "tb_spawn_ball": (C.c_int, [_ctx, C.c_float, C.c_float, C.c_int]),

@@ -388,7 +388,8 @@ int ring_fold(tb_ctx *c) {
     const bool first = r == 0, last = r == P - 1;
     const uint32_t epoch = ++c->ring_epoch;
     const int per = ((G + C - 1) / C + 127) / 128 * 128;                 // texels per chunk, CTA aligned
-    uint32_t *in_flag = c->ring_flags, *fin_flag = c->ring_flags + C;
+    constexpr int S = tb_ctx::kRingMaxChunks;                              // flag stride: [0,S) inbox ready, [S,2S) final ready
+    uint32_t *in_flag = c->ring_flags, *fin_flag = c->ring_flags + S;
     TB_CUDA(c, cudaMemsetAsync(c->ring_hot_counts, 0, C * sizeof(uint32_t), c->stream));
     if (c->last_frags == 0)   // no fragments on this rank: collect() left the segments of an earlier draw behind
         TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * static_cast<size_t>(G) * sizeof(uint32_t), c->stream));
@@ -414,7 +415,7 @@ int ring_fold(tb_ctx *c) {
             io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2);
         if (int e = check_launch(c, "k_splat_fold_hot")) return e;
         // chunk k of the next rank's inbox (or, from the last rank, of rank 0's grid) is complete
-        k_ring_signal<<<1, 1, 0, c->stream>>>(last ? c->next_flags + C + k : c->next_flags + k, epoch);
+        k_ring_signal<<<1, 1, 0, c->stream>>>(last ? c->next_flags + S + k : c->next_flags + k, epoch);
         if (int e = check_launch(c, "k_ring_signal")) return e;
     }
     // final chunks travel 0 -> 1 -> ... -> P-2 (the last rank already has them)
@@ -427,7 +428,7 @@ int ring_fold(tb_ctx *c) {
             if (r < P - 2) {
                 TB_CUDA(c, cudaMemcpyAsync(c->next_flow + t0, c->flow + t0, static_cast<size_t>(t1 - t0) * sizeof(float4),
                                            cudaMemcpyDeviceToDevice, c->ring_stream));
-                k_ring_signal<<<1, 1, 0, c->ring_stream>>>(c->next_flags + C + k, epoch);
+                k_ring_signal<<<1, 1, 0, c->ring_stream>>>(c->next_flags + S + k, epoch);
                 if (int e = check_launch(c, "k_ring_signal")) return e;
             }
         }
@@ -450,7 +451,8 @@ int tb_ring_export(tb_ctx *c, void *out, int64_t n_bytes) {
     TB_CUDA(c, cudaSetDevice(c->device));
     const size_t G = static_cast<size_t>(c->W) * c->H;
     if (const char *e = std::getenv("TB_RING_CHUNKS")) c->ring_chunks = std::max(1, std::min<int>(tb_ctx::kRingMaxChunks, std::atoi(e)));
-    const int C = c->ring_chunks;
+    else c->ring_chunks = 0;      // chosen from the world size in tb_ring_connect
+    const int C = tb_ctx::kRingMaxChunks;
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     ring_release(c);
     if (c->inbox) cudaFree(c->inbox);
@@ -471,7 +473,7 @@ int tb_ring_export(tb_ctx *c, void *out, int64_t n_bytes) {
     TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flow, c->flow));
     TB_CUDA(c, cudaIpcGetMemHandle(&hnd.inbox, c->inbox));
     TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flags, c->ring_flags));
-    hnd.w = c->W; hnd.h = c->H; hnd.chunks = C;
+    hnd.w = c->W; hnd.h = c->H; hnd.chunks = c->ring_chunks;
     std::memcpy(out, &hnd, sizeof(hnd));
     return TB_OK;
 }
@@ -487,12 +489,103 @@ int tb_ring_connect(tb_ctx *c, int32_t rank, int32_t world, const void *next_ran
     RingHandles hnd;
     std::memcpy(&hnd, next_rank_handles, sizeof(hnd));
     TB_REQUIRE(c, hnd.w == c->W && hnd.h == c->H && hnd.chunks == c->ring_chunks, "tb_ring_connect: the next rank's flow grid has another shape");
+    // Measured on 8xB200 (profiles/r01_multi_gpu.txt): every chunk adds the tail of its own hot texels, so few
+    // chunks win on short rings and about world/2 on long ones.
+    if (c->ring_chunks == 0) c->ring_chunks = std::max(1, world / 2);
     ring_release(c);
     TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_flow), hnd.flow, cudaIpcMemLazyEnablePeerAccess));
     TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_inbox), hnd.inbox, cudaIpcMemLazyEnablePeerAccess));
     TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_flags), hnd.flags, cudaIpcMemLazyEnablePeerAccess));
     c->ring_rank = rank; c->ring_world = world;
     c->ring_connected = true;
+    // a rank waiting for its predecessor's grid has idle SMs: let the next step's noise run there
+    c->overlap = true;
+    return TB_OK;
+}
+
+// ---- band exchange ("a2a"): every rank folds ONE band of the grid with the fragments of ALL ranks -------------
+int tb_splat_band_offsets(tb_ctx *c, int32_t n_bands, int32_t band_texels, int64_t *host_offsets) {
+    TB_REQUIRE(c, c && host_offsets, "null argument");
+    TB_REQUIRE(c, c->collected, "tb_splat_band_offsets without a preceding tb_splat_collect");
+    TB_REQUIRE(c, n_bands >= 1 && n_bands <= 64, "bad band count");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t F = static_cast<uint32_t>(c->last_frags);
+    uint32_t *d_out = c->hot;                                  // scratch: free between collect and fold
+    if (F > 0) {
+        k_band_offsets<<<1, 128, 0, c->stream>>>(c->keys[1], F, band_texels, n_bands, d_out);
+        if (int r = check_launch(c, "k_band_offsets")) return r;
+        uint32_t tmp[65];
+        TB_CUDA(c, cudaMemcpyAsync(tmp, d_out, (n_bands + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int b = 0; b <= n_bands; ++b) host_offsets[b] = tmp[b];
+    } else {
+        for (int b = 0; b <= n_bands; ++b) host_offsets[b] = 0;
+    }
+    return TB_OK;
+}
+
+// pointers for the exchange: send = the sorted fragments, recv = the (now free) pre-sort buffers, grown if needed
+int tb_splat_exchange_buffers(tb_ctx *c, int64_t recv_items, void **send_keys, void **send_vals, void **recv_keys,
+                              void **recv_vals, int32_t *val_bytes) {
+    TB_REQUIRE(c, c && send_keys && send_vals && recv_keys && recv_vals && val_bytes, "null argument");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (static_cast<uint64_t>(recv_items) > c->frag_cap) {
+        // growing reallocates all four buffers: keep the sorted fragments
+        const uint32_t F = static_cast<uint32_t>(c->last_frags);
+        uint32_t *k_old = nullptr; FragVal *v_old = nullptr;
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (F > 0) {
+            TB_CUDA(c, cudaMalloc(&k_old, F * sizeof(uint32_t)));
+            TB_CUDA(c, cudaMalloc(&v_old, F * sizeof(FragVal)));
+            TB_CUDA(c, cudaMemcpy(k_old, c->keys[1], F * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+            TB_CUDA(c, cudaMemcpy(v_old, c->vals[1], F * sizeof(FragVal), cudaMemcpyDeviceToDevice));
+        }
+        if (int r = ensure_frag_cap(c, static_cast<uint64_t>(recv_items))) return r;
+        if (F > 0) {
+            TB_CUDA(c, cudaMemcpy(c->keys[1], k_old, F * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+            TB_CUDA(c, cudaMemcpy(c->vals[1], v_old, F * sizeof(FragVal), cudaMemcpyDeviceToDevice));
+            cudaFree(k_old); cudaFree(v_old);
+        }
+    }
+    *send_keys = c->keys[1]; *send_vals = c->vals[1];
+    *recv_keys = c->keys[0]; *recv_vals = c->vals[0];
+    *val_bytes = static_cast<int32_t>(sizeof(FragVal));
+    return TB_OK;
+}
+
+// blend one received piece (fragments of ONE source rank, sorted, in draw order) onto texels [t_begin, t_end)
+int tb_splat_fold_piece(tb_ctx *c, int64_t piece_offset, int64_t piece_items, int32_t t_begin, int32_t t_end) {
+    TB_REQUIRE(c, c, "null context");
+    TB_REQUIRE(c, t_begin >= 0 && t_begin <= t_end && t_end <= c->W * c->H, "bad texel range");
+    TB_REQUIRE(c, piece_offset >= 0 && piece_items >= 0 && piece_offset + piece_items <= static_cast<int64_t>(c->frag_cap), "bad piece");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (piece_items == 0 || t_begin == t_end) return TB_OK;
+    const uint32_t n = static_cast<uint32_t>(piece_items);
+    const uint32_t *keys = c->keys[0] + piece_offset;
+    const FragVal *vals = c->vals[0] + piece_offset;
+    TB_CUDA(c, cudaMemsetAsync(c->seg + 2ull * t_begin, 0, 2ull * (t_end - t_begin) * sizeof(uint32_t), c->stream));
+    k_splat_bounds<<<blocks_for((static_cast<long long>(n) + 3) / 4, 256), 256, 0, c->stream>>>(keys, n, c->seg);
+    if (int r = check_launch(c, "k_splat_bounds")) return r;
+    FoldIO io{};
+    io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
+    io.t_begin = t_begin; io.t_end = t_end; io.copy_all = 0;
+    TB_CUDA(c, cudaMemsetAsync(c->hot, 0, sizeof(uint32_t), c->stream));
+    k_splat_fold<<<blocks_for(t_end - t_begin, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
+        io, reinterpret_cast<const uint2 *>(c->seg), vals, c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
+    if (int r = check_launch(c, "k_splat_fold")) return r;
+    k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
+        io, reinterpret_cast<const uint2 *>(c->seg), vals, c->collect_time, c->hot, c->hot + 2);
+    if (int r = check_launch(c, "k_splat_fold_hot")) return r;
+    return TB_OK;
+}
+
+// closes the splat timing span of a band-exchange draw and marks the collect as consumed
+int tb_splat_exchange_done(tb_ctx *c) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
+    c->ev_count[1] += 1;
+    c->collected = false;
     return TB_OK;
 }
 

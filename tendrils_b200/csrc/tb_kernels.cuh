@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) k_splat_bounds(const uint32_t *__restrict
     if (i0 >= n) return;
     uint32_t k[6];
     k[0] = i0 ? keys[i0 - 1] : 0u;
-    if (i0 + 4 <= n) {
+    if (i0 + 4 <= n && (reinterpret_cast<uintptr_t>(keys + i0) & 15u) == 0) {   // pieces of an exchange may start unaligned
         const uint4 v = *reinterpret_cast<const uint4 *>(keys + i0);
         k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
     } else {
@@ -548,6 +548,20 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(const FoldIO
         }
         __syncwarp();
     }
+}
+
+// first index of the sorted key array whose texel is >= each band's first texel (one thread per band edge)
+__global__ void k_band_offsets(const uint32_t *__restrict__ keys, uint32_t n, int band_texels, int n_bands,
+                               uint32_t *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_bands) return;
+    const uint64_t want = static_cast<uint64_t>(b) * static_cast<uint64_t>(band_texels);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (static_cast<uint64_t>(keys[mid] & ~kOpaqueBit) < want) lo = mid + 1; else hi = mid;
+    }
+    out[b] = lo;
 }
 
 // Gates of the sharded ring fold: flags carry the step number ("epoch") and live in memory the

@@ -34,8 +34,11 @@ class Device:
         self.rank = int(rank)
         self.world_size = int(world_size)
         self.group = group
-        # how the ordered flow fold travels between ranks: "peer" = CUDA IPC peer memory over NVLink
-        # (one node), "dist" = torch.distributed send/recv/broadcast
+        # how the ordered flow fold is shared between ranks:
+        #   "peer" = ring over CUDA-IPC peer memory: the grid travels rank to rank inside the fold kernels' stores (default)
+        #   "a2a"  = band exchange: all-to-all of sorted fragment slices, one grid band folded per rank; no serial
+        #            dependency between ranks, but the torch.distributed all-to-all it rides on is host-bound today
+        #   "dist" = the same ring over torch.distributed send/recv/broadcast (also what the gloo tests run)
         import os
         self.ring = ring or os.environ.get("TB_RING", "peer")
 
@@ -251,7 +254,12 @@ class Particles:
             N.check(ctx, L.tb_splat_flow(ctx, float(u["time"])))
             return
         N.check(ctx, L.tb_splat_collect(ctx, float(u["time"])))
-        if gl.ring == "peer":
+        G = self.flow_shape[0] * self.flow_shape[1]
+        if gl.ring == "a2a" and G % (gl.world_size * 128) == 0:
+            # band exchange: all-to-all of fragment slices, every rank folds one band (scales with the rank count)
+            from .multi_gpu import band_exchange_fold
+            band_exchange_fold(self)
+        elif gl.ring in ("peer", "a2a"):
             # the ordered fold over peer memory: chunks travel rank to rank inside the fold kernels' own stores
             self._ensure_ring()
             N.check(ctx, L.tb_splat_fold_ring(ctx))

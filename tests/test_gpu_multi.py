@@ -35,13 +35,13 @@ def _worker(rank, world, port, R, G, steps, out_dir, ring):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ring", ["peer", "dist"])
+@pytest.mark.parametrize("ring", ["a2a", "peer", "dist"])
 def test_two_gpu_ring_equals_oracle(oracle, tmp_path, ring):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    world, R, G, steps = 2, 96, 64, 8
+    world, R, G, steps = 2, 96, 64, 8          # 64*64 texels: divisible by world*128, so a2a is exercised
     mp.spawn(_worker, args=(world, _free_port(), R, G, steps, str(tmp_path), ring), nprocs=world, join=True)
     O = oracle
     DT = 1000 / 60
