@@ -395,10 +395,18 @@ int ring_fold(tb_ctx *c) {
         TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * static_cast<size_t>(G) * sizeof(uint32_t), c->stream));
     TB_CUDA(c, cudaEventRecord(c->ev_ring_begin, c->stream));
     TB_CUDA(c, cudaStreamWaitEvent(c->ring_stream, c->ev_ring_begin, 0));
+    // TB_RING_DEBUG=<epoch>: time the phases of that ring fold on every rank (diagnostics, stderr)
+    static const int dbg_epoch = std::getenv("TB_RING_DEBUG") ? std::atoi(std::getenv("TB_RING_DEBUG")) : -1;
+    const bool dbg = static_cast<int>(epoch) == dbg_epoch;
+    static cudaEvent_t dbg_ev[tb_ctx::kRingMaxChunks][5];
+    if (dbg)
+        for (int k = 0; k < C; ++k)
+            for (int j = 0; j < 5; ++j) cudaEventCreate(&dbg_ev[k][j]);
     for (int k = 0; k < C; ++k) {
         const int t0 = std::min(G, k * per), t1 = std::min(G, (k + 1) * per);
         if (t0 >= t1) continue;
         FoldIO io{};
+        if (dbg) cudaEventRecord(dbg_ev[k][0], c->stream);
         io.src = first ? c->flow : c->inbox;
         io.dst = last ? c->flow : c->next_inbox;
         io.dst2 = (last && P > 1) ? c->next_flow : nullptr;             // rank 0's grid
@@ -407,16 +415,32 @@ int ring_fold(tb_ctx *c) {
             k_ring_wait<<<1, 1, 0, c->stream>>>(in_flag + k, epoch);
             if (int e = check_launch(c, "k_ring_wait")) return e;
         }
+        if (dbg) cudaEventRecord(dbg_ev[k][1], c->stream);
         k_splat_fold<<<blocks_for(t1 - t0, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
             io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2,
             c->last_frags > 0 ? c->hot_threshold : 0xffffffffu);
         if (int e = check_launch(c, "k_splat_fold")) return e;
-        k_splat_fold_hot<<<c->n_sms, kFoldWarps * 32, 0, c->stream>>>(
+        if (dbg) cudaEventRecord(dbg_ev[k][2], c->stream);
+        k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
             io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2);
         if (int e = check_launch(c, "k_splat_fold_hot")) return e;
         // chunk k of the next rank's inbox (or, from the last rank, of rank 0's grid) is complete
+        if (dbg) cudaEventRecord(dbg_ev[k][3], c->stream);
         k_ring_signal<<<1, 1, 0, c->stream>>>(last ? c->next_flags + S + k : c->next_flags + k, epoch);
         if (int e = check_launch(c, "k_ring_signal")) return e;
+        if (dbg) cudaEventRecord(dbg_ev[k][4], c->stream);
+    }
+    if (dbg) {
+        cudaStreamSynchronize(c->stream);
+        for (int k = 0; k < C; ++k) {
+            float w = 0, m = 0, h = 0, sgl = 0;
+            cudaEventElapsedTime(&w, dbg_ev[k][0], dbg_ev[k][1]);
+            cudaEventElapsedTime(&m, dbg_ev[k][1], dbg_ev[k][2]);
+            cudaEventElapsedTime(&h, dbg_ev[k][2], dbg_ev[k][3]);
+            cudaEventElapsedTime(&sgl, dbg_ev[k][3], dbg_ev[k][4]);
+            std::fprintf(stderr, "[ring dbg] rank %d chunk %d: wait %.0f us, fold %.0f us, hot %.0f us, signal %.0f us (frags %lld)\n",
+                         r, k, w * 1e3f, m * 1e3f, h * 1e3f, sgl * 1e3f, static_cast<long long>(c->last_frags));
+        }
     }
     // final chunks travel 0 -> 1 -> ... -> P-2 (the last rank already has them)
     if (!last) {
