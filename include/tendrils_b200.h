@@ -81,6 +81,13 @@ typedef struct tb_pixel_spawner {
     float spawnMatrix[9];     /* column-major mat3 (gl-matrix)                          */
 } tb_pixel_spawner;
 
+/* Uniforms of the optical-flow pass (src/optical-flow/index.js:21-30, src/demo.main.js:1148-1153). */
+typedef struct tb_optical_flow_params {
+    float viewSize[2];
+    float scaleUV[2];
+    float offset, lambda, speed, speedLimit, time;
+} tb_optical_flow_params;
+
 /* Where a spawn pass writes: spawnShader(shader, update) vs spawnShader(shader, update, tendrils.targets)
  * (src/index.js:432-457, src/particles.js:123-130). */
 typedef enum tb_target { TB_TARGET_STATE = 0, TB_TARGET_TARGETS = 1 } tb_target;
@@ -194,6 +201,13 @@ int tb_blend_into_flow(tb_ctx *ctx, const float *rgba, int32_t w, int32_t h);
 /* diagnostic tap: [fold begin, end) of every texel's fragment segment left by the last splat
  * (2*W*H words); used by tools/ to study fragment-list length distributions. */
 int tb_debug_segments(tb_ctx *ctx, uint32_t *host, int64_t n_words);
+
+/* OpticalFlow.update() + screen.render() with the flow FBO bound (src/optical-flow/index.frag:55-81,
+ * src/optical-flow/index.js:50-58, call site src/demo.main.js:1131-1156): the gradient optical flow of two RGBA8
+ * frames (view = current, last = previous; w*h*4 bytes each, texel row 0 first), written in the flow encoding
+ * and alpha-over blended into the flow grid. */
+int tb_optical_flow(tb_ctx *ctx, const tb_optical_flow_params *params, const uint8_t *view_rgba8,
+                    const uint8_t *last_rgba8, int32_t w, int32_t h);
 
 /* plumbing for the host layer (PyTorch / NCCL): raw device pointers, stream, sync, timing */
 int tb_device_ptr(tb_ctx *ctx, tb_buffer which, void **ptr, int64_t *n_floats);

@@ -113,6 +113,9 @@ def lib():
         L.or_spawn_pixels_sample.argtypes = [C.POINTER(SpawnPixels), C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.c_int, _fp,
                                              _fp, C.c_int, C.c_int, C.c_float, _fp]
+        L.or_optical_flow.restype = None
+        L.or_optical_flow.argtypes = [_fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, _fp, C.c_int, C.c_int]
         L.or_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -211,3 +214,17 @@ def spawn_pixels_sample(S, variant, state, image, time, cols=None):
     lib().or_spawn_pixels_sample(C.byref(S), apply, vig, samples, PW, PH, x0, x1, _p(state),
                                  _p(image), IW, IH, f32(time), _p(out))
     return out
+
+
+def optical_flow(flow, view, last, viewSize=(1.0, 1.0), scaleUV=(1.0, -1.0), offset=1.0, lambda_=0.001, speed=1.0,
+                 speedLimit=1.0, time=1.0):
+    """Blends the optical flow of two RGBA8 frames ([h,w,4] uint8) into flow ([H,W,4] float32), in place."""
+    H, W = flow.shape[:2]
+    ih, iw = view.shape[:2]
+    assert view.dtype == np.uint8 and last.dtype == np.uint8 and view.shape == last.shape
+    vs = np.asarray(viewSize, np.float32)
+    sc = np.asarray(scaleUV, np.float32)
+    view, last = np.ascontiguousarray(view), np.ascontiguousarray(last)
+    lib().or_optical_flow(_p(vs), _p(sc), f32(offset), f32(lambda_), f32(speed), f32(speedLimit), f32(time),
+                          view.ctypes.data, last.ctypes.data, iw, ih, _p(flow), W, H)
+    return flow

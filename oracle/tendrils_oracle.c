@@ -621,3 +621,41 @@ void or_spawn_pixels_sample(const or_spawn_pixels *S, int apply, int vig, int sa
             out[4 * p] = st[0]; out[4 * p + 1] = st[1]; out[4 * p + 2] = st[2]; out[4 * p + 3] = st[3];
         }
 }
+
+/* ------------------------------------------------------------------------------------
+ * f1: optical flow into the flow grid -- src/optical-flow/index.frag:55-81 drawn with the big triangle
+ * (src/screen/index.vert:6-10) over the flow FBO under the alpha-over blend.  view / last are RGBA8
+ * textures (gl-fbo without `float`), NEAREST + CLAMP_TO_EDGE; a byte b reads as b/255.
+ * spec/PARITY.md OF1: the varying uv at fragment centre fc is ((fc/res)*2)-1.
+ * ---------------------------------------------------------------------------------- */
+static inline float of_gray(const unsigned char *tex, int w, int h, float u, float v) {
+    const unsigned char *t = tex + 4 * ((size_t)texel_of(v, h) * w + texel_of(u, w));
+    float r = (float)t[0] / 255.0f, g = (float)t[1] / 255.0f, b = (float)t[2] / 255.0f;
+    return (r * 0.3f + g * 0.59f) + b * 0.11f;            /* utils/gray-scale.glsl */
+}
+
+void or_optical_flow(const float viewSize[2], const float scaleUV[2], float offset, float lambda, float speed,
+                     float speedLimit, float time, const unsigned char *view, const unsigned char *last, int iw, int ih,
+                     float *flow, int W, int H) {
+#pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < H; ++gy)
+        for (int gx = 0; gx < W; ++gx) {
+            float uvx = (((float)gx + 0.5f) / (float)W) * 2.0f - 1.0f;
+            float uvy = (((float)gy + 0.5f) / (float)H) * 2.0f - 1.0f;
+            float px = (uvx * scaleUV[0]) / viewSize[0], py = (uvy * scaleUV[1]) / viewSize[1];
+            float su = 0.0f + (1.0f - 0.0f) * (px - -1.0f) / (1.0f - -1.0f);
+            float sv = 0.0f + (1.0f - 0.0f) * (py - -1.0f) / (1.0f - -1.0f);
+            float gradX = (of_gray(view, iw, ih, su + offset, sv + 0.0f) - of_gray(view, iw, ih, su - offset, sv - 0.0f)) +
+                          (of_gray(last, iw, ih, su + offset, sv + 0.0f) - of_gray(last, iw, ih, su - offset, sv - 0.0f));
+            float gradY = (of_gray(view, iw, ih, su + 0.0f, sv + offset) - of_gray(view, iw, ih, su - 0.0f, sv - offset)) +
+                          (of_gray(last, iw, ih, su + 0.0f, sv + offset) - of_gray(last, iw, ih, su - 0.0f, sv - offset));
+            float gradMag = sqrtf((gradX * gradX + gradY * gradY) + lambda);
+            float diff = of_gray(view, iw, ih, su, sv) - of_gray(last, iw, ih, su, sv);
+            float vx = (diff * (gradX / gradMag)) * speed, vy = (diff * (gradY / gradMag)) * speed;
+            float t = g_length2(vx, vy) / speedLimit, ut = 1.0f - t;
+            float bz = (0.0f * ut + 0.0f * t) * ut + (0.0f * ut + 1.0f * t) * t;      /* bezier(vec3(0,0,1), t) */
+            float ox = bz * vx, oy = bz * vy;
+            float c[4] = { ox, oy, time, g_min(g_length2(ox, oy) / speedLimit, 1.0f) };
+            blend_over(flow + 4 * ((size_t)gy * W + gx), c);
+        }
+}

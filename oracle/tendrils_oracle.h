@@ -94,6 +94,11 @@ void or_spawn_pixels_sample(const or_spawn_pixels *S, int apply, int vignette, i
                             int PW, int PH, int x0, int x1, const float *state_in,
                             const float *image, int IW, int IH, float time, float *out);
 
+/* f1: optical-flow pass blended into the flow grid (reference src/optical-flow/index.frag); view/last RGBA8 */
+void or_optical_flow(const float viewSize[2], const float scaleUV[2], float offset, float lambda, float speed,
+                     float speedLimit, float time, const unsigned char *view, const unsigned char *last, int iw, int ih,
+                     float *flow, int W, int H);
+
 int or_num_threads(void);
 
 #ifdef __cplusplus

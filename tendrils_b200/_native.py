@@ -29,6 +29,11 @@ class TbPixelSpawner(C.Structure):
                 ("bias", C.c_float), ("spawnMatrix", C.c_float * 9)]
 
 
+class TbOpticalFlowParams(C.Structure):
+    _fields_ = [("viewSize", C.c_float * 2), ("scaleUV", C.c_float * 2), ("offset", C.c_float), ("lambda_", C.c_float),
+                ("speed", C.c_float), ("speedLimit", C.c_float), ("time", C.c_float)]
+
+
 TB_TARGET_STATE, TB_TARGET_TARGETS = 0, 1
 TB_SPAWN_DIRECT, TB_SPAWN_BEST_SAMPLE, TB_SPAWN_BRIGHT_SAMPLE = 0, 1, 2
 TB_SPAWN_COLOR_SAMPLE, TB_SPAWN_DATA_SAMPLE, TB_SPAWN_FLOW_SAMPLE = 3, 4, 5
@@ -67,6 +72,7 @@ SYMBOLS = {
     "tb_download": (C.c_int, [_ctx, C.c_int, _fp, C.c_int64]),
     "tb_blend_into_flow": (C.c_int, [_ctx, _fp, C.c_int32, C.c_int32]),
     "tb_debug_segments": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_int64]),
+    "tb_optical_flow": (C.c_int, [_ctx, C.POINTER(TbOpticalFlowParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "tb_device_ptr": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "tb_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
     "tb_sync": (C.c_int, [_ctx]),

@@ -44,6 +44,8 @@ struct tb_ctx {
     int IW = 0, IH = 0;
     float4 *layer = nullptr;
     size_t layer_cap = 0;
+    uchar4 *frames = nullptr;               // optical flow: view + last, RGBA8
+    size_t frames_cap = 0;
 
     // flow splat scratch
     PairEntry *pairs = nullptr;
@@ -731,6 +733,7 @@ int tb_destroy(tb_ctx *c) {
     if (c->side) cudaStreamSynchronize(c->side);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
+    cudaFree(c->frames);
     cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off); cudaFree(c->row_pair);
     cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->hot); cudaFree(c->d_flag);
     for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); }
@@ -1034,6 +1037,31 @@ int tb_debug_segments(tb_ctx *c, uint32_t *host, int64_t n_words) {
     TB_CUDA(c, cudaSetDevice(c->device));
     TB_CUDA(c, cudaMemcpyAsync(host, c->seg, static_cast<size_t>(n_words) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+int tb_optical_flow(tb_ctx *c, const tb_optical_flow_params *params, const uint8_t *view_rgba8, const uint8_t *last_rgba8,
+                    int32_t w, int32_t h) {
+    TB_REQUIRE(c, c && params && view_rgba8 && last_rgba8, "null argument");
+    TB_REQUIRE(c, w >= 1 && h >= 1, "gl-texture2d: Texture dimensions are out of bounds");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = static_cast<size_t>(w) * h;
+    if (2 * n > c->frames_cap) {
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->frames) cudaFree(c->frames);
+        c->frames = nullptr; c->frames_cap = 0;
+        TB_CUDA(c, cudaMalloc(&c->frames, 2 * n * sizeof(uchar4)));
+        c->frames_cap = 2 * n;
+    }
+    TB_CUDA(c, cudaMemcpyAsync(c->frames, view_rgba8, n * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(c->frames + n, last_rgba8, n * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream));
+    OpticalArgs A{};
+    A.flow = c->flow; A.view = c->frames; A.last = c->frames + n;
+    A.W = c->W; A.H = c->H; A.IW = w; A.IH = h;
+    A.U = *params;
+    k_optical_flow<<<blocks_for(static_cast<long long>(c->W) * c->H, 256), 256, 0, c->stream>>>(A);
+    if (int r = check_launch(c, "k_optical_flow")) return r;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));       // the host frames are only borrowed
     return TB_OK;
 }
 

@@ -591,6 +591,58 @@ __global__ void k_blend_layer(float4 *__restrict__ flow, const float4 *__restric
     flow[t] = d;
 }
 
+// f1: optical flow of two RGBA8 frames, alpha-over blended into the flow grid
+// (src/optical-flow/index.frag:55-81 drawn with the big triangle of src/screen/index.vert).
+struct OpticalArgs {
+    float4 *__restrict__ flow;
+    const uchar4 *__restrict__ view;
+    const uchar4 *__restrict__ last;
+    int W, H, IW, IH;
+    tb_optical_flow_params U;
+};
+
+__device__ __forceinline__ float of_gray(const uchar4 *__restrict__ tex, int w, int h, float u, float v) {
+    const uchar4 t = __ldg(tex + (static_cast<size_t>(texel_of(v, h)) * w + texel_of(u, w)));
+    const float r = __fdiv_rn(static_cast<float>(t.x), 255.0f), g = __fdiv_rn(static_cast<float>(t.y), 255.0f),
+                b = __fdiv_rn(static_cast<float>(t.z), 255.0f);
+    return dot3(r, g, b, 0.3f, 0.59f, 0.11f);                 // utils/gray-scale.glsl
+}
+
+__global__ void __launch_bounds__(256) k_optical_flow(const OpticalArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.W * A.H) return;
+    const int gy = t / A.W, gx = t - gy * A.W;
+    const tb_optical_flow_params &U = A.U;
+    // the varying uv of the big triangle at the fragment centre (PARITY OF1)
+    const float uvx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(static_cast<float>(gx), 0.5f), static_cast<float>(A.W)), 2.0f), 1.0f);
+    const float uvy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(static_cast<float>(gy), 0.5f), static_cast<float>(A.H)), 2.0f), 1.0f);
+    const float px = __fdiv_rn(__fmul_rn(uvx, U.scaleUV[0]), U.viewSize[0]), py = __fdiv_rn(__fmul_rn(uvy, U.scaleUV[1]), U.viewSize[1]);
+    const float su = __fadd_rn(0.0f, __fdiv_rn(__fmul_rn(1.0f, __fsub_rn(px, -1.0f)), 2.0f));
+    const float sv = __fadd_rn(0.0f, __fdiv_rn(__fmul_rn(1.0f, __fsub_rn(py, -1.0f)), 2.0f));
+    const float up = __fadd_rn(su, U.offset), um = __fsub_rn(su, U.offset), u0p = __fadd_rn(su, 0.0f), u0m = __fsub_rn(su, 0.0f);
+    const float vp = __fadd_rn(sv, U.offset), vm = __fsub_rn(sv, U.offset), v0p = __fadd_rn(sv, 0.0f), v0m = __fsub_rn(sv, 0.0f);
+    const float gradX = __fadd_rn(__fsub_rn(of_gray(A.view, A.IW, A.IH, up, v0p), of_gray(A.view, A.IW, A.IH, um, v0m)),
+                                  __fsub_rn(of_gray(A.last, A.IW, A.IH, up, v0p), of_gray(A.last, A.IW, A.IH, um, v0m)));
+    const float gradY = __fadd_rn(__fsub_rn(of_gray(A.view, A.IW, A.IH, u0p, vp), of_gray(A.view, A.IW, A.IH, u0m, vm)),
+                                  __fsub_rn(of_gray(A.last, A.IW, A.IH, u0p, vp), of_gray(A.last, A.IW, A.IH, u0m, vm)));
+    const float gradMag = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gradX, gradX), __fmul_rn(gradY, gradY)), U.lambda));
+    const float diff = __fsub_rn(of_gray(A.view, A.IW, A.IH, su, sv), of_gray(A.last, A.IW, A.IH, su, sv));
+    const float vx = __fmul_rn(__fmul_rn(diff, __fdiv_rn(gradX, gradMag)), U.speed);
+    const float vy = __fmul_rn(__fmul_rn(diff, __fdiv_rn(gradY, gradMag)), U.speed);
+    const float tt = __fdiv_rn(glength(vx, vy), U.speedLimit), ut = __fsub_rn(1.0f, tt);
+    // bezier(vec3(0, 0, 1), t) (utils/bezier.glsl:9-13)
+    const float bz = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(0.0f, ut), __fmul_rn(0.0f, tt)), ut),
+                               __fmul_rn(__fadd_rn(__fmul_rn(0.0f, ut), __fmul_rn(1.0f, tt)), tt));
+    const float ox = __fmul_rn(bz, vx), oy = __fmul_rn(bz, vy);
+    const float a = gmin(__fdiv_rn(glength(ox, oy), U.speedLimit), 1.0f), om = __fsub_rn(1.0f, a);
+    float4 d = A.flow[t];
+    d.x = __fadd_rn(__fmul_rn(ox, a), __fmul_rn(d.x, om));
+    d.y = __fadd_rn(__fmul_rn(oy, a), __fmul_rn(d.y, om));
+    d.z = __fadd_rn(__fmul_rn(U.time, a), __fmul_rn(d.z, om));
+    d.w = __fadd_rn(__fmul_rn(a, a), __fmul_rn(d.w, om));
+    A.flow[t] = d;
+}
+
 // ------------------------------------------------------------------------------------------
 // Spawners (a12-a15)
 // ------------------------------------------------------------------------------------------

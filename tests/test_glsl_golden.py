@@ -75,3 +75,18 @@ def test_spawn_frags(oracle, g, name):
     assert_bits_equal(got, want, f"spawn {name}")
     if name not in ("init",):
         assert np.isfinite(want).all() and len(np.unique(want[..., 0])) > 3
+
+
+def test_optical_flow_frag(oracle, g):
+    """optical-flow/index.frag: the interpreter gives the fragment colour; blended over a zero grid the oracle must
+    give colour*alpha per channel (dst = src*a + 0*(1-a))."""
+    O = oracle
+    sx, sy, offset, lam, speed, limit, time = g["of_uniforms"]
+    H, W = g["of_frag"].shape[:2]
+    flow = np.zeros((H, W, 4), np.float32)
+    O.optical_flow(flow, g["of_view"], g["of_last"], viewSize=tuple(g["logic_viewSize"]), scaleUV=(sx, sy), offset=offset,
+                   lambda_=lam, speed=speed, speedLimit=limit, time=time)
+    frag = g["of_frag"]
+    want = (frag * frag[..., 3:4]).astype(np.float32)         # one rounding per channel, as the blend does
+    assert_bits_equal(flow, want, "optical flow blended onto zero")
+    assert (frag[..., 3] > 0).mean() > 0.5 and np.isfinite(frag).all()

@@ -317,3 +317,32 @@ def test_opaque_cut_is_exact(T, oracle):
         assert_bits_equal(got, sim.flow, f"flow after draw {k}")
     assert (sim.flow[..., 3] == 1.0).sum() > 20, "the case must actually contain opaque fragments"
     assert np.isnan(sim.flow).any()
+
+
+def test_optical_flow_bit_exact(T, oracle):
+    """f1: the optical-flow pass drawn into the flow grid after the particle splat (src/demo.main.js:1131-1159)."""
+    from tendrils_b200.optical_flow import OpticalFlow
+    from tendrils_b200.spawn import spawnBall
+    R, W, H = 32, 40, 24
+    t = make(T, R, 0, view=(W, H))
+    O = oracle
+    sim = OracleSim(O, R, W, H, oracle_params(O, t))
+    spawnBall(t.gl, {"uniforms": {"radius": 0.5, "speed": 0.004}}).spawn(t)
+    sim.spawn_ball(0.5, 0.004)
+    rng = np.random.default_rng(8)
+    of = OpticalFlow(t.gl, None, {"speed": 0.08, "offset": 0.1, "scaleUV": [-1, -1]})
+    frames = [rng.integers(0, 256, (18, 30, 4), dtype=np.uint8)]
+    for _ in range(4):
+        frames.append(np.clip(frames[-1].astype(np.int32) + rng.integers(-30, 31, frames[-1].shape), 0, 255).astype(np.uint8))
+    of.resize([30, 18])
+    last = np.zeros_like(frames[0])
+    for k, frame in enumerate(frames):
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); sim.draw(np.float32(t.timer.time))
+        of.setPixels(frame)
+        of.update({"speedLimit": t.state["speedLimit"], "time": t.timer.time, "viewSize": t.viewSize}).render(t)
+        O.optical_flow(sim.flow, frame, last, viewSize=tuple(np.float32(v) for v in t.viewSize), scaleUV=(-1, -1), offset=0.1,
+                       lambda_=0.001, speed=0.08, speedLimit=t.state["speedLimit"], time=np.float32(t.timer.time))
+        of.step(); last = frame
+        assert_bits_equal(t.flow.download(), sim.flow, f"flow after optical-flow pass {k}")
+        assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state {k}")

@@ -36,7 +36,20 @@ TOKEN = re.compile(r"\s*(?:(\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?|\d+
 def tokenize(src):
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
-    src = "\n".join(l for l in src.split("\n") if not l.strip().startswith("#"))
+    lines, keep = [], [True]                              # minimal preprocessor: #if <int> / #else / #endif
+    for l in src.split("\n"):
+        st = l.strip()
+        if st.startswith("#if"):
+            keep.append(keep[-1] and bool(int(st.split()[1])))
+        elif st.startswith("#else"):
+            keep[-1] = (not keep[-1]) and keep[-2]
+        elif st.startswith("#endif"):
+            keep.pop()
+        elif st.startswith("#"):
+            pass
+        elif keep[-1]:
+            lines.append(l)
+    src = "\n".join(lines)
     out, pos = [], 0
     while True:
         m = TOKEN.match(src, pos)

@@ -122,6 +122,23 @@ def main():
                                ("flow", "/src/spawn/pixels/flow-sample.frag", flow)]:
         sh = Shader(shader_source("demo.js.map", suffix))
         out["spawn_" + name] = run_fragments(sh, R, {**sp, "spawnData": nearest_sampler(data)})
+    # ---- optical-flow/index.frag (f1), drawn over a W x H flow grid with the big triangle ----------------
+    of = Shader(shader_source("demo.js.map", "/src/optical-flow/index.frag"))
+    iw, ih = 9, 6
+    view = rng.integers(0, 256, (ih, iw, 4), dtype=np.uint8)
+    last = np.clip(view.astype(np.int32) + rng.integers(-40, 41, (ih, iw, 4)), 0, 255).astype(np.uint8)
+    as_float = lambda img: (img.astype(f32) / f32(255.0)).astype(f32)           # RGBA8 sampler: byte/255
+    ofu = {"view": nearest_sampler(as_float(view)), "last": nearest_sampler(as_float(last)), "viewSize": view_size,
+           "scaleUV": [-1.0, -1.0], "offset": f32(0.1), "lambda": f32(0.001), "time": f32(9 * DT), "speed": f32(0.08),
+           "speedLimit": f32(STATE["speedLimit"])}
+    frag = np.zeros((H, W, 4), f32)
+    for gy in range(H):
+        for gx in range(W):
+            uv = [f32(f32(f32(gx + 0.5) / f32(W)) * f32(2.0)) - f32(1.0), f32(f32(f32(gy + 0.5) / f32(H)) * f32(2.0)) - f32(1.0)]
+            frag[gy, gx] = of.run({**ofu, "uv": uv})["gl_FragColor"]
+    out["of_view"], out["of_last"], out["of_frag"] = view, last, frag
+    out["of_uniforms"] = np.array([-1.0, -1.0, 0.1, 0.001, 0.08, STATE["speedLimit"], 9 * DT], f32)
+
     path = os.path.join(ROOT, "tests", "golden", "glsl_v1.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
