@@ -315,12 +315,12 @@ int fold(tb_ctx *c) {
         FoldIO io{};
         io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
         io.t_begin = 0; io.t_end = G; io.copy_all = 0;
-        TB_CUDA(c, cudaMemsetAsync(c->hot, 0, sizeof(uint32_t), c->stream));
+        TB_CUDA(c, cudaMemsetAsync(c->hot, 0, 2 * sizeof(uint32_t), c->stream));       // [0] count, [1] cursor
         k_splat_fold<<<blocks_for(G, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
             io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
         if (int r = check_launch(c, "k_splat_fold")) return r;
-        k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
-            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2);
+        k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
+            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2, c->hot + 1);
         if (int r = check_launch(c, "k_splat_fold_hot")) return r;
     }
     TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
@@ -392,7 +392,7 @@ int ring_fold(tb_ctx *c) {
     const int per = ((G + C - 1) / C + 127) / 128 * 128;                 // texels per chunk, CTA aligned
     constexpr int S = tb_ctx::kRingMaxChunks;                              // flag stride: [0,S) inbox ready, [S,2S) final ready
     uint32_t *in_flag = c->ring_flags, *fin_flag = c->ring_flags + S;
-    TB_CUDA(c, cudaMemsetAsync(c->ring_hot_counts, 0, C * sizeof(uint32_t), c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->ring_hot_counts, 0, 2 * tb_ctx::kRingMaxChunks * sizeof(uint32_t), c->stream));   // counts, cursors
     if (c->last_frags == 0)   // no fragments on this rank: collect() left the segments of an earlier draw behind
         TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * static_cast<size_t>(G) * sizeof(uint32_t), c->stream));
     TB_CUDA(c, cudaEventRecord(c->ev_ring_begin, c->stream));
@@ -423,8 +423,9 @@ int ring_fold(tb_ctx *c) {
             c->last_frags > 0 ? c->hot_threshold : 0xffffffffu);
         if (int e = check_launch(c, "k_splat_fold")) return e;
         if (dbg) cudaEventRecord(dbg_ev[k][2], c->stream);
-        k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
-            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2);
+        k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
+            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2,
+            c->ring_hot_counts + tb_ctx::kRingMaxChunks + k);
         if (int e = check_launch(c, "k_splat_fold_hot")) return e;
         // chunk k of the next rank's inbox (or, from the last rank, of rank 0's grid) is complete
         if (dbg) cudaEventRecord(dbg_ev[k][3], c->stream);
@@ -487,7 +488,7 @@ int tb_ring_export(tb_ctx *c, void *out, int64_t n_bytes) {
     c->inbox = nullptr; c->ring_flags = nullptr; c->ring_hot_counts = nullptr;
     TB_CUDA(c, cudaMalloc(&c->inbox, G * sizeof(float4)));
     TB_CUDA(c, cudaMalloc(&c->ring_flags, 2 * C * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->ring_hot_counts, C * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->ring_hot_counts, 2 * C * sizeof(uint32_t)));
     TB_CUDA(c, cudaMemset(c->ring_flags, 0, 2 * C * sizeof(uint32_t)));
     c->ring_epoch = 0;
     if (!c->ring_stream) {
@@ -595,12 +596,12 @@ int tb_splat_fold_piece(tb_ctx *c, int64_t piece_offset, int64_t piece_items, in
     FoldIO io{};
     io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
     io.t_begin = t_begin; io.t_end = t_end; io.copy_all = 0;
-    TB_CUDA(c, cudaMemsetAsync(c->hot, 0, sizeof(uint32_t), c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->hot, 0, 2 * sizeof(uint32_t), c->stream));
     k_splat_fold<<<blocks_for(t_end - t_begin, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
         io, reinterpret_cast<const uint2 *>(c->seg), vals, c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
     if (int r = check_launch(c, "k_splat_fold")) return r;
-    k_splat_fold_hot<<<c->n_sms * 4, kFoldWarps * 32, 0, c->stream>>>(
-        io, reinterpret_cast<const uint2 *>(c->seg), vals, c->collect_time, c->hot, c->hot + 2);
+    k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
+        io, reinterpret_cast<const uint2 *>(c->seg), vals, c->collect_time, c->hot, c->hot + 2, c->hot + 1);
     if (int r = check_launch(c, "k_splat_fold_hot")) return r;
     return TB_OK;
 }

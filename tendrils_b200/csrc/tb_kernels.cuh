@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) k_splat_bounds(const uint32_t *__restrict
 constexpr int kFoldChunk = 256;           // fragments per warp per pass through shared memory
 constexpr int kFoldWarps = 4;             // warps per CTA
 constexpr int kFoldPer = kFoldChunk / 32; // fragments per lane per chunk
-constexpr uint32_t kFoldHot = 192;        // segment length above which a texel is "hot"
+constexpr uint32_t kFoldHot = 96;         // segment length above which a texel is "hot" (swept: 24..2048)
 
 struct __align__(16) FoldTerm { float tx, ty, tz, tw; };   // src*a for the four channels
 
@@ -510,41 +510,102 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(const FoldIO io,
     }
 }
 
-// One warp per hot texel: all lanes load and pre-multiply a chunk, lane 0 runs the blend chain
-// while the next chunk is already in flight.  Persistent over the worklist.
-__global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold_hot(const FoldIO io, const uint2 *__restrict__ seg,
-                                                                     const FragVal *__restrict__ vals, float time,
-                                                                     const uint32_t *__restrict__ hot_count,
-                                                                     const uint32_t *__restrict__ hot_list) {
-    __shared__ FoldTerm s_term[kFoldWarps][2][kFoldChunk];
-    __shared__ float s_om[kFoldWarps][2][kFoldChunk];
+// Long segments ("hot" texels: dense filaments, the centre of a ball spawn, a whole shard of a sharded run):
+// a warp runs kHotChains blend chains side by side, one texel per chain, and takes the next texel from the
+// worklist whenever a chain finishes (persistent, dynamically balanced).  Per pass every chain advances by up
+// to kHotStep fragments: all 32 lanes pull the chains' next fragments into shared memory with cp.async
+// (coalesced, no registers), pre-multiply the order-independent half in place (src*a, 1-a), then lanes
+// 0..kHotChains-1 each run the serial half of their texel: two dependent roundings per fragment and channel.
+// (Measured alternatives, profiles/r01_fold_variants.txt: one chain per warp is issue bound, 32 chains per warp
+// with 32-fragment steps pays the staging latency too often on the longest segments.)
+constexpr int kHotChains = 8;
+constexpr int kHotStep = 128;
+constexpr int kHotWarps = 2;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kHotWarps * 32) k_splat_fold_hot(const FoldIO io, const uint2 *__restrict__ seg,
+                                                                   const FragVal *__restrict__ vals, float time,
+                                                                   const uint32_t *__restrict__ hot_count,
+                                                                   const uint32_t *__restrict__ hot_list,
+                                                                   uint32_t *__restrict__ cursor) {
+    __shared__ __align__(16) FoldTerm s_term[kHotWarps][kHotChains][kHotStep];
+    __shared__ float s_om[kHotWarps][kHotChains][kHotStep];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_hot = *hot_count;
-    const uint32_t n_warps = gridDim.x * kFoldWarps;
-    for (uint32_t w = blockIdx.x * kFoldWarps + warp; w < n_hot; w += n_warps) {
-        const uint32_t t = hot_list[w];
-        const uint2 se = seg[t];
-        float4 d = io.src[t];
-        float rcx[kFoldPer], rcy[kFoldPer], ra[kFoldPer];
-        auto prefetch = [&](uint32_t c0) {
-#pragma unroll
-            for (int j = 0; j < kFoldPer; ++j) {
-                const uint32_t i = c0 + j * 32 + lane;
-                if (i < se.y) { const FragVal f = load_frag(vals + i); rcx[j] = f.cx; rcy[j] = f.cy; ra[j] = f.a; }
-            }
-        };
-        prefetch(se.x);
-        int buf = 0;
-        for (uint32_t c0 = se.x; c0 < se.y; c0 += kFoldChunk, buf ^= 1) {
-            const uint32_t c1 = min(c0 + static_cast<uint32_t>(kFoldChunk), se.y);
-            stage_terms(s_term[warp][buf], s_om[warp][buf], rcx, rcy, ra, c0, c1, lane, time);
-            __syncwarp();
-            if (c1 < se.y) prefetch(c1);
-            if (lane == 0) fold_terms(d, s_term[warp][buf], s_om[warp][buf], 0u, c1 - c0);
+    // chain state, held by lane k for chain k
+    uint32_t pos = 0, end = 0, tex = 0;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool active = false;
+    auto grab = [&]() {                                  // next hot texel for this chain, if any
+        active = false;
+        const uint32_t w = atomicAdd(cursor, 1u);
+        if (w < n_hot) {
+            tex = hot_list[w];
+            const uint2 se = seg[tex];
+            pos = se.x; end = se.y;
+            d = io.src[tex];
+            active = true;
         }
-        if (lane == 0) {
-            io.dst[t] = d;
-            if (io.dst2) io.dst2[t] = d;
+    };
+    if (lane < kHotChains) grab();
+    while (__any_sync(0xffffffffu, active)) {
+        // 1. pull the next fragments of every chain into shared memory
+#pragma unroll
+        for (int k = 0; k < kHotChains; ++k) {
+            const uint32_t p = __shfl_sync(0xffffffffu, pos, k), e = __shfl_sync(0xffffffffu, end, k);
+            const bool on = __shfl_sync(0xffffffffu, active ? 1 : 0, k) != 0;
+            if (on) {
+#pragma unroll
+                for (int j = 0; j < kHotStep / 32; ++j) {
+                    const uint32_t i = p + j * 32 + lane;
+                    if (i < e) cp_async16(&s_term[warp][k][j * 32 + lane], vals + i);
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        // 2. pre-multiply in place: (cx, cy, a, -) -> (cx*a, cy*a, time*a, a*a), 1-a
+#pragma unroll
+        for (int k = 0; k < kHotChains; ++k) {
+            const uint32_t p = __shfl_sync(0xffffffffu, pos, k), e = __shfl_sync(0xffffffffu, end, k);
+            const bool on = __shfl_sync(0xffffffffu, active ? 1 : 0, k) != 0;
+            if (on) {
+#pragma unroll
+                for (int j = 0; j < kHotStep / 32; ++j) {
+                    const int q = j * 32 + lane;
+                    if (p + q < e) {
+                        const FoldTerm raw = s_term[warp][k][q];          // raw fragment: tx = cx, ty = cy, tz = a
+                        const float a = raw.tz;
+                        FoldTerm tm;
+                        tm.tx = __fmul_rn(raw.tx, a);
+                        tm.ty = __fmul_rn(raw.ty, a);
+                        tm.tz = __fmul_rn(time, a);
+                        tm.tw = __fmul_rn(a, a);
+                        s_term[warp][k][q] = tm;
+                        s_om[warp][k][q] = __fsub_rn(1.0f, a);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // 3. the serial half: lane k folds chain k
+        if (lane < kHotChains && active) {
+            const uint32_t n = min(static_cast<uint32_t>(kHotStep), end - pos);
+            fold_terms(d, s_term[warp][lane], s_om[warp][lane], 0u, n);
+            pos += n;
+            if (pos == end) {
+                io.dst[tex] = d;
+                if (io.dst2) io.dst2[tex] = d;
+                grab();
+            }
         }
         __syncwarp();
     }
