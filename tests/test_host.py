@@ -120,3 +120,33 @@ def test_pixel_spawner_uniforms():
     assert u["jitter"][0] == np.float32(np.float32(1 / 1024) * 2) and u["jitter"][1] == np.float32(np.float32(1 / 512) * 2)
     m = PX.mat3_scale(PX.mat3_identity(), [-1, 1])
     assert list(m) == [-1, 0, 0, 0, 1, 0, 0, 0, 1]
+
+
+def test_optical_flow_mirror_buffers():
+    """src/optical-flow/index.js: two RGBA8 buffers rotated by step(); resize keeps matching shapes, zeroes others."""
+    from tendrils_b200.optical_flow import OpticalFlow, defaults
+    of = OpticalFlow(None, None, {"speed": 0.08, "offset": 0.1, "scaleUV": [-1, -1]})
+    assert of.uniforms["lambda"] == defaults()["uniforms"]["lambda"] == 0.001 and of.uniforms["speed"] == 0.08
+    of.resize([4, 3])
+    assert all(b.shape == (3, 4, 4) and b.dtype == np.uint8 for b in of.buffers)
+    a = np.full((3, 4, 4), 7, np.uint8)
+    of.setPixels(a)
+    of.step()                                  # utils.step: pop the last buffer to the front
+    assert (of.buffers[1] == 7).all() and (of.buffers[0] == 0).all()
+    of.setPixels(np.full((3, 4, 4), 9, np.uint8))
+    of.step()
+    assert (of.buffers[0] == 7).all() and (of.buffers[1] == 9).all()
+    of.update({"time": 5.0})
+    assert of._bound["time"] == 5.0 and of._bound["offset"] == 0.1
+
+
+def test_env_knobs_are_documented():
+    """every TB_* environment variable read by the library is listed in DESIGN.md"""
+    import glob
+    names = set()
+    for f in glob.glob(os.path.join(ROOT, "tendrils_b200", "**", "*"), recursive=True):
+        if f.endswith((".cu", ".cuh", ".py")):
+            names |= set(re.findall(r'"(TB_[A-Z_0-9]+)"', open(f).read()))
+    doc = open(os.path.join(ROOT, "DESIGN.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
