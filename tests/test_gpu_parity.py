@@ -346,3 +346,121 @@ def test_optical_flow_bit_exact(T, oracle):
         of.step(); last = frame
         assert_bits_equal(t.flow.download(), sim.flow, f"flow after optical-flow pass {k}")
         assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state {k}")
+
+
+# ---------------------------------------------------------------------------------------------
+# degenerate and extreme shapes
+# ---------------------------------------------------------------------------------------------
+def test_all_inert_and_tiny_shapes(T, oracle):
+    """Nothing to integrate, nothing to draw; the smallest texture (2x2) and a 1x1 flow grid."""
+    t = make(T, 2, 1)
+    O = oracle
+    sim = OracleSim(O, 2, 1, 1, oracle_params(O, t))
+    for _ in range(3):                                   # everything inert after setup(): state and flow stay put
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); n = sim.draw(np.float32(t.timer.time))
+        assert n == 0 and t.particles.stats()["last_fragments"] == 0
+    assert_bits_equal(t.particles.buffers[0].download(), sim.cur, "inert state")
+    assert (t.flow.download() == 0).all()
+    from tendrils_b200.spawn import spawnBall
+    spawnBall(t.gl, {"uniforms": {"radius": 0.9, "speed": 0.05}}).spawn(t)
+    sim.spawn_ball(0.9, 0.05)
+    for k in range(5):
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); sim.draw(np.float32(t.timer.time))
+        assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"2x2 state {k}")
+        assert_bits_equal(t.flow.download(), sim.flow, f"1x1 flow {k}")
+
+
+def test_non_square_particle_texture(T, oracle):
+    """Particles accepts any [w, h] (src/particles.js:56); the sharded runs use tall textures."""
+    from tendrils_b200.spawn import spawnBall
+    W, H = 40, 24
+    t = T.Tendrils(T.Device(W, H))
+    t.setup([12, 50]); t.resize()
+    O = oracle
+    P = oracle_params(O, t)
+    cur, prev = O.spawn_ball(12, 50, 0.6, 0.006), O.spawn_init(12, 50)
+    spawnBall(t.gl, {"uniforms": {"radius": 0.6, "speed": 0.006}}).spawn(t)
+    targets, flow = np.zeros((12, 50, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    for k in range(6):
+        t.timer.tick(); t.step().draw()
+        new = O.integrate(P, cur, targets, flow, np.float32(t.timer.time), np.float32(t.timer.dt))
+        prev, cur = cur, new
+        O.splat(P, cur, prev, flow, np.float32(t.timer.time))
+        assert_bits_equal(t.particles.buffers[0].download(), cur, f"state {k}")
+        assert_bits_equal(t.flow.download(), flow, f"flow {k}")
+
+
+def test_redraw_after_parameter_change_recounts(T, oracle):
+    """The fragment count rides in the integrate kernel; a draw whose viewSize / grid differs from the step's
+    must not use it."""
+    from tendrils_b200.spawn import spawnBall
+    R = 48
+    t = make(T, R, 32)
+    O = oracle
+    spawnBall(t.gl, {"uniforms": {"radius": 0.7, "speed": 0.008}}).spawn(t)
+    cur, prev = O.spawn_ball(R, R, 0.7, 0.008), O.spawn_init(R, R)
+    targets = np.zeros((R, R, 4), np.float32)
+    t.timer.tick(); t.step()
+    P = oracle_params(O, t)
+    new = O.integrate(P, cur, targets, np.zeros((32, 32, 4), np.float32), np.float32(t.timer.time), np.float32(t.timer.dt))
+    prev, cur = cur, new
+    t.gl.drawingBufferWidth, t.gl.drawingBufferHeight = 56, 24          # the canvas was resized between step and draw
+    t.resize()
+    t.draw()
+    P2 = oracle_params(O, t)
+    flow = np.zeros((24, 56, 4), np.float32)
+    n = O.splat(P2, cur, prev, flow, np.float32(t.timer.time))
+    assert t.particles.stats()["last_fragments"] == n
+    assert_bits_equal(t.flow.download(), flow, "flow after a resized draw")
+
+
+@pytest.mark.parametrize("steps", [2])
+def test_full_size_cfg3_bit_exact(T, oracle, steps):
+    """BASELINE.json configs[2] at FULL size (4096^2 particles, 1024^2 flow grid): direct image spawn, then every
+    step compared with the oracle bit for bit -- state (16.8 M particles) and flow grid (1 M texels)."""
+    from tendrils_b200.spawn import PixelSpawner
+    from tendrils_b200.spawn import pixels as PX
+    R, G = 4096, 1024
+    t = make(T, R, G)
+    O = oracle
+    img = synthetic_image(G, G)
+    sp = PixelSpawner(t.gl, {"shader": PX.pixelsFrag, "buffer": img, "speed": 0.3, "jitterRad": 2, "spawnSize": [1, 1]})
+    sp.spawnMatrix = PX.mat3_scale(PX.mat3_identity(), [-1, 1])
+    sp.spawn(t)
+    j = np.float32(np.float32(1.0 / G) * 2.0)
+    S = O.make_spawn_pixels(jitter=(j, j), speed=0.3, spawnMatrix=(-1, 0, 0, 0, 1, 0, 0, 0, 1))
+    cur = O.spawn_pixels_direct(S, R, R, img, np.float32(t.timer.time))
+    prev = O.spawn_init(R, R)
+    assert_bits_equal(t.particles.buffers[0].download(), cur, "direct spawn at full size")
+    P = oracle_params(O, t)
+    targets, flow = np.zeros((R, R, 4), np.float32), np.zeros((G, G, 4), np.float32)
+    for k in range(steps):
+        t.timer.tick(); t.step().draw()
+        new = O.integrate(P, cur, targets, flow, np.float32(t.timer.time), np.float32(t.timer.dt))
+        prev, cur = cur, new
+        n = O.splat(P, cur, prev, flow, np.float32(t.timer.time), mt=True)
+        assert t.particles.stats()["last_fragments"] == n and n > 10_000_000
+        assert_bits_equal(t.particles.buffers[0].download(), cur, f"full-size state {k}")
+        assert_bits_equal(t.flow.download(), flow, f"full-size flow {k}")
+    # size-independent properties (what the reference guarantees by construction)
+    sp_ = np.hypot(cur[..., 2], cur[..., 3])
+    assert sp_.max() <= np.float32(0.01) * (1 + 1e-6)                 # speedLimit clamp
+    assert (flow[..., 3] >= 0).all() and (flow[..., 3] <= 1).all()    # alpha is a convex combination
+    assert flow[..., 2].max() <= np.float32(t.timer.time)             # time stamps never exceed `time`
+    t.dispose()
+
+
+def test_determinism_full_size(T):
+    """Run-to-run determinism at cfg2 size: no atomics decide any value, so two runs agree bit for bit."""
+    from tendrils_b200.spawn import spawnBall
+    outs = []
+    for _ in range(2):
+        t = make(T, 2048, 512)
+        spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}}).spawn(t)
+        for _ in range(12):
+            t.timer.tick(); t.step().draw()
+        outs.append((t.particles.buffers[0].download(), t.flow.download()))
+        t.dispose()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
