@@ -243,7 +243,8 @@ def run_ours(args, wl, rank, world, local_rank):
                    "flow_grid": [wl["G"], wl["G"]], "state": "reference defaults (src/index.js:29-57), noise on",
                    "splat": "exact ordered alpha-over (reference semantics)", "fragments_last_step": frags,
                    "l2": "inputs larger than L2 (state 2 x %d MiB per GPU)" % (n_local * 16 >> 20),
-                   "parallelism": f"particle columns sharded over {world} GPU(s), ordered ring fold of the flow grid"},
+                   "parallelism": (f"particle columns sharded over {world} GPU(s), ordered flow fold shared by transport "
+                                   f"'{t.gl.ring}'" if world > 1 else "1 GPU")},
         "clocks": clocks,
         "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": UNIT, "steps": e2e_steps,
                 "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 16},

@@ -159,6 +159,20 @@ int tb_ring_export(tb_ctx *ctx, void *handles_out, int64_t n_bytes);
 int tb_ring_connect(tb_ctx *ctx, int32_t rank, int32_t world, const void *next_rank_handles, int64_t n_bytes);
 int tb_splat_fold_ring(tb_ctx *ctx);
 
+/* The PARALLEL ordered fold of a column-sharded run over peer memory ("bands"; one process per GPU, one node,
+ * at most 16 ranks).  Every rank exports IPC handles of its sorted fragments / segment table / flow grid / flags
+ * (tb_bands_export; `reserve_fragments` fixes the capacity of the fragment buffers, which the other ranks map --
+ * a draw that needs more fails with TB_ERR_UNSUPPORTED), the host layer all-gathers the blobs, and each rank
+ * maps all of them (tb_bands_connect, `all_handles` = world x tb_bands_handle_bytes(), rank order).  After
+ * tb_splat_collect, tb_splat_fold_bands: barrier; fold the 32-texel tiles this rank owns (tile % world == rank)
+ * with the fragments of source rank 0, 1, ... read straight out of their memory over NVLink (source order =
+ * column order = the reference's primitive order, src/particles.js:182-186); store the finished tiles into
+ * every rank's grid; barrier.  No rank waits for another rank's fold.  Must be redone after tb_resize_flow. */
+int64_t tb_bands_handle_bytes(void);
+int tb_bands_export(tb_ctx *ctx, int64_t reserve_fragments, void *handles_out, int64_t n_bytes);
+int tb_bands_connect(tb_ctx *ctx, int32_t rank, int32_t world, const void *all_handles, int64_t n_bytes);
+int tb_splat_fold_bands(tb_ctx *ctx);
+
 /* Band exchange for column-sharded runs (the scalable form of the ordered fold): the grid is cut into one band
  * of texels per rank; every rank sends each band's slice of its sorted fragments to the band's owner (an
  * all-to-all the host layer performs on the device pointers below), folds the pieces it received in source-rank

@@ -58,6 +58,10 @@ SYMBOLS = {
     "tb_ring_export": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "tb_ring_connect": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "tb_splat_fold_ring": (C.c_int, [_ctx]),
+    "tb_bands_handle_bytes": (C.c_int64, []),
+    "tb_bands_export": (C.c_int, [_ctx, C.c_int64, C.c_void_p, C.c_int64]),
+    "tb_bands_connect": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "tb_splat_fold_bands": (C.c_int, [_ctx]),
     "tb_splat_band_offsets": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "tb_splat_exchange_buffers": (C.c_int, [_ctx, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                             C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),

@@ -82,6 +82,25 @@ struct tb_ctx {
     uint32_t ring_epoch = 0;
     cudaStream_t ring_stream = nullptr;    // forwards final chunks around the ring
     cudaEvent_t ev_ring_fwd = nullptr, ev_ring_begin = nullptr;
+    // band fold over peer memory (tb_bands_*): every rank maps every rank's sorted fragments, segments, grid, flags
+    bool bands_connected = false;
+    bool frag_fixed = false;               // keys/vals are exported through IPC handles: they must not be reallocated
+    int bands_rank = 0, bands_world = 1;
+    uint32_t bands_epoch = 0;
+    uint32_t *bands_flags = nullptr;       // [kBandPhases][kMaxBandRanks]: the epoch each rank has reached
+    BandSources band_src{};                // every rank's segment table (own slot: local pointer)
+    BandSinks band_sinks{};                // every rank's merged fragment array (its vals[0]) and offset table
+    BandPeers band_peers{};                // every rank's flow grid and flags
+    int bands_mine = 0;                    // 32-texel tiles this rank folds
+    uint32_t *bands_len = nullptr;         // [mine*32*world + 1] fragments per (local texel, source), texel-major; last = 0
+    uint32_t *bands_off = nullptr;         // its exclusive scan: where each segment goes in the merged array
+    uint32_t *bands_dst = nullptr;         // [G] written by the owners: where MY segment of each texel goes in its owner's array
+    uint32_t *bands_seg = nullptr;         // 2*G: merged segment table (only this rank's texels are meaningful)
+    void *bands_scan_tmp = nullptr;
+    size_t bands_scan_bytes = 0;
+    int *bands_overflow = nullptr;         // device flag: the merged fragments did not fit
+    int *h_bands_overflow = nullptr;       // pinned copy, read at the start of the next fold
+    cudaEvent_t ev_bands = nullptr;
     int key_bits = 1;
     uint32_t *h_total = nullptr;           // pinned
     cudaEvent_t ev_total = nullptr;
@@ -177,9 +196,11 @@ bool columns_are_identity(int PW) {
 }
 
 int ring_release(tb_ctx *c);
+int bands_release(tb_ctx *c);
 
 int alloc_flow(tb_ctx *c, int w, int h) {
     ring_release(c);
+    bands_release(c);
     TB_REQUIRE(c, w >= 1 && h >= 1 && static_cast<long long>(w) * h < (1LL << 31), "flow grid dimensions out of bounds");
     if (c->flow) cudaFree(c->flow);
     if (c->seg) cudaFree(c->seg);
@@ -200,6 +221,10 @@ int alloc_flow(tb_ctx *c, int w, int h) {
 int ensure_frag_cap(tb_ctx *c, uint64_t need) {
     if (need <= c->frag_cap) return TB_OK;
     TB_REQUIRE(c, need < (1ull << 31), "flow splat: more than 2^31 fragments in one draw");
+    if (c->frag_fixed)
+        return fail(c, TB_ERR_UNSUPPORTED, "flow splat: " + std::to_string(need) + " fragments exceed the " +
+                    std::to_string(c->frag_cap) + " reserved by tb_bands_export (the buffers are mapped by the other ranks); "
+                    "export with a larger reserve and reconnect");
     uint64_t cap = std::max<uint64_t>(need + need / 4, 1u << 16);
     if (cap >= (1ull << 31)) cap = (1ull << 31) - 1;
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -303,6 +328,8 @@ int collect(tb_ctx *c, float time) {
         TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * G * sizeof(uint32_t), c->stream));
         k_splat_bounds<<<blocks_for((static_cast<long long>(F) + 3) / 4, 256), 256, 0, c->stream>>>(c->keys[1], F, c->seg);
         if (int r = check_launch(c, "k_splat_bounds")) return r;
+    } else if (c->bands_connected) {
+        TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * G * sizeof(uint32_t), c->stream));   // the other ranks read this table
     }
     c->collected = true;
     return TB_OK;
@@ -530,6 +557,238 @@ int tb_ring_connect(tb_ctx *c, int32_t rank, int32_t world, const void *next_ran
     return TB_OK;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Band fold over peer memory: all ranks fold in parallel, each its own tiles of the grid
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct BandHandles {                 // what tb_bands_export hands to every other rank
+    cudaIpcMemHandle_t seg, merged, dst, flow, flags;
+    int32_t w, h;
+    uint32_t frag_cap, pad;
+};
+
+int bands_release(tb_ctx *c) {
+    for (int j = 0; j < kMaxBandRanks; ++j) {
+        if (j != c->bands_rank || !c->bands_connected) {
+            if (c->band_src.seg[j]) cudaIpcCloseMemHandle(const_cast<uint2 *>(c->band_src.seg[j]));
+            if (c->band_sinks.merged[j]) cudaIpcCloseMemHandle(c->band_sinks.merged[j]);
+            if (c->band_sinks.dst[j]) cudaIpcCloseMemHandle(c->band_sinks.dst[j]);
+            if (c->band_peers.flow[j]) cudaIpcCloseMemHandle(c->band_peers.flow[j]);
+            if (c->band_peers.flags[j]) cudaIpcCloseMemHandle(c->band_peers.flags[j]);
+        }
+        c->band_src.seg[j] = nullptr;
+        c->band_sinks.merged[j] = nullptr; c->band_sinks.dst[j] = nullptr;
+        c->band_peers.flow[j] = nullptr; c->band_peers.flags[j] = nullptr;
+    }
+    cudaFree(c->bands_len); cudaFree(c->bands_off); cudaFree(c->bands_seg); cudaFree(c->bands_scan_tmp);
+    c->bands_len = c->bands_off = c->bands_seg = nullptr;
+    c->bands_scan_tmp = nullptr;
+    c->bands_connected = false;
+    c->frag_fixed = false;
+    return TB_OK;
+}
+
+// Every rank folds the tiles it owns (tile % world == rank).  The fragments of those tiles are first brought
+// together in one local array -- per texel the sources side by side in rank order = column order = primitive
+// order, and inside a source the stable sort kept the draw order -- then the local fold runs on it.
+// The result equals the single-GPU fold bit for bit, and no rank waits for another rank's fold.
+int bands_fold(tb_ctx *c) {
+    TB_REQUIRE(c, c->collected, "tb_splat_fold_bands without a preceding tb_splat_collect");
+    TB_REQUIRE(c, c->bands_connected, "tb_bands_connect must be called first");
+    const int G = c->W * c->H, P = c->bands_world, r = c->bands_rank, mine = c->bands_mine;
+    if (c->bands_epoch > 0) {                        // the previous fold's overflow flag has long arrived
+        TB_CUDA(c, cudaEventSynchronize(c->ev_bands));
+        if (*c->h_bands_overflow)
+            return fail(c, TB_ERR_UNSUPPORTED, "flow splat (bands): the fragments of this rank's tiles exceeded the reserve of " +
+                        std::to_string(c->frag_cap) + "; export with a larger reserve (TB_BANDS_RESERVE) and reconnect");
+    }
+    const uint32_t epoch = ++c->bands_epoch;
+    // TB_RING_DEBUG=<epoch>: time the phases of that fold on every rank (diagnostics, stderr)
+    static const int dbg_epoch = std::getenv("TB_RING_DEBUG") ? std::atoi(std::getenv("TB_RING_DEBUG")) : -1;
+    const bool dbg = static_cast<int>(epoch) == dbg_epoch;
+    static cudaEvent_t dbg_ev[12];
+    int dbg_n = 0;
+    auto mark = [&]() { if (dbg) { cudaEventCreate(&dbg_ev[dbg_n]); cudaEventRecord(dbg_ev[dbg_n++], c->stream); } };
+    auto barrier = [&](int phase) -> int {
+        k_bands_barrier<<<1, 32, 0, c->stream>>>(c->band_peers, c->bands_flags, phase, epoch);
+        return check_launch(c, "k_bands_barrier");
+    };
+    mark();
+    // barrier 0: every rank's sorted fragments and segment table of this step are in place (and every rank is done
+    // with the merged array and the grid of the previous step)
+    if (int e = barrier(0)) return e;
+    mark();
+    const long long warps = static_cast<long long>(mine) * P;
+    const int n_seg = mine * 32 * P + 1;
+    k_bands_lengths<<<blocks_for(warps * 32, 256), 256, 0, c->stream>>>(c->band_src, P, r, mine, G, c->bands_len);
+    if (int e = check_launch(c, "k_bands_lengths")) return e;
+    TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->bands_scan_tmp, c->bands_scan_bytes, c->bands_len, c->bands_off, n_seg, c->stream));
+    c->launches += 2;
+    k_bands_offsets<<<blocks_for(warps * 32, 256), 256, 0, c->stream>>>(c->band_sinks, P, r, mine, G, c->bands_off, c->frag_cap,
+                                                                           c->bands_seg, c->bands_overflow);
+    if (int e = check_launch(c, "k_bands_offsets")) return e;
+    TB_CUDA(c, cudaMemcpyAsync(c->h_bands_overflow, c->bands_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaEventRecord(c->ev_bands, c->stream));
+    mark();
+    // barrier 1: every owner has told every source where its segments go
+    if (int e = barrier(1)) return e;
+    mark();
+    if (c->last_frags > 0) {
+        const uint32_t F = static_cast<uint32_t>(c->last_frags);
+        k_bands_push<<<blocks_for(F, 256), 256, 0, c->stream>>>(c->keys[1], c->vals[1], F, reinterpret_cast<const uint2 *>(c->seg),
+                                                                  c->bands_dst, c->band_sinks, P, c->frag_cap);
+        if (int e = check_launch(c, "k_bands_push")) return e;
+    }
+    mark();
+    // barrier 2: every source's fragments have landed in the owners' merged arrays
+    if (int e = barrier(2)) return e;
+    mark();
+    FoldIO io{};
+    io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
+    io.t_begin = 0; io.t_end = G; io.copy_all = 0;
+    io.tile_first = r; io.tile_stride = P;
+    TB_CUDA(c, cudaMemsetAsync(c->hot, 0, 2 * sizeof(uint32_t), c->stream));       // [0] count, [1] cursor
+    k_splat_fold<<<blocks_for(mine, kFoldWarps), kFoldWarps * 32, 0, c->stream>>>(
+        io, reinterpret_cast<const uint2 *>(c->bands_seg), c->vals[0], c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
+    if (int e = check_launch(c, "k_splat_fold")) return e;
+    k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
+        io, reinterpret_cast<const uint2 *>(c->bands_seg), c->vals[0], c->collect_time, c->hot, c->hot + 2, c->hot + 1);
+    if (int e = check_launch(c, "k_splat_fold_hot")) return e;
+    mark();
+    k_bands_publish<<<blocks_for(static_cast<long long>(mine) * 32, 256), 256, 0, c->stream>>>(c->flow, c->band_peers, G);
+    if (int e = check_launch(c, "k_bands_publish")) return e;
+    mark();
+    // barrier 3: every tile has landed in every grid
+    if (int e = barrier(3)) return e;
+    mark();
+    if (dbg) {
+        cudaStreamSynchronize(c->stream);
+        float ms[8] = {};
+        for (int k = 0; k < 8; ++k) cudaEventElapsedTime(&ms[k], dbg_ev[k], dbg_ev[k + 1]);
+        std::fprintf(stderr, "[bands dbg] rank %d: barrier0 %.0f us, lengths+scan+offsets %.0f us, barrier1 %.0f us, push %.0f us, "
+                             "barrier2 %.0f us, fold+hot %.0f us, publish %.0f us, barrier3 %.0f us (own frags %lld)\n",
+                     r, 1e3 * ms[0], 1e3 * ms[1], 1e3 * ms[2], 1e3 * ms[3], 1e3 * ms[4], 1e3 * ms[5], 1e3 * ms[6], 1e3 * ms[7],
+                     static_cast<long long>(c->last_frags));
+        for (int k = 0; k < 9; ++k) cudaEventDestroy(dbg_ev[k]);
+    }
+    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
+    c->ev_count[1] += 1;
+    c->collected = false;
+    return TB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t tb_bands_handle_bytes(void) { return static_cast<int64_t>(sizeof(BandHandles)); }
+
+int tb_bands_export(tb_ctx *c, int64_t reserve_fragments, void *out, int64_t n_bytes) {
+    TB_REQUIRE(c, c && out, "null argument");
+    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(BandHandles)), "tb_bands_export: buffer must be tb_bands_handle_bytes() long");
+    TB_REQUIRE(c, reserve_fragments >= 0 && reserve_fragments < (1ll << 31), "tb_bands_export: reserve out of range");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    bands_release(c);
+    if (int e = ensure_frag_cap(c, std::max<uint64_t>(static_cast<uint64_t>(reserve_fragments), 1u << 16))) return e;
+    if (!c->bands_flags) {
+        TB_CUDA(c, cudaMalloc(&c->bands_flags, kBandPhases * kMaxBandRanks * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMalloc(&c->bands_overflow, sizeof(int)));
+        TB_CUDA(c, cudaMallocHost(&c->h_bands_overflow, sizeof(int)));
+        TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_bands, cudaEventDisableTiming));
+    }
+    TB_CUDA(c, cudaMemset(c->bands_overflow, 0, sizeof(int)));
+    *c->h_bands_overflow = 0;
+    TB_CUDA(c, cudaMemset(c->bands_flags, 0, kBandPhases * kMaxBandRanks * sizeof(uint32_t)));
+    c->bands_epoch = 0;
+    if (c->bands_dst) cudaFree(c->bands_dst);
+    c->bands_dst = nullptr;
+    TB_CUDA(c, cudaMalloc(&c->bands_dst, static_cast<size_t>(c->W) * c->H * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMemset(c->bands_dst, 0, static_cast<size_t>(c->W) * c->H * sizeof(uint32_t)));
+    BandHandles hnd{};
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.seg, c->seg));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.merged, c->vals[0]));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.dst, c->bands_dst));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flow, c->flow));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flags, c->bands_flags));
+    hnd.w = c->W; hnd.h = c->H; hnd.frag_cap = c->frag_cap;
+    std::memcpy(out, &hnd, sizeof(hnd));
+    c->frag_fixed = true;
+    return TB_OK;
+}
+
+int tb_bands_connect(tb_ctx *c, int32_t rank, int32_t world, const void *all_handles, int64_t n_bytes) {
+    TB_REQUIRE(c, c && all_handles, "null argument");
+    TB_REQUIRE(c, world >= 2 && world <= kMaxBandRanks && rank >= 0 && rank < world, "tb_bands_connect: bad rank/world");
+    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(BandHandles)) * world, "tb_bands_connect: expected world x tb_bands_handle_bytes()");
+    TB_REQUIRE(c, c->frag_fixed && c->bands_flags, "tb_bands_export must be called before tb_bands_connect");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const bool fixed = c->frag_fixed;
+    bands_release(c);
+    c->frag_fixed = fixed;
+    c->bands_rank = rank; c->bands_world = world;
+    c->bands_connected = true;                 // from here on bands_release skips this rank's own slots
+    const auto *h = static_cast<const unsigned char *>(all_handles);
+    for (int j = 0; j < world; ++j) {
+        if (j == rank) {
+            c->band_src.seg[j] = reinterpret_cast<const uint2 *>(c->seg);
+            c->band_sinks.merged[j] = c->vals[0];
+            c->band_sinks.dst[j] = c->bands_dst;
+            c->band_peers.flow[j] = c->flow;
+            c->band_peers.flags[j] = c->bands_flags;
+            continue;
+        }
+        BandHandles hnd;
+        std::memcpy(&hnd, h + sizeof(BandHandles) * j, sizeof(hnd));
+        if (hnd.w != c->W || hnd.h != c->H) {
+            bands_release(c);
+            return fail(c, TB_ERR_INVALID, "tendrils-b200: tb_bands_connect: rank " + std::to_string(j) + " has another flow grid shape");
+        }
+        void *p[5] = {};
+        const cudaIpcMemHandle_t *hs[5] = {&hnd.seg, &hnd.merged, &hnd.dst, &hnd.flow, &hnd.flags};
+        for (int k = 0; k < 5; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess);
+            // keep what was opened so far where bands_release will find it
+            if (k == 0) c->band_src.seg[j] = static_cast<const uint2 *>(p[0]);
+            if (k == 1) c->band_sinks.merged[j] = static_cast<FragVal *>(p[1]);
+            if (k == 2) c->band_sinks.dst[j] = static_cast<uint32_t *>(p[2]);
+            if (k == 3) c->band_peers.flow[j] = static_cast<float4 *>(p[3]);
+            if (k == 4) c->band_peers.flags[j] = static_cast<uint32_t *>(p[4]);
+            if (e != cudaSuccess) {
+                bands_release(c);
+                return fail(c, TB_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(j) + "): " + cudaGetErrorString(e));
+            }
+        }
+    }
+    c->band_peers.n = world; c->band_peers.me = rank;
+    // scratch of the owner side: lengths / offsets per (local texel, source), the merged segment table
+    const size_t G = static_cast<size_t>(c->W) * c->H;
+    const int tiles = static_cast<int>((G + 31) / 32);
+    c->bands_mine = (tiles - rank + world - 1) / world;
+    const size_t n_seg = static_cast<size_t>(c->bands_mine) * 32 * world + 1;
+    TB_CUDA(c, cudaMalloc(&c->bands_len, n_seg * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->bands_off, n_seg * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->bands_seg, 2 * G * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMemset(c->bands_len, 0, n_seg * sizeof(uint32_t)));
+    c->bands_scan_bytes = 0;
+    TB_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, c->bands_scan_bytes, c->bands_len, c->bands_off, static_cast<int>(n_seg), c->stream));
+    TB_CUDA(c, cudaMalloc(&c->bands_scan_tmp, std::max<size_t>(c->bands_scan_bytes, 16)));
+    return TB_OK;
+}
+
+int tb_splat_fold_bands(tb_ctx *c) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    return bands_fold(c);
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // ---- band exchange ("a2a"): every rank folds ONE band of the grid with the fragments of ALL ranks -------------
 int tb_splat_band_offsets(tb_ctx *c, int32_t n_bands, int32_t band_texels, int64_t *host_offsets) {
     TB_REQUIRE(c, c && host_offsets, "null argument");
@@ -746,6 +1005,10 @@ int tb_destroy(tb_ctx *c) {
             for (int j = 0; j < 2; ++j)
                 if (c->ev_ring[k][i][j]) cudaEventDestroy(c->ev_ring[k][i][j]);
     ring_release(c);
+    bands_release(c);
+    cudaFree(c->bands_flags); cudaFree(c->bands_overflow); cudaFree(c->bands_dst);
+    if (c->h_bands_overflow) cudaFreeHost(c->h_bands_overflow);
+    if (c->ev_bands) cudaEventDestroy(c->ev_bands);
     cudaFree(c->inbox); cudaFree(c->ring_flags); cudaFree(c->ring_hot_counts);
     if (c->ring_stream) { cudaStreamSynchronize(c->ring_stream); cudaStreamDestroy(c->ring_stream); }
     if (c->ev_ring_fwd) cudaEventDestroy(c->ev_ring_fwd);

@@ -444,7 +444,11 @@ struct FoldIO {
     float4 *dst2;
     int t_begin, t_end;
     int copy_all;
+    // which 32-texel tiles this launch owns: tile_first + k*tile_stride (all of them by default; the band
+    // fold of a sharded run deals the tiles round-robin to the ranks)
+    int tile_first = 0, tile_stride = 1;
 };
+__device__ __forceinline__ int fold_tile(int tile_first, int tile_stride, int k) { return tile_first + tile_stride * k; }
 
 __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(const FoldIO io, const uint2 *__restrict__ seg,
                                                                  const FragVal *__restrict__ vals, float time,
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(kFoldWarps * 32) k_splat_fold(const FoldIO io,
     __shared__ FoldTerm s_term[kFoldWarps][kFoldChunk];
     __shared__ float s_om[kFoldWarps][kFoldChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = io.t_begin + (blockIdx.x * kFoldWarps + warp) * 32 + lane;
+    const int t = io.t_begin + fold_tile(io.tile_first, io.tile_stride, blockIdx.x * kFoldWarps + warp) * 32 + lane;
     uint2 se = make_uint2(0u, 0u);
     if (t < io.t_end) se = seg[t];
     bool has = se.y > se.x;
@@ -636,6 +640,102 @@ __global__ void k_ring_wait(const uint32_t *flag, uint32_t epoch) {
 __global__ void k_ring_signal(uint32_t *peer_flag, uint32_t epoch) {
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(peer_flag) = epoch;
+}
+
+// Band fold of a sharded run (tb_splat_fold_bands): every rank maps every other rank's segment table, merged
+// fragment buffer, offset table, flow grid and flags over NVLink (CUDA IPC).  The 32-texel tiles of the grid are
+// dealt round-robin to the ranks.  Per step:
+//   1. an owner reads the lengths of its texels' segments from every source rank's segment table (small),
+//      scans them texel-major -- per texel the sources side by side in rank order = column order = draw order --
+//      and writes each source the offsets its segments get in the owner's merged array;
+//   2. every source PUSHES its sorted fragments to the owners of their texels (posted NVLink writes: measured
+//      5-8x faster here than pulling the same bytes with remote loads, profiles/r01_multi_gpu.txt);
+//   3. the local fold kernels run unchanged on the merged array, and the finished tiles are stored into every
+//      rank's grid.
+// All-rank barriers fence the phases: sorted / offsets known / fragments landed / grid complete.
+constexpr int kMaxBandRanks = 16;
+constexpr int kBandPhases = 4;
+struct BandPeers {
+    float4 *flow[kMaxBandRanks];
+    uint32_t *flags[kMaxBandRanks];
+    int n, me;
+};
+struct BandSources { const uint2 *seg[kMaxBandRanks]; };
+struct BandSinks {
+    FragVal *merged[kMaxBandRanks];
+    uint32_t *dst[kMaxBandRanks];
+};
+
+// Lengths of the (local texel, source) segments, texel-major so that their exclusive scan lays a texel's
+// sources side by side: warp = (tile k of mine, source j), lane = texel of the tile.
+__global__ void __launch_bounds__(256) k_bands_lengths(const BandSources S, int n_src, int me, int mine, int G,
+                                                        uint32_t *__restrict__ len) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= mine * n_src) return;
+    const int k = w / n_src, j = w - k * n_src;
+    const int t = fold_tile(me, n_src, k) * 32 + lane;
+    uint2 se = make_uint2(0u, 0u);
+    if (t < G) se = S.seg[j][t];
+    len[static_cast<size_t>(k * 32 + lane) * n_src + j] = se.y - se.x;
+}
+
+// off = exclusive scan of len (one extra element: the total).  Tell source j where its segment of each of my
+// texels goes (its table dst, indexed by texel), and write the merged segment table of my texels.
+__global__ void __launch_bounds__(256) k_bands_offsets(const BandSinks D, int n_src, int me, int mine, int G,
+                                                        const uint32_t *__restrict__ off, uint32_t cap,
+                                                        uint32_t *__restrict__ seg_m, int *__restrict__ overflow) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= mine * n_src) return;
+    const int k = w / n_src, j = w - k * n_src;
+    const int t = fold_tile(me, n_src, k) * 32 + lane;
+    if (t >= G) return;
+    const size_t idx = static_cast<size_t>(k * 32 + lane) * n_src + j;
+    const uint32_t o = off[idx];
+    D.dst[j][t] = o;
+    if (j == 0) {
+        const uint32_t e = off[idx + n_src];
+        seg_m[2 * t] = o;
+        seg_m[2 * t + 1] = e <= cap ? e : o;              // overflow: fold nothing, the host raises
+        if (e > cap) *overflow = 1;
+    }
+}
+
+// Every source pushes its sorted fragments into the merged arrays of the owners of their texels.
+__global__ void __launch_bounds__(256) k_bands_push(const uint32_t *__restrict__ keys, const FragVal *__restrict__ vals, uint32_t n,
+                                                     const uint2 *__restrict__ seg, const uint32_t *__restrict__ dst,
+                                                     const BandSinks D, int n_src, uint32_t cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = keys[i] & ~kOpaqueBit;
+    const uint32_t b = seg[t].x;
+    if (i < b) return;                                    // overwritten by a later opaque fragment of this source
+    const uint32_t d = dst[t] + (i - b);
+    if (d < cap) D.merged[(t >> 5) % static_cast<uint32_t>(n_src)][d] = vals[i];
+}
+
+// all-rank barrier over peer memory: thread j tells rank j "I reached `epoch`" and waits for rank j to say so
+__global__ void k_bands_barrier(const BandPeers P, uint32_t *my_flags, int phase, uint32_t epoch) {
+    const int j = threadIdx.x;
+    if (j >= P.n) return;
+    __threadfence_system();                               // everything this rank stored before the barrier
+    *reinterpret_cast<volatile uint32_t *>(P.flags[j] + phase * kMaxBandRanks + P.me) = epoch;
+    const volatile uint32_t *f = my_flags + phase * kMaxBandRanks + j;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        __nanosleep(100);
+        if (clock64() - t0 > (1ll << 37)) __trap();       // ~1 min: a rank died; fail instead of hanging the GPU
+    }
+    __threadfence_system();
+}
+
+// copy this rank's finished tiles into every other rank's grid
+__global__ void __launch_bounds__(256) k_bands_publish(const float4 *__restrict__ flow, const BandPeers P, int G) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const long long t = (static_cast<long long>(P.me) + static_cast<long long>(P.n) * w) * 32 + lane;
+    if (t >= G) return;
+    const float4 v = flow[t];
+    for (int j = 0; j < P.n; ++j)
+        if (j != P.me) P.flow[j][t] = v;
 }
 
 // Full-grid alpha-over of an RGBA layer (L4 inputs drawn into the flow FBO).

@@ -38,8 +38,8 @@ def _global_rank(group, group_rank):
     return dist.get_global_rank(group, group_rank)
 
 
-def exchange_ring_handles(mine: bytes, rank, world_size, group, device):
-    """all-gather the ranks' IPC handle blobs and return the one of rank+1 (the ring successor)."""
+def gather_handles(mine: bytes, world_size, group, device):
+    """all-gather the ranks' IPC handle blobs (rank order).  torch.distributed is only the courier."""
     import torch
     import torch.distributed as dist
     use_cuda = dist.get_backend(group) == "nccl"
@@ -47,7 +47,12 @@ def exchange_ring_handles(mine: bytes, rank, world_size, group, device):
     t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
     out = [torch.empty_like(t) for _ in range(world_size)]
     dist.all_gather(out, t, group=group)
-    return bytes(out[(rank + 1) % world_size].cpu().tolist())
+    return [bytes(o.cpu().tolist()) for o in out]
+
+
+def exchange_ring_handles(mine: bytes, rank, world_size, group, device):
+    """all-gather the ranks' IPC handle blobs and return the one of rank+1 (the ring successor)."""
+    return gather_handles(mine, world_size, group, device)[(rank + 1) % world_size]
 
 
 class _CudaArray:

@@ -11,6 +11,7 @@ CUDA device ordinal plus the size of the drawing buffer the flow FBO follows.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -39,7 +40,8 @@ class Device:
         #   "a2a"  = band exchange: all-to-all of sorted fragment slices, one grid band folded per rank; no serial
         #            dependency between ranks, but the torch.distributed all-to-all it rides on is host-bound today
         #   "dist" = the same ring over torch.distributed send/recv/broadcast (also what the gloo tests run)
-        import os
+        #   "bands" = parallel fold over CUDA-IPC peer memory: every rank owns the grid tiles t % world == rank and folds
+        #            them with all ranks' fragments, read over NVLink in rank order; two all-rank barriers per step
         self.ring = ring or os.environ.get("TB_RING", "peer")
 
 
@@ -161,6 +163,7 @@ class Particles:
         self.col0, self.col1 = shard_columns(self.shape[0], gl.rank, gl.world_size)
         self.flow_shape = [1, 1]
         self._ring_ready = False
+        self._bands_ready = False
         self._L = N.load()
         cfg = N.TbConfig(self.shape[0], self.shape[1], self.col0, self.col1, 1, 1, gl.device, 0)
         ctx = C.c_void_p()
@@ -195,6 +198,7 @@ class Particles:
         N.check(self._ctx, self._L.tb_resize_flow(self._ctx, w, h))
         self.flow_shape = [w, h]
         self._ring_ready = False          # new allocation: the IPC handles must be exchanged again
+        self._bands_ready = False
 
     def step(self, update, buffer=None):                                # src/particles.js:123-145
         """Runs `self.logic` once over the state texture.  buffer=None rotates the ping-pong
@@ -253,12 +257,18 @@ class Particles:
         if gl.world_size == 1:
             N.check(ctx, L.tb_splat_flow(ctx, float(u["time"])))
             return
+        if gl.ring == "bands":
+            self._ensure_bands()          # before the collect: the export fixes (and may reallocate) the fragment buffers
         N.check(ctx, L.tb_splat_collect(ctx, float(u["time"])))
         G = self.flow_shape[0] * self.flow_shape[1]
         if gl.ring == "a2a" and G % (gl.world_size * 128) == 0:
             # band exchange: all-to-all of fragment slices, every rank folds one band (scales with the rank count)
             from .multi_gpu import band_exchange_fold
             band_exchange_fold(self)
+        elif gl.ring == "bands":
+            # parallel ordered fold over peer memory: every rank folds its own tiles of the grid with the fragments
+            # of all ranks, read over NVLink in rank order; no rank waits for another rank's fold
+            N.check(ctx, L.tb_splat_fold_bands(ctx))
         elif gl.ring in ("peer", "a2a"):
             # the ordered fold over peer memory: chunks travel rank to rank inside the fold kernels' own stores
             self._ensure_ring()
@@ -284,6 +294,24 @@ class Particles:
         buf = (C.c_ubyte * nbytes).from_buffer_copy(nxt)
         N.check(ctx, L.tb_ring_connect(ctx, gl.rank, gl.world_size, buf, nbytes))
         self._ring_ready = True
+
+    def _ensure_bands(self):
+        """Exchange CUDA IPC handles of (sorted fragments, segment table, flow grid, flags) once per flow-grid
+        allocation and map every rank's.  The fragment buffers are fixed at `TB_BANDS_RESERVE` (default 6)
+        fragments per local particle while mapped."""
+        if self._bands_ready:
+            return
+        from .multi_gpu import gather_handles
+        L, ctx, gl = self._L, self._ctx, self.gl
+        per = float(os.environ.get("TB_BANDS_RESERVE", "6"))
+        reserve = min(int(per * (self.col1 - self.col0) * self.shape[1]) + (1 << 16), (1 << 31) - 1)
+        nbytes = L.tb_bands_handle_bytes()
+        mine = (C.c_ubyte * nbytes)()
+        N.check(ctx, L.tb_bands_export(ctx, reserve, mine, nbytes))
+        blobs = gather_handles(bytes(mine), gl.world_size, gl.group, gl.device)
+        buf = (C.c_ubyte * (nbytes * gl.world_size)).from_buffer_copy(b"".join(blobs))
+        N.check(ctx, L.tb_bands_connect(ctx, gl.rank, gl.world_size, buf, nbytes * gl.world_size))
+        self._bands_ready = True
 
     # -- plumbing ------------------------------------------------------------------------
     def stream_handle(self) -> int:
