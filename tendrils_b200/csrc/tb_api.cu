@@ -764,6 +764,8 @@ int tb_bands_connect(tb_ctx *c, int32_t rank, int32_t world, const void *all_han
         }
     }
     c->band_peers.n = world; c->band_peers.me = rank;
+    // barriers, NVLink-bound pushes and latency-bound blend chains leave SMs idle: let the next step's noise run there
+    c->overlap = true;
     // scratch of the owner side: lengths / offsets per (local texel, source), the merged segment table
     const size_t G = static_cast<size_t>(c->W) * c->H;
     const int tiles = static_cast<int>((G + 31) / 32);

@@ -40,9 +40,11 @@ class Device:
         #   "a2a"  = band exchange: all-to-all of sorted fragment slices, one grid band folded per rank; no serial
         #            dependency between ranks, but the torch.distributed all-to-all it rides on is host-bound today
         #   "dist" = the same ring over torch.distributed send/recv/broadcast (also what the gloo tests run)
-        #   "bands" = parallel fold over CUDA-IPC peer memory: every rank owns the grid tiles t % world == rank and folds
-        #            them with all ranks' fragments, read over NVLink in rank order; two all-rank barriers per step
-        self.ring = ring or os.environ.get("TB_RING", "peer")
+        #   "bands" = parallel fold over CUDA-IPC peer memory: every rank owns the grid tiles t % world == rank; the
+        #            sources push their sorted fragments to the owners over NVLink, laid out per texel in rank order,
+        #            and the owners fold and publish their tiles; four all-rank barriers per step, no serial chain
+        #   default: "peer" on 2 ranks, "bands" on more (measured on 8 x B200, profiles/r01_multi_gpu.txt)
+        self.ring = ring or os.environ.get("TB_RING") or ("peer" if self.world_size <= 2 else "bands")
 
 
 class Shader:
