@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- particle-steps/s of the Tendrils step (integrate + flow splat + respawn) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg1|cfg5]
 
 N > 1 is launched by torchrun (one rank per GPU); rank 0 prints ONE JSON line.
 
@@ -38,8 +38,14 @@ WORKLOADS = {
     "cfg3": dict(R=4096, G=1024, respawn="best-sample", every=60,
                  desc="4096x4096 particles per GPU, 1024^2 flow grid, flowDecay + trail splat, "
                       "direct image-pixel spawn (spawnImage) at step 0, best-sample image respawn (spawnSamples) every 60th step"),
+    # strong scaling: the texture is 4096 x 32768 (= 8 shards of 4096^2) whatever the rank count
+    "cfg5": dict(R=4096, rows=32768, G=2048, respawn="best-sample", every=30, optical=True,
+                 desc="2^27 particles in total (4096 x 32768 texture, column shards), 2048^2 flow grid, every step the optical "
+                      "flow of a synthetic two-frame video pair (moving gaussian blobs) is drawn into the flow grid, "
+                      "best-sample respawn from the current frame every 30th step"),
 }
 METRIC = "particle_steps_per_sec"
+OPTICAL = {"speed": 0.08, "offset": 0.1, "scaleUV": [-1, -1]}      # as the parity test drives src/optical-flow
 UNIT = "particle-steps/s"
 
 
@@ -48,10 +54,17 @@ def synthetic_image(n):
     return mk(n, n)
 
 
-def algorithmic_bytes(n_particles, grid):
+def synthetic_frames(n, count=8):
+    from util import synthetic_video as mk
+    return mk(n, n, count)
+
+
+def algorithmic_bytes(n_particles, grid, optical=False):
     """SURVEY.md 8(d): state read+write 32 B/particle; flow grid gathered once 16 B/texel;
-    flow update read+write 32 B/texel."""
-    return {"integrate": 32 * n_particles + 16 * grid, "splat": 32 * grid, "step": 32 * n_particles + 48 * grid}
+    flow update read+write 32 B/texel.  The optical-flow pass adds two RGBA8 frames read (8 B/texel)
+    and one more read+write of the grid (32 B/texel)."""
+    extra = 40 * grid if optical else 0
+    return {"integrate": 32 * n_particles + 16 * grid, "splat": 32 * grid, "step": 32 * n_particles + 48 * grid + extra}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -121,7 +134,7 @@ def build_sim(wl, rank, world, local_rank, group):
     t = T.Tendrils(T.Device(G, G, device=local_rank, rank=rank, world_size=world, group=group))
     # N ranks: one R x (R*N) texture sharded by columns (R/N columns x R*N rows = R^2 particles per rank).
     # Widening instead (R*N x R) would leave the exact 1:1 vertex->column range of the reference's LUT.
-    t.setup([R, R * world])
+    t.setup([R, wl.get("rows") or R * world])
     t.resize()
     first = spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}})  # src/demo.main.js:1402-1405
     sp = None
@@ -133,6 +146,16 @@ def build_sim(wl, rank, world, local_rank, group):
         sp = PixelSpawner(t.gl, {"shader": bestSampleFrag, "buffer": img, "speed": 1, "bias": 1, "jitterRad": 2,
                                  "spawnSize": [1, 1]})
         first.spawnMatrix = sp.spawnMatrix = flip
+    if wl.get("optical"):
+        # cfg5: the video frames live on the device (a decoder would put them there); every step the pair
+        # (frame k, frame k-1) drives the optical-flow pass, every respawn samples the current frame
+        import torch
+        from tendrils_b200.optical_flow import OpticalFlow
+        dev = torch.device("cuda", local_rank)
+        t.video = [torch.as_tensor(f, device=dev) for f in synthetic_frames(G)]
+        t.optical = OpticalFlow(t.gl, None, dict(OPTICAL))
+        t.optical.resize([G, G])
+        first.setPixels(t.video[0].float() / 255.0)
     return t, first, sp
 
 
@@ -157,9 +180,16 @@ def run_ours(args, wl, rank, world, local_rank):
         if k == 0:
             first.spawn(t)                    # spawnShader ticks the timer itself (src/index.js:433)
         elif wl["every"] and k % wl["every"] == 0:
+            if wl.get("optical"):
+                sp.setPixels(t.video[k % len(t.video)].float() / 255.0)
             sp.spawn(t)
         t.timer.tick()
         t.step().draw()
+        if wl.get("optical"):                  # drawn into the flow FBO after the particles (src/demo.main.js:1131-1159)
+            of = t.optical
+            of.setPixels(t.video[k % len(t.video)])
+            of.update({"speedLimit": t.state["speedLimit"], "time": t.timer.time, "viewSize": t.viewSize}).render(t)
+            of.step()
         counter["k"] = k + 1
 
     def barrier():
@@ -227,7 +257,7 @@ def run_ours(args, wl, rank, world, local_rank):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("k_integrate")
     except Exception:
         pass
-    ab = algorithmic_bytes(n_local, grid)
+    ab = algorithmic_bytes(n_local, grid, bool(wl.get("optical")))
     fin_us = 1e3 * tm["integrate_ms"] / max(tm["n_integrate"], 1)      # main-stream launch (fused, or the finish half)
     noise_us = 1e3 * tm["noise_ms"] / max(tm["n_integrate"], 1)        # side-stream noise launch, hidden under the splat
     int_us = fin_us + noise_us                                          # device time of logic.frag, all launches
@@ -238,7 +268,8 @@ def run_ours(args, wl, rank, world, local_rank):
     out = {
         "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if wl.get("rows") else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "particles_per_gpu": n_local, "particles_total": n_total,
                    "flow_grid": [wl["G"], wl["G"]], "state": "reference defaults (src/index.js:29-57), noise on",
                    "splat": "exact ordered alpha-over (reference semantics)", "fragments_last_step": frags,
@@ -272,34 +303,46 @@ def cpu_arm(args, wl, budget_s, as_reference):
     from oracle import oracle as O
     O.build()
     R, G = wl["R"], wl["G"]
-    cols = (0, max(R // 4, 1))                          # the bounded sample: the first quarter of the columns
-    n_sample = (cols[1] - cols[0]) * R
+    PH = wl.get("rows") or R
+    cols = (0, max(min(R // 4, (1 << 22) // PH), 1))   # the bounded sample: the first columns, at most a quarter / 4M particles
+    n_sample = (cols[1] - cols[0]) * PH
     Pm = O.make_params()
     S = O.make_spawn_pixels(jitter=(np.float32(np.float32(1.0 / G) * 2), np.float32(np.float32(1.0 / G) * 2)),
                             spawnMatrix=(-1, 0, 0, 0, 1, 0, 0, 0, 1))
     img = synthetic_image(G)
-    state = {"cur": O.spawn_init(R, R), "prev": O.spawn_init(R, R), "k": 0, "time": 0.0}
-    targets = np.zeros((R, R, 4), np.float32)
+    state = {"cur": O.spawn_init(R, PH), "prev": O.spawn_init(R, PH), "k": 0, "time": 0.0}
+    targets = np.zeros((R, PH, 4), np.float32)
     flow = np.zeros((G, G, 4), np.float32)
     dt = 1000 / 60
+    video = synthetic_frames(G) if wl.get("optical") else None
+    last_frame = np.zeros((G, G, 4), np.uint8)
+    if video:
+        img = video[0].astype(np.float32) / np.float32(255.0)
 
     def one_step():
         k = state["k"]
         if k == 0 or (wl["every"] and k % wl["every"] == 0):
             state["time"] += dt
             if k == 0 and wl["respawn"] == "ball":
-                new = O.spawn_ball(R, R, 0.3, 0.005, cols=cols)
+                new = O.spawn_ball(R, PH, 0.3, 0.005, cols=cols)
             elif k == 0:
                 S.speed = 0.3
-                new = O.spawn_pixels_direct(S, R, R, img, state["time"], cols=cols)
+                new = O.spawn_pixels_direct(S, R, PH, img, state["time"], cols=cols)
                 S.speed = 1.0
             else:
-                new = O.spawn_pixels_sample(S, "best", state["cur"], img, state["time"], cols=cols)
+                src = video[k % len(video)].astype(np.float32) / np.float32(255.0) if video else img
+                new = O.spawn_pixels_sample(S, "best", state["cur"], src, state["time"], cols=cols)
             state["prev"], state["cur"] = state["cur"], new
         state["time"] += dt
         new = O.integrate(Pm, state["cur"], targets, flow, state["time"], dt, cols=cols)
         state["prev"], state["cur"] = state["cur"], new
         O.splat(Pm, state["cur"], state["prev"], flow, state["time"], cols=cols, mt=True)
+        if video:
+            nonlocal last_frame
+            frame = video[k % len(video)]
+            O.optical_flow(flow, frame, last_frame, viewSize=(1.0, 1.0), scaleUV=tuple(OPTICAL["scaleUV"]), offset=OPTICAL["offset"],
+                           lambda_=0.001, speed=OPTICAL["speed"], speedLimit=Pm.speedLimit, time=np.float32(state["time"]))
+            last_frame = frame
         state["k"] = k + 1
 
     if as_reference:
@@ -315,8 +358,8 @@ def cpu_arm(args, wl, budget_s, as_reference):
         one_step()
     el = time.perf_counter() - t0
     return {"value": n_sample * steps / el, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-            "sample": f"columns [{cols[0]},{cols[1]}) of the {R}x{R} particle texture ({n_sample} particles) on the full "
-                      f"{G}^2 flow grid, {steps} steps of integrate + ordered splat (+ respawn when due), OpenMP over "
+            "sample": f"columns [{cols[0]},{cols[1]}) of the {R}x{PH} particle texture ({n_sample} particles) on the full "
+                      f"{G}^2 flow grid, {steps} steps of integrate + ordered splat (+ respawn / optical flow when due), OpenMP over "
                       f"{O.num_threads()} threads; oracle/tendrils_oracle.c",
             "steps": steps, "seconds": el, "ms_per_step": 1e3 * el / steps}
 
@@ -328,7 +371,7 @@ def run_reference(args, wl, rank, world):
     return {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if wl.get("rows") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}",
                    "note": "CPU oracle port of the reference shaders (the WebGL reference cannot run here); host cores only"},
         "cpu_baseline": cb,

@@ -199,6 +199,8 @@ int tb_reset(tb_ctx *ctx);
  * timer first (src/index.js:433) and passes the resulting time. */
 int tb_spawn_init(tb_ctx *ctx, tb_target target);                               /* spawn/init/index.frag */
 int tb_spawn_ball(tb_ctx *ctx, float radius, float speed, tb_target target);    /* spawn/ball/index.frag */
+/* `rgba` may be a host pointer (borrowed for the call) or a pointer to memory of this device (unified
+ * addressing; copied in stream order on tb_stream, the caller keeps it unchanged until then). */
 int tb_set_spawn_image(tb_ctx *ctx, const float *rgba, int32_t w, int32_t h);   /* PixelSpawner.setPixels */
 int tb_spawn_pixels(tb_ctx *ctx, const tb_pixel_spawner *params, tb_spawn_variant variant,
                     tb_spawn_source source, float time, tb_target target);
@@ -219,7 +221,8 @@ int tb_debug_segments(tb_ctx *ctx, uint32_t *host, int64_t n_words);
 /* OpticalFlow.update() + screen.render() with the flow FBO bound (src/optical-flow/index.frag:55-81,
  * src/optical-flow/index.js:50-58, call site src/demo.main.js:1131-1156): the gradient optical flow of two RGBA8
  * frames (view = current, last = previous; w*h*4 bytes each, texel row 0 first), written in the flow encoding
- * and alpha-over blended into the flow grid. */
+ * and alpha-over blended into the flow grid.  The frames may be host pointers (borrowed for the call) or both
+ * device pointers (e.g. decoded video frames; copied in stream order, no host synchronisation). */
 int tb_optical_flow(tb_ctx *ctx, const tb_optical_flow_params *params, const uint8_t *view_rgba8,
                     const uint8_t *last_rgba8, int32_t w, int32_t h);
 

@@ -120,3 +120,17 @@ def check(ctx, status: int):
     if status != 0:
         msg = load().tb_last_error(ctx)
         raise TendrilsError((msg or b"unknown error").decode() + f" (status {status})")
+
+
+def is_device_array(a) -> bool:
+    """A torch CUDA tensor (anything with .is_cuda set): its memory is handed to the library as a device pointer."""
+    return bool(getattr(a, "is_cuda", False))
+
+
+def array_pointer(a, dtype: str) -> int:
+    """Address of a contiguous numpy array or torch CUDA tensor of the given dtype name."""
+    if is_device_array(a):
+        if str(a.dtype) != f"torch.{dtype}" or not a.is_contiguous():
+            raise TendrilsError(f"tendrils-b200: device arrays must be contiguous {dtype}")
+        return a.data_ptr()
+    return a.ctypes.data

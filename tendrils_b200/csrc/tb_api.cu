@@ -248,6 +248,14 @@ int ensure_frag_cap(tb_ctx *c, uint64_t need) {
     return TB_OK;
 }
 
+// Image / frame arguments may live on the host or (unified addressing) on this device, e.g. a decoded video frame
+// or a torch tensor: device-resident inputs are used in stream order, with no copy-back synchronisation.
+bool is_device_pointer(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
 int check_launch(tb_ctx *c, const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, TB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -1186,8 +1194,8 @@ int tb_set_spawn_image(tb_ctx *c, const float *rgba, int32_t w, int32_t h) {
         TB_CUDA(c, cudaMalloc(&c->image, need * sizeof(float4)));
         c->image_cap = need;
     }
-    TB_CUDA(c, cudaMemcpyAsync(c->image, rgba, need * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));       // the host pointer is only borrowed
+    TB_CUDA(c, cudaMemcpyAsync(c->image, rgba, need * sizeof(float4), cudaMemcpyDefault, c->stream));
+    if (!is_device_pointer(rgba)) TB_CUDA(c, cudaStreamSynchronize(c->stream));       // a host pointer is only borrowed
     c->IW = w; c->IH = h;
     return TB_OK;
 }
@@ -1319,15 +1327,16 @@ int tb_optical_flow(tb_ctx *c, const tb_optical_flow_params *params, const uint8
         TB_CUDA(c, cudaMalloc(&c->frames, 2 * n * sizeof(uchar4)));
         c->frames_cap = 2 * n;
     }
-    TB_CUDA(c, cudaMemcpyAsync(c->frames, view_rgba8, n * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream));
-    TB_CUDA(c, cudaMemcpyAsync(c->frames + n, last_rgba8, n * sizeof(uchar4), cudaMemcpyHostToDevice, c->stream));
+    const bool resident = is_device_pointer(view_rgba8) && is_device_pointer(last_rgba8);
+    TB_CUDA(c, cudaMemcpyAsync(c->frames, view_rgba8, n * sizeof(uchar4), cudaMemcpyDefault, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(c->frames + n, last_rgba8, n * sizeof(uchar4), cudaMemcpyDefault, c->stream));
     OpticalArgs A{};
     A.flow = c->flow; A.view = c->frames; A.last = c->frames + n;
     A.W = c->W; A.H = c->H; A.IW = w; A.IH = h;
     A.U = *params;
     k_optical_flow<<<blocks_for(static_cast<long long>(c->W) * c->H, 256), 256, 0, c->stream>>>(A);
     if (int r = check_launch(c, "k_optical_flow")) return r;
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));       // the host frames are only borrowed
+    if (!resident) TB_CUDA(c, cudaStreamSynchronize(c->stream));       // host frames are only borrowed
     return TB_OK;
 }
 

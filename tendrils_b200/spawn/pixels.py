@@ -62,5 +62,6 @@ class PixelSpawner:
         return tendrils.spawnShader(self.shader, update or self.update, *rest)
 
     def setPixels(self, pixels):                                         # :65-67
-        self.buffer = np.ascontiguousarray(pixels, dtype=np.float32)
+        from .. import _native as N
+        self.buffer = pixels if N.is_device_array(pixels) else np.ascontiguousarray(pixels, dtype=np.float32)
         return self.buffer

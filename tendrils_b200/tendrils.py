@@ -239,10 +239,12 @@ class Particles:
             elif self.buffers and src is self.buffers[0]:
                 source = N.TB_SOURCE_PARTICLES
             else:
-                img = np.ascontiguousarray(src, dtype=np.float32)
+                img = src if N.is_device_array(src) else np.ascontiguousarray(src, dtype=np.float32)
                 if img.ndim != 3 or img.shape[2] != 4:
                     raise N.TendrilsError("tendrils-b200: spawnData must be an [h,w,4] float image")
-                N.check(ctx, L.tb_set_spawn_image(ctx, img.ctypes.data_as(N._fp), img.shape[1], img.shape[0]))
+                ptr = C.cast(C.c_void_p(N.array_pointer(img, "float32")), N._fp)
+                N.check(ctx, L.tb_set_spawn_image(ctx, ptr, img.shape[1], img.shape[0]))
+                self._spawn_image = img       # a device image is copied in stream order: keep it alive
                 source = N.TB_SOURCE_IMAGE
             N.check(ctx, L.tb_spawn_pixels(ctx, C.byref(ps), sh.variant, source, float(u["time"]), target))
         else:

@@ -464,3 +464,38 @@ def test_determinism_full_size(T):
         outs.append((t.particles.buffers[0].download(), t.flow.download()))
         t.dispose()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_device_resident_inputs_equal_host_inputs(T):
+    """Frames and spawn images may already live on the device (unified addressing): same bits as host inputs."""
+    import torch
+    from tendrils_b200.optical_flow import OpticalFlow
+    from tendrils_b200.spawn import PixelSpawner
+    from tendrils_b200.spawn import pixels as PX
+    from util import synthetic_video
+    R, G = 64, 48
+    frames = synthetic_video(G, G, 4)
+    outs = []
+    for on_device in (False, True):
+        conv = (lambda a: torch.as_tensor(a, device="cuda")) if on_device else (lambda a: a)
+        t = make(T, R, G)
+        of = OpticalFlow(t.gl, None, {"speed": 0.08, "offset": 0.1, "scaleUV": [-1, -1]})
+        of.resize([G, G])
+        sp = PixelSpawner(t.gl, {"shader": PX.pixelsFrag, "buffer": conv(frames[0].astype(np.float32) / np.float32(255)),
+                                 "speed": 0.3, "jitterRad": 2, "spawnSize": [1, 1]})
+        best = PixelSpawner(t.gl, {"shader": PX.bestSampleFrag, "buffer": None, "speed": 1, "bias": 1, "jitterRad": 2,
+                                   "spawnSize": [1, 1]})
+        sp.spawn(t)
+        for k in range(6):
+            if k == 3:
+                best.setPixels(conv(frames[k % 4].astype(np.float32) / np.float32(255)))
+                best.spawn(t)
+            t.timer.tick(); t.step().draw()
+            of.setPixels(conv(frames[k % 4]))
+            of.update({"speedLimit": t.state["speedLimit"], "time": t.timer.time, "viewSize": t.viewSize}).render(t)
+            of.step()
+        outs.append((t.particles.buffers[0].download(), t.flow.download()))
+        assert np.abs(outs[-1][1]).max() > 0
+        t.dispose()
+    assert_bits_equal(outs[1][0], outs[0][0], "state: device-resident vs host inputs")
+    assert_bits_equal(outs[1][1], outs[0][1], "flow: device-resident vs host inputs")
