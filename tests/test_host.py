@@ -150,3 +150,33 @@ def test_env_knobs_are_documented():
     doc = open(os.path.join(ROOT, "DESIGN.md")).read()
     missing = sorted(n for n in names if n not in doc)
     assert not missing, missing
+
+
+def test_default_transport_by_world_size(monkeypatch):
+    """2 ranks: the serial peer ring (one hop); 3 or more: the parallel band fold; TB_RING overrides."""
+    import tendrils_b200 as T
+    monkeypatch.delenv("TB_RING", raising=False)
+    assert T.Device(4, 4, world_size=2, rank=1).ring == "peer"
+    assert T.Device(4, 4, world_size=8, rank=3).ring == "bands"
+    assert T.Device(4, 4, world_size=8, rank=3, ring="dist").ring == "dist"
+    monkeypatch.setenv("TB_RING", "a2a")
+    assert T.Device(4, 4, world_size=8).ring == "a2a"
+
+
+def test_synthetic_video_loops_and_moves():
+    from util import synthetic_video
+    a, b = synthetic_video(40, 24, 4), synthetic_video(40, 24, 4)
+    assert all(f.shape == (24, 40, 4) and f.dtype == np.uint8 for f in a)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))                    # closed form: no RNG
+    assert not np.array_equal(a[0], a[1]) and (a[0][..., 3] == 255).all() and a[0][..., :3].max() > 100
+
+
+def test_bench_workloads_and_bytes():
+    import bench
+    assert set(bench.WORKLOADS) >= {"cfg1", "cfg2", "cfg3", "cfg5"}
+    n, g = 4096 * 4096, 1024 * 1024
+    ab = bench.algorithmic_bytes(n, g)
+    assert ab["step"] == 587_202_560                                          # SURVEY.md 8(d), cfg3
+    assert bench.algorithmic_bytes(n, g, optical=True)["step"] == ab["step"] + 40 * g
+    w5 = bench.WORKLOADS["cfg5"]
+    assert w5["R"] * w5["rows"] == 2 ** 27 and w5["G"] == 2048
