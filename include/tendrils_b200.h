@@ -88,6 +88,13 @@ typedef struct tb_optical_flow_params {
     float offset, lambda, speed, speedLimit, time;
 } tb_optical_flow_params;
 
+/* Uniforms of a FlowLine's Line (src/flow-line/index.js:19-22, src/geom/line/index.js:16-20; the app merges
+ * tendrils.state in before every draw, src/demo.main.js:1118, which is where speedLimit comes from). */
+typedef struct tb_flow_line_params {
+    float viewSize[2];
+    float rad, speed, speedLimit, crestShape;
+} tb_flow_line_params;
+
 /* Where a spawn pass writes: spawnShader(shader, update) vs spawnShader(shader, update, tendrils.targets)
  * (src/index.js:432-457, src/particles.js:123-130). */
 typedef enum tb_target { TB_TARGET_STATE = 0, TB_TARGET_TARGETS = 1 } tb_target;
@@ -223,6 +230,14 @@ int tb_debug_segments(tb_ctx *ctx, uint32_t *host, int64_t n_words);
  * frames (view = current, last = previous; w*h*4 bytes each, texel row 0 first), written in the flow encoding
  * and alpha-over blended into the flow grid.  The frames may be host pointers (borrowed for the call) or both
  * device pointers (e.g. decoded video frames; copied in stream order, no host synchronisation). */
+/* FlowLine.draw() with the flow FBO bound (src/demo.main.js:1107-1121): the TRIANGLE_STRIP of a pointer path,
+ * two vertices per path point, run through src/flow-line/index.vert and src/flow-line/index.frag and alpha-over
+ * blended into the flow grid in triangle order.  The six attribute arrays are the ones Line.update() fills
+ * (src/geom/line/index.js:73-117, src/flow-line/index.js:54-69): position, normal, previous hold 2 floats per
+ * vertex, miter, time, dt one.  Fewer than 3 vertices draw nothing. */
+int tb_flow_line(tb_ctx *ctx, const tb_flow_line_params *params, int32_t n_vertices, const float *position,
+                 const float *normal, const float *miter, const float *previous, const float *time, const float *dt);
+
 int tb_optical_flow(tb_ctx *ctx, const tb_optical_flow_params *params, const uint8_t *view_rgba8,
                     const uint8_t *last_rgba8, int32_t w, int32_t h);
 

@@ -34,6 +34,12 @@ class SpawnPixels(C.Structure):
                 ("bias", C.c_float), ("spawnMatrix", C.c_float * 9), ("flowDecay", C.c_float)]
 
 
+class FlowLineUniforms(C.Structure):
+    """or_flow_line_uniforms (reference src/flow-line/index.js:19-22 + src/geom/line/index.js:16-20)."""
+    _fields_ = [("viewSize", C.c_float * 2), ("rad", C.c_float), ("speed", C.c_float), ("speedLimit", C.c_float),
+                ("crestShape", C.c_float)]
+
+
 APPLY_COLOR, APPLY_BRIGHTEST, APPLY_IDENTITY, APPLY_FLOW = 0, 1, 2, 3
 
 DEFAULT_STATE = dict(damping=0.043, speedLimit=0.01, forceWeight=0.016, varyForce=-0.1,
@@ -116,6 +122,12 @@ def lib():
         L.or_optical_flow.restype = None
         L.or_optical_flow.argtypes = [_fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, _fp, C.c_int, C.c_int]
+        L.or_flow_line_vertex.restype = None
+        L.or_flow_line_vertex.argtypes = [C.POINTER(FlowLineUniforms), _fp, _fp, C.c_float, _fp, C.c_float, C.c_float, _fp]
+        L.or_flow_line_fragment.restype = None
+        L.or_flow_line_fragment.argtypes = [C.c_float, _fp, _fp]
+        L.or_flow_line.restype = C.c_longlong
+        L.or_flow_line.argtypes = [C.POINTER(FlowLineUniforms), C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int]
         L.or_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -228,3 +240,36 @@ def optical_flow(flow, view, last, viewSize=(1.0, 1.0), scaleUV=(1.0, -1.0), off
     lib().or_optical_flow(_p(vs), _p(sc), f32(offset), f32(lambda_), f32(speed), f32(speedLimit), f32(time),
                           view.ctypes.data, last.ctypes.data, iw, ih, _p(flow), W, H)
     return flow
+
+
+def flow_line_uniforms(viewSize=(1.0, 1.0), rad=0.1, speed=3.0, speedLimit=0.01, crestShape=0.6):
+    u = FlowLineUniforms()
+    u.viewSize[0], u.viewSize[1] = float(viewSize[0]), float(viewSize[1])
+    u.rad, u.speed, u.speedLimit, u.crestShape = float(rad), float(speed), float(speedLimit), float(crestShape)
+    return u
+
+
+def flow_line_vertex(U, position, normal, miter, previous, time, dt):
+    """src/flow-line/index.vert for one vertex: (gl_Position.xy, values.rgba, crest.xy, sdf)."""
+    out = np.zeros(9, np.float32)
+    pos, nor, prv = (np.ascontiguousarray(v, np.float32) for v in (position, normal, previous))
+    lib().or_flow_line_vertex(C.byref(U), _p(pos), _p(nor), f32(miter), _p(prv), f32(time), f32(dt), _p(out))
+    return out
+
+
+def flow_line_fragment(crestShape, in7):
+    """src/flow-line/index.frag for one fragment: in7 = (values.rgba, crest.xy, sdf)."""
+    out = np.zeros(4, np.float32)
+    a = np.ascontiguousarray(in7, np.float32)
+    lib().or_flow_line_fragment(f32(crestShape), _p(a), _p(out))
+    return out
+
+
+def flow_line(U, attributes, flow):
+    """Draws the strip into flow ([H,W,4], in place).  attributes: dict of float32 arrays as gl-geometry holds
+    them (position [n,2], normal [n,2], miter [n], previous [n,2], time [n], dt [n]).  Returns the fragment count."""
+    H, W = flow.shape[:2]
+    a = {k: np.ascontiguousarray(attributes[k], np.float32) for k in ("position", "normal", "miter", "previous", "time", "dt")}
+    n = a["miter"].shape[0]
+    return lib().or_flow_line(C.byref(U), n, _p(a["position"]), _p(a["normal"]), _p(a["miter"]), _p(a["previous"]),
+                              _p(a["time"]), _p(a["dt"]), _p(flow), W, H)

@@ -659,3 +659,110 @@ void or_optical_flow(const float viewSize[2], const float scaleUV[2], float offs
             blend_over(flow + 4 * ((size_t)gy * W + gx), c);
         }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * f4: pointer flow lines drawn into the flow grid -- src/flow-line/index.vert, src/flow-line/index.frag over the
+ * TRIANGLE_STRIP that src/geom/line/index.js builds (two vertices per path point, attributes position, normal,
+ * miter, previous, time, dt).  Fixed function per spec/PARITY.md FL3-FL6: vertices snapped to 1/256 pixel,
+ * exact integer edge functions, top-left rule, affine interpolation from the edge functions, alpha-over blend
+ * in triangle order with the unclamped alpha values.a - d.
+ * ------------------------------------------------------------------------------------------------ */
+static inline float g_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+
+/* src/flow-line/index.vert:21-37.  out9 = (gl_Position.xy, values.rgba, crest.xy, sdf) */
+void or_flow_line_vertex(const or_flow_line_uniforms *U, const float position[2], const float normal[2], float miter,
+                         const float previous[2], float time, float dt, float *out9) {
+    float sdf = g_sign(miter);
+    float rate = U->speed / g_max(dt, 1.0f);
+    float velx = (position[0] - previous[0]) * rate, vely = (position[1] - previous[1]) * rate;
+    float values[4];
+    flow_colour(velx, vely, time, U->speedLimit, values);        /* flow(vel, speedLimit), time = the attribute */
+    float crx = normal[0] * miter, cry = normal[1] * miter;
+    float rad = U->rad * values[3];
+    float vx = position[0] + (normal[0] * rad) * miter, vy = position[1] + (normal[1] * rad) * miter;   /* expand() */
+    out9[0] = vx * U->viewSize[0]; out9[1] = vy * U->viewSize[1];
+    out9[2] = values[0]; out9[3] = values[1]; out9[4] = values[2]; out9[5] = values[3];
+    out9[6] = crx; out9[7] = cry; out9[8] = sdf;
+}
+
+/* src/flow-line/index.frag:10-17.  in7 = (values.rgba, crest.xy, sdf) */
+void or_flow_line_fragment(float crestShape, const float *in7, float *rgba) {
+    float d = fabsf(in7[6]);
+    float speed = g_length2(in7[0], in7[1]) * (1.0f - d);
+    float t = d * crestShape;
+    float mx = g_mix(in7[0], in7[4], t), my = g_mix(in7[1], in7[5], t);
+    float len = g_length2(mx, my);
+    rgba[0] = (mx / len) * speed; rgba[1] = (my / len) * speed;   /* normalize(m)*speed */
+    rgba[2] = in7[2];
+    rgba[3] = in7[3] - d;
+}
+
+static inline long long fl_orient(long long ax, long long ay, long long bx, long long by, long long cx, long long cy) {
+    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+
+/* a centre exactly on the edge a->b of a counter-clockwise triangle belongs to it iff the edge runs down, or is
+ * horizontal and runs towards -x (FL4) */
+static inline int fl_tie(long long ax, long long ay, long long bx, long long by) {
+    long long dx = bx - ax, dy = by - ay;
+    return dy < 0 || (dy == 0 && dx < 0);
+}
+
+long long or_flow_line(const or_flow_line_uniforms *U, int n_vertices, const float *position, const float *normal,
+                       const float *miter, const float *previous, const float *time, const float *dt,
+                       float *flow, int W, int H) {
+    if (n_vertices < 3) return 0;
+    float *vs = (float *)malloc(sizeof(float) * 9 * (size_t)n_vertices);
+    long long *fx = (long long *)malloc(sizeof(long long) * 2 * (size_t)n_vertices);
+    char *ok = (char *)malloc((size_t)n_vertices);
+    const float hw = (float)W / 2.0f, hh = (float)H / 2.0f;
+    for (int i = 0; i < n_vertices; ++i) {
+        float *o = vs + 9 * (size_t)i;
+        or_flow_line_vertex(U, position + 2 * i, normal + 2 * i, miter[i], previous + 2 * i, time[i], dt[i], o);
+        float xw = o[0] * hw + hw, yw = o[1] * hh + hh;                       /* FL3 */
+        ok[i] = isfinite(xw) && isfinite(yw) && fabsf(xw) < 262144.0f && fabsf(yw) < 262144.0f;
+        fx[2 * i] = ok[i] ? llrintf(xw * 256.0f) : 0;
+        fx[2 * i + 1] = ok[i] ? llrintf(yw * 256.0f) : 0;
+    }
+    long long frags = 0;
+    for (int t = 0; t + 2 < n_vertices; ++t) {
+        if (!(ok[t] && ok[t + 1] && ok[t + 2])) continue;
+        const long long x0 = fx[2 * t], y0 = fx[2 * t + 1], x1 = fx[2 * t + 2], y1 = fx[2 * t + 3], x2 = fx[2 * t + 4], y2 = fx[2 * t + 5];
+        const long long area = fl_orient(x0, y0, x1, y1, x2, y2);
+        if (area == 0) continue;
+        const long long sg = area > 0 ? 1 : -1;
+        /* tie rule on the counter-clockwise orientation: with area < 0 every edge is walked backwards */
+        const int tie0 = sg > 0 ? fl_tie(x1, y1, x2, y2) : fl_tie(x2, y2, x1, y1);
+        const int tie1 = sg > 0 ? fl_tie(x2, y2, x0, y0) : fl_tie(x0, y0, x2, y2);
+        const int tie2 = sg > 0 ? fl_tie(x0, y0, x1, y1) : fl_tie(x1, y1, x0, y0);
+        long long minx = x0 < x1 ? x0 : x1, maxx = x0 > x1 ? x0 : x1, miny = y0 < y1 ? y0 : y1, maxy = y0 > y1 ? y0 : y1;
+        if (x2 < minx) minx = x2;
+        if (x2 > maxx) maxx = x2;
+        if (y2 < miny) miny = y2;
+        if (y2 > maxy) maxy = y2;
+        long long px0 = (minx - 128 + 255) >> 8, px1 = (maxx - 128) >> 8;      /* ceil / floor of (v-128)/256 */
+        long long py0 = (miny - 128 + 255) >> 8, py1 = (maxy - 128) >> 8;
+        if (px0 < 0) px0 = 0;
+        if (py0 < 0) py0 = 0;
+        if (px1 > W - 1) px1 = W - 1;
+        if (py1 > H - 1) py1 = H - 1;
+        const float *v0 = vs + 9 * (size_t)t + 2, *v1 = v0 + 9, *v2 = v1 + 9;
+        for (long long py = py0; py <= py1; ++py)
+            for (long long px = px0; px <= px1; ++px) {
+                const long long cx = px * 256 + 128, cy = py * 256 + 128;
+                const long long e0 = fl_orient(x1, y1, x2, y2, cx, cy), e1 = fl_orient(x2, y2, x0, y0, cx, cy),
+                                e2 = fl_orient(x0, y0, x1, y1, cx, cy);
+                const long long s0 = e0 * sg, s1 = e1 * sg, s2 = e2 * sg;
+                if (!((s0 > 0 || (s0 == 0 && tie0)) && (s1 > 0 || (s1 == 0 && tie1)) && (s2 > 0 || (s2 == 0 && tie2)))) continue;
+                const float b1 = (float)((double)e1 / (double)area), b2 = (float)((double)e2 / (double)area);   /* FL5 */
+                float in7[7], rgba[4];
+                for (int k = 0; k < 7; ++k) in7[k] = (v0[k] + b1 * (v1[k] - v0[k])) + b2 * (v2[k] - v0[k]);
+                or_flow_line_fragment(U->crestShape, in7, rgba);
+                blend_over(flow + 4 * ((size_t)py * W + (size_t)px), rgba);
+                ++frags;
+            }
+    }
+    free(vs); free(fx); free(ok);
+    return frags;
+}
+

@@ -99,6 +99,24 @@ void or_optical_flow(const float viewSize[2], const float scaleUV[2], float offs
                      float speedLimit, float time, const unsigned char *view, const unsigned char *last, int iw, int ih,
                      float *flow, int W, int H);
 
+/* f4: pointer flow lines (reference src/flow-line/index.{vert,frag} over the strip of src/geom/line/index.js).
+ * Uniforms of the Line (src/flow-line/index.js:19-22, src/geom/line/index.js:16-20, state merged in at
+ * src/demo.main.js:1118). */
+typedef struct or_flow_line_uniforms {
+    float viewSize[2];
+    float rad, speed, speedLimit, crestShape;
+} or_flow_line_uniforms;
+/* the vertex stage alone: out9 = (gl_Position.xy, values.rgba, crest.xy, sdf) */
+void or_flow_line_vertex(const or_flow_line_uniforms *U, const float position[2], const float normal[2], float miter,
+                         const float previous[2], float time, float dt, float *out9);
+/* the fragment stage alone: in7 = (values.rgba, crest.xy, sdf) -> gl_FragColor */
+void or_flow_line_fragment(float crestShape, const float *in7, float *rgba);
+/* the whole draw: vertex stage, TRIANGLE_STRIP raster (spec/PARITY.md FL3-FL5), fragment stage, ordered
+ * alpha-over blend into flow [H][W][4]; attribute arrays as gl-geometry holds them.  Returns the fragment count. */
+long long or_flow_line(const or_flow_line_uniforms *U, int n_vertices, const float *position, const float *normal,
+                       const float *miter, const float *previous, const float *time, const float *dt,
+                       float *flow, int W, int H);
+
 int or_num_threads(void);
 
 #ifdef __cplusplus

@@ -5,6 +5,7 @@ built from csrc/ by `python -m tendrils_b200.build`).  This package is the host-
 reference's JS classes on top of it.  There is no CPU fallback.
 """
 from . import spawn  # noqa: F401
+from .flow_line import FlowLine, FlowLines, Line  # noqa: F401
 from .optical_flow import OpticalFlow  # noqa: F401
 from ._native import TendrilsError, lib_path, load  # noqa: F401
 from .tendrils import (INERT, Device, Particles, Shader, Tendrils, Timer, defaults,  # noqa: F401

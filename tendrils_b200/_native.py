@@ -34,6 +34,11 @@ class TbOpticalFlowParams(C.Structure):
                 ("speed", C.c_float), ("speedLimit", C.c_float), ("time", C.c_float)]
 
 
+class TbFlowLineParams(C.Structure):
+    _fields_ = [("viewSize", C.c_float * 2), ("rad", C.c_float), ("speed", C.c_float), ("speedLimit", C.c_float),
+                ("crestShape", C.c_float)]
+
+
 TB_TARGET_STATE, TB_TARGET_TARGETS = 0, 1
 TB_SPAWN_DIRECT, TB_SPAWN_BEST_SAMPLE, TB_SPAWN_BRIGHT_SAMPLE = 0, 1, 2
 TB_SPAWN_COLOR_SAMPLE, TB_SPAWN_DATA_SAMPLE, TB_SPAWN_FLOW_SAMPLE = 3, 4, 5
@@ -76,6 +81,7 @@ SYMBOLS = {
     "tb_download": (C.c_int, [_ctx, C.c_int, _fp, C.c_int64]),
     "tb_blend_into_flow": (C.c_int, [_ctx, _fp, C.c_int32, C.c_int32]),
     "tb_debug_segments": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_int64]),
+    "tb_flow_line": (C.c_int, [_ctx, C.POINTER(TbFlowLineParams), C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp]),
     "tb_optical_flow": (C.c_int, [_ctx, C.POINTER(TbOpticalFlowParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "tb_device_ptr": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "tb_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),

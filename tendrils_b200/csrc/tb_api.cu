@@ -4,6 +4,7 @@
 // Tendrils (src/index.js) and Particles (src/particles.js) classes: ping-pong state
 // buffers, the logic pass, the flow splat, the spawn passes.  No CPU fallback.
 #include "tb_kernels.cuh"
+#include "tb_flowline.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -12,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -46,6 +48,10 @@ struct tb_ctx {
     size_t layer_cap = 0;
     uchar4 *frames = nullptr;               // optical flow: view + last, RGBA8
     size_t frames_cap = 0;
+    float *line_attr = nullptr;             // flow lines: 9 attribute floats per vertex, then the shaded vertices, then the bbox
+    fl::Vertex *line_verts = nullptr;
+    int *line_bbox = nullptr;
+    int line_cap = 0;
 
     // flow splat scratch
     PairEntry *pairs = nullptr;
@@ -1004,6 +1010,7 @@ int tb_destroy(tb_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
     cudaFree(c->frames);
+    cudaFree(c->line_attr); cudaFree(c->line_verts); cudaFree(c->line_bbox);
     cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off); cudaFree(c->row_pair);
     cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->hot); cudaFree(c->d_flag);
     for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); }
@@ -1302,6 +1309,46 @@ int tb_blend_into_flow(tb_ctx *c, const float *rgba, int32_t w, int32_t h) {
     k_blend_layer<<<blocks_for(static_cast<long long>(G), 256), 256, 0, c->stream>>>(c->flow, c->layer, static_cast<int>(G));
     if (int r = check_launch(c, "k_blend_layer")) return r;
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TB_OK;
+}
+
+int tb_flow_line(tb_ctx *c, const tb_flow_line_params *params, int32_t n_vertices, const float *position, const float *normal,
+                 const float *miter, const float *previous, const float *time, const float *dt) {
+    TB_REQUIRE(c, c && params, "null argument");
+    TB_REQUIRE(c, n_vertices >= 0 && n_vertices <= (1 << 24), "tb_flow_line: vertex count out of range");
+    if (n_vertices < 3) return TB_OK;                       // a strip needs three vertices to make a triangle
+    TB_REQUIRE(c, position && normal && miter && previous && time && dt, "null attribute array");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const int n = n_vertices;
+    if (n > c->line_cap) {
+        TB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->line_attr); cudaFree(c->line_verts);
+        c->line_attr = nullptr; c->line_verts = nullptr; c->line_cap = 0;
+        const int cap = std::max(n, 256);
+        TB_CUDA(c, cudaMalloc(&c->line_attr, static_cast<size_t>(cap) * 9 * sizeof(float)));
+        TB_CUDA(c, cudaMalloc(&c->line_verts, static_cast<size_t>(cap) * sizeof(fl::Vertex)));
+        c->line_cap = cap;
+    }
+    if (!c->line_bbox) TB_CUDA(c, cudaMalloc(&c->line_bbox, 4 * sizeof(int)));
+    // attribute arrays as gl-geometry holds them (src/geom/line/index.js:119-123): one buffer per attribute
+    float *d_pos = c->line_attr, *d_nor = d_pos + 2 * n, *d_mit = d_nor + 2 * n, *d_prv = d_mit + n, *d_tim = d_prv + 2 * n,
+          *d_dt = d_tim + n;
+    TB_CUDA(c, cudaMemcpyAsync(d_pos, position, 2 * n * sizeof(float), cudaMemcpyDefault, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(d_nor, normal, 2 * n * sizeof(float), cudaMemcpyDefault, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(d_mit, miter, n * sizeof(float), cudaMemcpyDefault, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(d_prv, previous, 2 * n * sizeof(float), cudaMemcpyDefault, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(d_tim, time, n * sizeof(float), cudaMemcpyDefault, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(d_dt, dt, n * sizeof(float), cudaMemcpyDefault, c->stream));
+    const int empty_box[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
+    TB_CUDA(c, cudaMemcpyAsync(c->line_bbox, empty_box, sizeof(empty_box), cudaMemcpyHostToDevice, c->stream));
+    fl::Uniforms U{params->viewSize[0], params->viewSize[1], params->rad, params->speed, params->speedLimit, params->crestShape};
+    k_flow_line_vertices<<<blocks_for(n, 128), 128, 0, c->stream>>>(U, n, d_pos, d_nor, d_mit, d_prv, d_tim, d_dt, c->W, c->H,
+                                                                     c->line_verts, c->line_bbox);
+    if (int r = check_launch(c, "k_flow_line_vertices")) return r;
+    const dim3 grid(blocks_for(c->W, 256), static_cast<unsigned>(c->H));
+    k_flow_line_raster<<<grid, 256, 0, c->stream>>>(c->line_verts, n, U.crestShape, c->line_bbox, c->flow, c->W, c->H);
+    if (int r = check_launch(c, "k_flow_line_raster")) return r;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));           // the host arrays are only borrowed
     return TB_OK;
 }
 

@@ -499,3 +499,42 @@ def test_device_resident_inputs_equal_host_inputs(T):
         t.dispose()
     assert_bits_equal(outs[1][0], outs[0][0], "state: device-resident vs host inputs")
     assert_bits_equal(outs[1][1], outs[0][1], "flow: device-resident vs host inputs")
+
+
+@pytest.mark.parametrize("seed,closed,view", [(11, False, (48, 32)), (12, True, (40, 56)), (13, False, (64, 64))])
+def test_flow_lines_bit_exact(T, oracle, seed, closed, view):
+    """f4: FlowLine.update().draw() into the flow grid after the particle splat (src/demo.main.js:1107-1121)."""
+    from test_flow_line import random_path
+    from tendrils_b200.spawn import spawnBall
+    R, (W, H) = 32, view
+    t = make(T, R, 0, view=(W, H))
+    O = oracle
+    sim = OracleSim(O, R, W, H, oracle_params(O, t))
+    spawnBall(t.gl, {"uniforms": {"radius": 0.5, "speed": 0.004}}).spawn(t)
+    sim.spawn_ball(0.5, 0.004)
+    rng = np.random.default_rng(seed)
+    lines = T.FlowLines(t.gl)
+    fl = lines.get(1, {"closed": closed})
+    path = random_path(rng, 18)
+    if seed == 13:
+        path.insert(7, path[6])                                           # a repeated point: Inf / NaN miters, culled triangles
+    clock = 2000.0
+    for k, p in enumerate(path):
+        clock += float(rng.uniform(0.3, 30.0))
+        fl.add(clock, p)
+        if k < 3 or k % 5:
+            continue
+        t.timer.tick(); t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); sim.draw(np.float32(t.timer.time))
+        fl.line.uniforms.update(t.state)                                  # Object.assign(flowLine.line.uniforms, tendrils.state)
+        fl.update().draw(t)
+        u = fl.line.uniforms
+        U = O.flow_line_uniforms(viewSize=u["viewSize"], rad=u["rad"], speed=u["speed"], speedLimit=u["speedLimit"],
+                                 crestShape=u["crestShape"])
+        a = {name: np.ascontiguousarray(v["data"], np.float32) for name, v in fl.line.attributes.items()}
+        with np.errstate(all="ignore"):
+            n = O.flow_line(U, a, sim.flow)
+        assert n > 20
+        assert_bits_equal(t.flow.download(), sim.flow, f"flow after the flow line, {k + 1} points")
+        assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state, {k + 1} points")
+    assert lines.trim(1 / t.state["flowDecay"], clock) > 0

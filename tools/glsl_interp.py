@@ -338,6 +338,10 @@ BUILTINS = {
     "mix": _cw(lambda x, y, a: x * (f32(1.0) - a) + y * a),
     "dot": _dot,
     "length": lambda v: f32(np.sqrt(_dot(v, v))),
+    # GLSL ES 1.00 8.3: 1.0 if x > 0, 0.0 if x = 0, -1.0 if x < 0 (NaN falls through to 0, spec/PARITY.md FL2)
+    "sign": _cw(lambda x: f32(1.0) if x > 0 else (f32(-1.0) if x < 0 else f32(0.0))),
+    # v / length(v), component-wise (spec/PARITY.md FL2); the zero vector gives 0/0 = NaN
+    "normalize": lambda v: (v / f32(np.sqrt(_dot(v, v)))).astype(f32),
 }
 
 

@@ -144,5 +144,51 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def flow_line():
+    """f4: ./src/flow-line/index.vert and index.frag (docs/js/demo.js.map) on random attribute / varying values ->
+    tests/golden/glsl_flowline_v1.npz (a file of its own, so that glsl_v1.npz never has to be regenerated)."""
+    rng = np.random.default_rng(4242)
+    vert = Shader(shader_source("demo.js.map", "/src/flow-line/index.vert"))
+    frag = Shader(shader_source("demo.js.map", "/src/flow-line/index.frag"))
+    uni = {"viewSize": [1.0, f32(4 / 3)], "rad": f32(0.1), "speed": f32(3.0), "speedLimit": f32(0.01)}
+    n = 64
+    vin = np.zeros((n, 9), f32)                      # position.xy, normal.xy, miter, previous.xy, time, dt
+    vin[:, 0:2] = rng.uniform(-1, 1, (n, 2))
+    ang = rng.uniform(0, 2 * np.pi, n)
+    vin[:, 2], vin[:, 3] = np.cos(ang), np.sin(ang)
+    vin[:, 4] = rng.uniform(0.8, 3.0, n) * rng.choice([-1.0, 1.0], n)
+    vin[:, 5:7] = vin[:, 0:2] + rng.normal(0, 0.02, (n, 2))
+    vin[:, 7] = rng.uniform(1000, 90000, n)
+    vin[:, 8] = rng.uniform(0.0, 40.0, n)
+    vin[0, 5:7] = vin[0, 0:2]                        # first path point: previous = itself, dt = 0
+    vin[0, 8] = 0.0
+    vin[1, 4] = 0.0                                  # miter 0: sign() = 0
+    vin[2, 8] = 0.25                                 # dt below 1 ms: max(dt, 1.0)
+    vout = np.zeros((n, 9), f32)                     # gl_Position.xy, values.rgba, crest.xy, sdf
+    with np.errstate(all="ignore"):
+        for i in range(n):
+            g = vert.run({**uni, "position": vin[i, 0:2], "normal": vin[i, 2:4], "miter": vin[i, 4], "previous": vin[i, 5:7],
+                          "time": vin[i, 7], "dt": vin[i, 8]})
+            vout[i, 0:2], vout[i, 2:6], vout[i, 6:8], vout[i, 8] = g["gl_Position"][0:2], g["values"], g["crest"], g["sdf"]
+        fin = np.zeros((n, 7), f32)                  # values.rgba, crest.xy, sdf
+        fin[:, 0:2] = rng.normal(0, 0.006, (n, 2))
+        fin[:, 2] = rng.uniform(1000, 90000, n)
+        fin[:, 3] = rng.uniform(0, 1, n)
+        fin[:, 4:6] = rng.normal(0, 1.2, (n, 2))
+        fin[:, 6] = rng.uniform(-1, 1, n)
+        fin[0, 6] = 0.0                              # on the path: d = 0
+        fin[1, 0:2] = 0.0                            # no velocity: direction comes from the crest alone
+        fout = np.zeros((n, 4), f32)
+        for i in range(n):
+            fout[i] = frag.run({"crestShape": f32(0.6), "values": fin[i, 0:4], "crest": fin[i, 4:6], "sdf": fin[i, 6]})["gl_FragColor"]
+    path = os.path.join(ROOT, "tests", "golden", "glsl_flowline_v1.npz")
+    np.savez_compressed(path, uniforms=np.array([1.0, f32(4 / 3), 0.1, 3.0, 0.01, 0.6], f32), vert_in=vin, vert_out=vout,
+                        frag_in=fin, frag_out=fout)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "flow-line":
+        flow_line()
+    else:
+        main()
