@@ -88,4 +88,33 @@ export const accelerate = (Tendrils, shaderKinds /* Map(shader -> {kind, variant
     }
   };
 
+/**
+ * The inputs the app draws into the flow FBO after the particles (src/demo.main.js:1107-1159), routed to the
+ * library's grid instead:
+ *   accelerateFlowLine(FlowLine)      -- `flowLine.update().draw(tendrils)` hands the attribute arrays that
+ *                                        Line.update() filled (src/geom/line/index.js:73-117) to tb_flow_line;
+ *   accelerateOpticalFlow(OpticalFlow) -- `opticalFlow.update(u).render(tendrils, view, last, [w, h])` hands the
+ *                                        two RGBA8 frames (what setPixels uploaded) to tb_optical_flow.
+ */
+export const accelerateFlowLine = (FlowLine) =>
+  class FlowLineB200 extends FlowLine {
+    draw(tendrils) {
+      const { line } = this;
+      if(line.path.length > 0) {
+        const a = line.attributes;
+        addon.flowLine(tendrils.b200, line.uniforms, a.position.data, a.normal.data, a.miter.data,
+          a.previous.data, a.time.data, a.dt.data);
+      }
+      return this;
+    }
+  };
+
+export const accelerateOpticalFlow = (OpticalFlow) =>
+  class OpticalFlowB200 extends OpticalFlow {
+    render(tendrils, view, last, [w, h]) {
+      addon.opticalFlow(tendrils.b200, this.uniforms, view, last, w, h);
+      return this;
+    }
+  };
+
 export default accelerate;

@@ -211,6 +211,98 @@ napi_value Transfer(napi_env env, napi_callback_info info, bool up) {
 napi_value Upload(napi_env env, napi_callback_info info) { return Transfer(env, info, true); }
 napi_value Download(napi_env env, napi_callback_info info) { return Transfer(env, info, false); }
 
+// a typed array argument of the expected element type; returns its data pointer and length, or throws
+void *typed(napi_env env, napi_value v, napi_typedarray_type want, size_t *len) {
+    napi_typedarray_type type;
+    void *data = nullptr;
+    *len = 0;
+    if (napi_get_typedarray_info(env, v, &type, len, &data, nullptr, nullptr) != napi_ok || type != want) {
+        napi_throw_error(env, nullptr, "tendrils-b200: typed array of the wrong element type");
+        return nullptr;
+    }
+    return data;
+}
+
+void vec2(napi_env env, napi_value obj, const char *key, float *dst) {
+    napi_value arr, e;
+    napi_get_named_property(env, obj, key, &arr);
+    for (uint32_t i = 0; i < 2; ++i) {
+        napi_get_element(env, arr, i, &e);
+        dst[i] = static_cast<float>(num(env, e));
+    }
+}
+
+// opticalFlow(ctx, {viewSize, scaleUV, offset, lambda, speed, speedLimit, time}, Uint8Array view, Uint8Array last, w, h)
+// = OpticalFlow.update() + screen.render() with the flow FBO bound (src/demo.main.js:1131-1156)
+napi_value OpticalFlow(napi_env env, napi_callback_info info) {
+    size_t argc = 6;
+    napi_value argv[6];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    tb_ctx *ctx = unwrap(env, argv[0]);
+    tb_optical_flow_params p{};
+    vec2(env, argv[1], "viewSize", p.viewSize);
+    vec2(env, argv[1], "scaleUV", p.scaleUV);
+    p.offset = static_cast<float>(prop(env, argv[1], "offset", 1));
+    p.lambda = static_cast<float>(prop(env, argv[1], "lambda", 0.001));
+    p.speed = static_cast<float>(prop(env, argv[1], "speed", 1));
+    p.speedLimit = static_cast<float>(prop(env, argv[1], "speedLimit", 1));
+    p.time = static_cast<float>(prop(env, argv[1], "time", 1));
+    const int32_t w = static_cast<int32_t>(num(env, argv[4])), h = static_cast<int32_t>(num(env, argv[5]));
+    size_t n_view = 0, n_last = 0;
+    const void *view = typed(env, argv[2], napi_uint8_array, &n_view);
+    const void *last = typed(env, argv[3], napi_uint8_array, &n_last);
+    if (!view || !last) return nullptr;
+    if (n_view != static_cast<size_t>(w) * h * 4 || n_last != n_view) {
+        napi_throw_error(env, nullptr, "tendrils-b200: frames must be Uint8Arrays of w*h*4");
+        return nullptr;
+    }
+    return check(env, ctx, tb_optical_flow(ctx, &p, static_cast<const uint8_t *>(view), static_cast<const uint8_t *>(last), w, h));
+}
+
+// flowLine(ctx, {viewSize, rad, speed, speedLimit, crestShape}, position, normal, miter, previous, time, dt)
+// = FlowLine.draw() with the flow FBO bound (src/demo.main.js:1107-1121); the arrays are line.attributes.*.data
+napi_value FlowLine(napi_env env, napi_callback_info info) {
+    size_t argc = 8;
+    napi_value argv[8];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    tb_ctx *ctx = unwrap(env, argv[0]);
+    tb_flow_line_params p{};
+    vec2(env, argv[1], "viewSize", p.viewSize);
+    p.rad = static_cast<float>(prop(env, argv[1], "rad", 0.1));
+    p.speed = static_cast<float>(prop(env, argv[1], "speed", 3));
+    p.speedLimit = static_cast<float>(prop(env, argv[1], "speedLimit", 0.01));
+    p.crestShape = static_cast<float>(prop(env, argv[1], "crestShape", 0.6));
+    size_t len[6] = {};
+    const float *a[6] = {};
+    for (int i = 0; i < 6; ++i) {
+        a[i] = static_cast<const float *>(typed(env, argv[2 + i], napi_float32_array, &len[i]));
+        if (!a[i] && len[i]) return nullptr;
+    }
+    const size_t n = len[2];                                   // miter: one float per vertex
+    if (len[0] != 2 * n || len[1] != 2 * n || len[3] != 2 * n || len[4] != n || len[5] != n) {
+        napi_throw_error(env, nullptr, "tendrils-b200: flow line attribute arrays disagree in length");
+        return nullptr;
+    }
+    return check(env, ctx, tb_flow_line(ctx, &p, static_cast<int32_t>(n), a[0], a[1], a[2], a[3], a[4], a[5]));
+}
+
+// blendIntoFlow(ctx, Float32Array rgba, w, h): any other layer the application draws into the flow FBO
+napi_value BlendIntoFlow(napi_env env, napi_callback_info info) {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    tb_ctx *ctx = unwrap(env, argv[0]);
+    size_t len = 0;
+    const void *data = typed(env, argv[1], napi_float32_array, &len);
+    if (!data) return nullptr;
+    const int32_t w = static_cast<int32_t>(num(env, argv[2])), h = static_cast<int32_t>(num(env, argv[3]));
+    if (len != static_cast<size_t>(w) * h * 4) {
+        napi_throw_error(env, nullptr, "tendrils-b200: layer must be a Float32Array of w*h*4");
+        return nullptr;
+    }
+    return check(env, ctx, tb_blend_into_flow(ctx, static_cast<const float *>(data), w, h));
+}
+
 napi_value Init(napi_env env, napi_value exports) {
     const napi_property_descriptor props[] = {
         {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -226,6 +318,9 @@ napi_value Init(napi_env env, napi_value exports) {
         {"spawnPixels", nullptr, SpawnPixels, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"upload", nullptr, Upload, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"download", nullptr, Download, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"opticalFlow", nullptr, OpticalFlow, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"flowLine", nullptr, FlowLine, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"blendIntoFlow", nullptr, BlendIntoFlow, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
     return exports;

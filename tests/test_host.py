@@ -180,3 +180,15 @@ def test_bench_workloads_and_bytes():
     assert bench.algorithmic_bytes(n, g, optical=True)["step"] == ab["step"] + 40 * g
     w5 = bench.WORKLOADS["cfg5"]
     assert w5["R"] * w5["rows"] == 2 ** 27 and w5["G"] == 2048
+
+
+def test_napi_shim_matches_the_c_header():
+    """bindings/node cannot be built here (no Node), but it must at least type-check against include/tendrils_b200.h:
+    g++ -fsyntax-only with a stub of node_api.h (tests/host_harness/node_api.h)."""
+    import subprocess
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "tests", "host_harness"),
+                        os.path.join(ROOT, "bindings", "node", "tendrils_b200_napi.cc")], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    shim = open(os.path.join(ROOT, "bindings", "node", "tendrils_b200_napi.cc")).read()
+    for sym in ("tb_create", "tb_step", "tb_splat_flow", "tb_spawn_pixels", "tb_optical_flow", "tb_flow_line", "tb_blend_into_flow"):
+        assert sym + "(" in shim, sym
