@@ -118,12 +118,19 @@ class _Buffer:
     def _ctx(self):
         return self._owner._ctx
 
-    def download(self) -> np.ndarray:
+    def download(self, out=None) -> np.ndarray:
+        """Reads the texture back (gl.readPixels).  `out`: an existing C-contiguous float32 array of the texture's
+        shape to read into -- e.g. a view of pinned host memory, which makes the copy a single DMA."""
         p = self._owner
         if self._which == N.TB_BUF_FLOW:
-            out = np.empty((p.flow_shape[1], p.flow_shape[0], 4), np.float32)
+            shape = (p.flow_shape[1], p.flow_shape[0], 4)
         else:
-            out = np.empty((p.col1 - p.col0, p.shape[1], 4), np.float32)
+            shape = (p.col1 - p.col0, p.shape[1], 4)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == shape
+                  and out.flags["C_CONTIGUOUS"] and out.flags["WRITEABLE"]):
+            raise N.TendrilsError(f"tendrils-b200: download(out=...) needs a writable C-contiguous float32 array of shape {shape}")
         N.check(self._ctx(), N.load().tb_download(self._ctx(), self._which, out.ctypes.data_as(N._fp), out.size))
         return out
 

@@ -192,3 +192,34 @@ def test_napi_shim_matches_the_c_header():
     shim = open(os.path.join(ROOT, "bindings", "node", "tendrils_b200_napi.cc")).read()
     for sym in ("tb_create", "tb_step", "tb_splat_flow", "tb_spawn_pixels", "tb_optical_flow", "tb_flow_line", "tb_blend_into_flow"):
         assert sym + "(" in shim, sym
+
+
+def test_buffer_download_into_caller_memory(monkeypatch):
+    """_Buffer.download(out=...) hands the caller's (e.g. pinned) array to tb_download: same call, no extra host copy."""
+    import ctypes as C
+    from tendrils_b200 import _native as N
+    from tendrils_b200 import tendrils as TT
+    calls = []
+
+    class FakeLib:
+        def tb_download(self, ctx, which, ptr, n):
+            calls.append((which, C.addressof(ptr.contents), n))
+            np.ctypeslib.as_array(ptr, shape=(n,))[:] = np.arange(n, dtype=np.float32)
+            return 0
+
+    class Owner:
+        _ctx = C.c_void_p(1)
+        flow_shape, shape, col0, col1 = [5, 3], [4, 6], 1, 3
+
+    monkeypatch.setattr(N, "load", lambda: FakeLib())
+    buf = TT._Buffer(Owner(), N.TB_BUF_CURRENT)
+    fresh = buf.download()
+    assert fresh.shape == (2, 6, 4) and fresh.dtype == np.float32 and fresh[0, 0, 1] == 1.0
+    mine = np.zeros((2, 6, 4), np.float32)
+    got = buf.download(out=mine)
+    assert got is mine and calls[-1] == (N.TB_BUF_CURRENT, mine.ctypes.data, 48) and mine[1, 5, 3] == 47.0
+    flow = TT._Buffer(Owner(), N.TB_BUF_FLOW).download(out=np.zeros((3, 5, 4), np.float32))
+    assert flow.shape == (3, 5, 4) and calls[-1][2] == 60
+    for bad in (np.zeros((2, 6, 4), np.float64), np.zeros((6, 2, 4), np.float32), np.zeros((2, 6, 8), np.float32)[..., ::2]):
+        with pytest.raises(N.TendrilsError):
+            buf.download(out=bad)
