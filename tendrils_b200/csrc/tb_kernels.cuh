@@ -74,7 +74,7 @@ struct IntegrateArgs {
     int n_pairs;
 };
 
-// a3: src/logic.frag:45-101.  One thread per particle, 16 B in / 16 B out, flow gather via L2.
+// [raster-begin]  (tests/test_raster_host.py compiles the text between these markers for the CPU)
 // RASTER-1 (spec/PARITY.md): GL_LINES of width 1, centre-sampled along the major axis, half-open
 // towards the second vertex, scissored to the grid.  emit(gx, gy, t) per fragment.
 template <class Emit>
@@ -148,6 +148,7 @@ __device__ __forceinline__ uint32_t count_fragments(const float4 &sa, const floa
     raster_line(xa, ya, xb, yb, W, H, [&](int, int, float) { ++n; });
     return n;
 }
+// [raster-end]
 
 #ifndef TB_INTEGRATE_MIN_BLOCKS
 #define TB_INTEGRATE_MIN_BLOCKS 5
