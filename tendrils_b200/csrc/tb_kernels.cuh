@@ -531,9 +531,24 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// [cp-async-end]  (the CPU tests swap the helpers above for plain copies)
+// one fragment into the first three floats of a FoldTerm slot (tx = cx, ty = cy, tz = a)
+__device__ __forceinline__ void stage_frag(FoldTerm *slot, const FragVal *f) {
+#if TB_FRAG_BYTES == 16
+    cp_async16(slot, f);
+#else
+    cp_async4(&slot->tx, &f->cx);
+    cp_async4(&slot->ty, &f->cy);
+    cp_async4(&slot->tz, &f->a);
+#endif
 }
 
 __global__ void __launch_bounds__(kHotWarps * 32) k_splat_fold_hot(const FoldIO io, const uint2 *__restrict__ seg,
@@ -571,7 +586,7 @@ __global__ void __launch_bounds__(kHotWarps * 32) k_splat_fold_hot(const FoldIO 
 #pragma unroll
                 for (int j = 0; j < kHotStep / 32; ++j) {
                     const uint32_t i = p + j * 32 + lane;
-                    if (i < e) cp_async16(&s_term[warp][k][j * 32 + lane], vals + i);
+                    if (i < e) stage_frag(&s_term[warp][k][j * 32 + lane], vals + i);
                 }
             }
         }

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from test_fold_host import CP_ASYNC_HOST, make_segments
+from test_fold_host import compile_harness, fold_source, make_segments
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _fp = C.POINTER(C.c_float)
@@ -99,27 +99,18 @@ extern "C" int bh_bands_fold(int world, int G, const uint32_t *const *seg, const
 '''
 
 
-@pytest.fixture(scope="module")
-def bh(tmp_path_factory):
+@pytest.fixture(scope="module", params=[16, 12], ids=["frag16", "frag12"])
+def bh(request, tmp_path_factory):
     d = tmp_path_factory.mktemp("bh")
     ksrc = open(os.path.join(ROOT, "tendrils_b200", "csrc", "tb_kernels.cuh")).read()
-    frag = ksrc[ksrc.index("#ifndef TB_FRAG_BYTES"):ksrc.index("// Line pair k of a column")]
-    fold = ksrc[ksrc.index("// Pass 5: ordered alpha-over fold"):ksrc.index("// first index of the sorted key array")]
-    a = fold.index("__device__ __forceinline__ void cp_async16(")
-    b = fold.index("__global__ void __launch_bounds__(kHotWarps * 32) k_splat_fold_hot(")
-    fold = fold[:a] + CP_ASYNC_HOST + fold[b:]
+    frag, fold = fold_source(ksrc)
     bands = (ksrc[ksrc.index("// Band fold of a sharded run"):ksrc.index("// all-rank barrier over peer memory")] +
              ksrc[ksrc.index("// copy this rank's finished tiles"):ksrc.index("// Full-grid alpha-over of an RGBA layer")])
-    cpp = d / "bands_host.cpp"
-    cpp.write_text(HARNESS % {k: v.replace("__device__", "") for k, v in (("frag", frag), ("fold", fold), ("bands", bands))})
-    out = d / "libbands_host.so"
-    subprocess.run(["g++", "-O2", "-std=c++20", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                    "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
-                    "-I", os.path.join(ROOT, "tests", "host_harness"), "-o", str(out), str(cpp)], check=True)
-    L = C.CDLL(str(out))
+    L = compile_harness(d, "bands_host", HARNESS % {"frag": frag, "fold": fold, "bands": bands.replace("__device__", "")}, request.param)
     L.bh_bands_fold.restype = C.c_int
     L.bh_bands_fold.argtypes = [C.c_int, C.c_int, C.POINTER(_up), C.POINTER(_up), C.POINTER(_fp), _up, C.POINTER(_fp), C.c_uint32,
                                 C.c_float, C.c_uint32]
+    L.frag_floats = request.param // 4
     return L
 
 
@@ -167,7 +158,8 @@ def test_band_fold_equals_plain_fold_in_rank_order(bh, world, G, mean, hot_every
             want[t] = d
     cap = int(kept.max()) + cap_slack                                        # -1: one owner's merged fragments do not fit
     arr = lambda ptr_t, xs, cast: (ptr_t * world)(*[x.ctypes.data_as(cast) for x in xs])
-    rc = bh.bh_bands_fold(world, G, arr(_up, segs, _up), arr(_up, keys, _up), arr(_fp, vals, _fp), n_frag.ctypes.data_as(_up),
+    packed = [np.ascontiguousarray(v[:, :bh.frag_floats]) for v in vals]     # the harness's fragment layout (with / without pad lane)
+    rc = bh.bh_bands_fold(world, G, arr(_up, segs, _up), arr(_up, keys, _up), arr(_fp, packed, _fp), n_frag.ctypes.data_as(_up),
                           arr(_fp, flows, _fp), max(cap, 1), time, 96)
     if cap_slack < 0:
         assert rc == -1                                                      # the overflow flag the host turns into an error

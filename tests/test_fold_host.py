@@ -17,8 +17,30 @@ _up = C.POINTER(C.c_uint32)
 
 CP_ASYNC_HOST = r'''
 inline void cp_async16(void *smem_dst, const void *gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+inline void cp_async4(void *smem_dst, const void *gmem_src) { std::memcpy(smem_dst, gmem_src, 4); }
 inline void cp_async_wait_all() {}
 '''
+
+
+def fold_source(ksrc):
+    """The fragment type and the fold kernels of tb_kernels.cuh, the cp.async helpers swapped for plain copies."""
+    frag = ksrc[ksrc.index("#ifndef TB_FRAG_BYTES"):ksrc.index("// Line pair k of a column")]
+    fold = ksrc[ksrc.index("// Pass 5: ordered alpha-over fold"):ksrc.index("// first index of the sorted key array")]
+    a, b = fold.index("__device__ __forceinline__ void cp_async16("), fold.index("// [cp-async-end]")
+    assert fold[a:b].count("asm volatile") == 4                              # exactly the cp.async helpers are swapped
+    fold = fold[:a] + CP_ASYNC_HOST + fold[b:]
+    assert "asm" not in fold.replace("// [cp-async-end]", "")
+    return frag.replace("__device__", ""), fold.replace("__device__", "")
+
+
+def compile_harness(d, name, text, frag_bytes, std="c++20"):
+    cpp = d / f"{name}_{frag_bytes}.cpp"
+    cpp.write_text(text)
+    out = d / f"lib{name}_{frag_bytes}.so"
+    subprocess.run(["g++", "-O2", f"-std={std}", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
+                    f"-DTB_FRAG_BYTES={frag_bytes}", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes",
+                    "-I/usr/local/cuda/include", "-I", os.path.join(ROOT, "tests", "host_harness"), "-o", str(out), str(cpp)], check=True)
+    return C.CDLL(str(out))
 
 HARNESS = r'''
 #include <algorithm>
@@ -63,25 +85,16 @@ extern "C" long long fh_fold(const uint32_t *seg, const float *vals, float *src,
 '''
 
 
-@pytest.fixture(scope="module")
-def fh(tmp_path_factory):
+@pytest.fixture(scope="module", params=[16, 12], ids=["frag16", "frag12"])
+def fh(request, tmp_path_factory):
+    """The harness built for the default 16-byte fragments and for -DTB_FRAG_BYTES=12 (a build option)."""
     d = tmp_path_factory.mktemp("fh")
     ksrc = open(os.path.join(ROOT, "tendrils_b200", "csrc", "tb_kernels.cuh")).read()
-    frag = ksrc[ksrc.index("#ifndef TB_FRAG_BYTES"):ksrc.index("// Line pair k of a column")]
-    fold = ksrc[ksrc.index("// Pass 5: ordered alpha-over fold"):ksrc.index("// first index of the sorted key array")]
-    a = fold.index("__device__ __forceinline__ void cp_async16(")
-    b = fold.index("__global__ void __launch_bounds__(kHotWarps * 32) k_splat_fold_hot(")
-    assert fold[a:b].count("asm volatile") == 3                              # exactly the cp.async helpers are swapped
-    fold = fold[:a] + CP_ASYNC_HOST + fold[b:]
-    cpp = d / "fold_host.cpp"
-    cpp.write_text(HARNESS % {"frag": frag.replace("__device__", ""), "fold": fold.replace("__device__", "")})
-    out = d / "libfold_host.so"
-    subprocess.run(["g++", "-O2", "-std=c++20", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
-                    "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
-                    "-I", os.path.join(ROOT, "tests", "host_harness"), "-o", str(out), str(cpp)], check=True)
-    L = C.CDLL(str(out))
+    frag, fold = fold_source(ksrc)
+    L = compile_harness(d, "fold_host", HARNESS % {"frag": frag, "fold": fold}, request.param)
     L.fh_fold.restype = C.c_longlong
     L.fh_fold.argtypes = [_up, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint32, _up]
+    L.frag_floats = request.param // 4
     return L
 
 
@@ -130,6 +143,7 @@ def plain_fold(seg, vals, src, time, texels):
 def run(fh, seg, vals, src, dst, dst2, t_begin, t_end, copy_all, tile_first, tile_stride, n_warps, time, hot):
     G = src.shape[0]
     scratch = np.zeros(2 + G, np.uint32)
+    vals = np.ascontiguousarray(vals[:, :fh.frag_floats])                    # 16-byte fragments carry a pad lane, 12-byte ones do not
     p = lambda a: None if a is None else a.ctypes.data_as(_fp)
     n_hot = fh.fh_fold(seg.ctypes.data_as(_up), p(vals), p(src), p(dst), p(dst2), t_begin, t_end, copy_all, tile_first, tile_stride,
                        n_warps, np.float32(time), hot, scratch.ctypes.data_as(_up))

@@ -121,8 +121,8 @@ extern "C" long long sh_step_and_splat(const float *state18, int PW, int PH, int
 '''
 
 
-@pytest.fixture(scope="module")
-def sh(tmp_path_factory):
+@pytest.fixture(scope="module", params=[16, 12], ids=["frag16", "frag12"])
+def sh(request, tmp_path_factory):
     d = tmp_path_factory.mktemp("sh")
     csrc = os.path.join(ROOT, "tendrils_b200", "csrc")
     math = d / "tb_math_host.cuh"
@@ -143,6 +143,7 @@ def sh(tmp_path_factory):
                               "kernels": kernels, "pairs": pairs})
     out = d / "libsplat_host.so"
     subprocess.run(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+                    f"-DTB_FRAG_BYTES={request.param}",                       # 12: the build option without the pad lane
                     "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
                     "-I", os.path.join(ROOT, "tests", "host_harness"), "-o", str(out), str(cpp)], check=True)
     L = C.CDLL(str(out))
