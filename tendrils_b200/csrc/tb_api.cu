@@ -981,7 +981,9 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
         for (size_t k = 0; k < pairs.size(); ++k) {
             const int ra = pairs[k].row_a & 0x7fffffff, rb = pairs[k].row_b & 0x7fffffff;
             const bool ca = pairs[k].row_a < 0, cb = pairs[k].row_b < 0;
-            if (ra != rb || ca == cb || k >= (1u << 30)) { c->fuse_count = false; break; }
+            // the count can ride in k_integrate only if every drawn row is drawn by exactly ONE pair: the D6 table of many
+            // non-power-of-two heights draws some rows twice (e.g. PH = 47: pairs 0 and 1 both draw row 0)
+            if (ra != rb || ca == cb || k >= (1u << 30) || rp[static_cast<size_t>(ra)] != -1) { c->fuse_count = false; break; }
             rp[static_cast<size_t>(ra)] = static_cast<int32_t>(static_cast<uint32_t>(k) | ((cb ? 1u : 2u) << 30));   // 1: prev->cur, 2: cur->prev
         }
         TB_TRY(cudaMalloc(&c->row_pair, rp.size() * sizeof(int32_t)));

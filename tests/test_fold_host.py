@@ -204,3 +204,26 @@ def test_band_tiles(fh, world, rank, G):
         want[t] = d
     assert np.array_equal(flow.view(np.uint32), want.view(np.uint32))
     assert len(owned) < 40 or any(seg[2 * t + 1] > seg[2 * t] for t in owned)
+
+
+STRESS = int(os.environ.get("TB_STRESS", "0"))        # TB_STRESS=n: n extra random configurations (off in the normal run)
+
+
+@pytest.mark.parametrize("seed", range(STRESS))
+def test_stress_random_configurations(fh, seed):
+    rng = np.random.default_rng(10_000 + seed)
+    G = int(rng.integers(1, 700))
+    seg, vals = make_segments(rng, G, float(rng.choice([0.5, 3, 12, 40])), int(rng.choice([0, 3, 17, 64])), int(rng.integers(97, 2500)),
+                              gap_p=float(rng.choice([0.0, 0.3, 0.9])))
+    threshold = int(rng.choice([0, 8, 96, 96, 96, 0xffffffff]))
+    world = int(rng.integers(1, 9))
+    rank = int(rng.integers(0, world))
+    flow0 = rng.normal(0, 0.01, (G, 4)).astype(np.float32)
+    flow = flow0.copy()
+    tiles = (G + 31) // 32
+    mine = (tiles - rank + world - 1) // world
+    run(fh, seg, vals, flow, flow, None, 0, G, 0, rank, world, mine, 9.75, threshold)
+    want = flow0.copy()
+    for t, d in plain_fold(seg, vals, flow0, 9.75, [t for t in range(G) if (t // 32) % world == rank]).items():
+        want[t] = d
+    assert np.array_equal(flow.view(np.uint32), want.view(np.uint32)), (seed, G, threshold, world, rank)

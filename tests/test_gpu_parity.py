@@ -538,3 +538,29 @@ def test_flow_lines_bit_exact(T, oracle, seed, closed, view):
         assert_bits_equal(t.flow.download(), sim.flow, f"flow after the flow line, {k + 1} points")
         assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state, {k + 1} points")
     assert lines.trim(1 / t.state["flowDecay"], clock) > 0
+
+
+@pytest.mark.parametrize("PW,PH,G", [(24, 47, 40), (16, 83, 32)])
+def test_rows_drawn_twice_bit_exact(T, oracle, PW, PH, G):
+    """Heights whose D6 vertex table draws some texel rows TWICE (two line pairs land on one row; most
+    non-power-of-two heights do): the count cannot ride in k_integrate there.  Found by tests/test_splat_host.py."""
+    from tendrils_b200.spawn import spawnBall
+    row, cur_of = oracle.vertex_table(PH)
+    drawn = [int(row[2 * k]) for k in range(PH) if not (row[2 * k] == row[2 * k + 1] and cur_of[2 * k] == cur_of[2 * k + 1])]
+    assert len(drawn) > len(set(drawn))                                       # the premise: a row is drawn twice
+    t = T.Tendrils(T.Device(G, G))
+    t.setup([PW, PH]); t.resize()
+    t.state["speedLimit"] = 0.2
+    O = oracle
+    P = oracle_params(O, t)
+    cur, prev = O.spawn_ball(PW, PH, 0.6, 0.15), O.spawn_init(PW, PH)
+    spawnBall(t.gl, {"uniforms": {"radius": 0.6, "speed": 0.15}}).spawn(t)
+    targets, flow = np.zeros((PW, PH, 4), np.float32), np.zeros((G, G, 4), np.float32)
+    for k in range(5):
+        t.timer.tick(); t.step().draw()
+        new = O.integrate(P, cur, targets, flow, np.float32(t.timer.time), np.float32(t.timer.dt))
+        prev, cur = cur, new
+        n = O.splat(P, cur, prev, flow, np.float32(t.timer.time))
+        assert t.particles.stats()["last_fragments"] == n and n > 100
+        assert_bits_equal(t.particles.buffers[0].download(), cur, f"state {k}")
+        assert_bits_equal(t.flow.download(), flow, f"flow {k}")

@@ -70,7 +70,7 @@ extern "C" long long sh_step_and_splat(const float *state18, int PW, int PH, int
     for (size_t k = 0; k < pairs.size(); ++k) {
         const int ra = pairs[k].row_a & 0x7fffffff, rb = pairs[k].row_b & 0x7fffffff;
         const bool ca = pairs[k].row_a < 0, cb = pairs[k].row_b < 0;
-        if (ra != rb || ca == cb || k >= (1u << 30)) { fuse = false; break; }
+        if (ra != rb || ca == cb || k >= (1u << 30) || rp[(size_t)ra] != -1) { fuse = false; break; }
         rp[(size_t)ra] = (int32_t)((uint32_t)k | ((cb ? 1u : 2u) << 30));
     }
     std::vector<uint32_t> fused((size_t)n_prims + 1, 0u), counted((size_t)n_prims + 1, 0u);
@@ -136,7 +136,8 @@ def sh(request, tmp_path_factory):
     asrc = open(os.path.join(csrc, "tb_api.cu")).read()
     pairs = asrc[asrc.index("int host_texel(float u, int size) {"):asrc.index("// column sampled by vertex column i")]
     # the harness repeats tb_create's row -> pair loop: make sure the product still has it verbatim
-    assert "if (ra != rb || ca == cb || k >= (1u << 30)) { c->fuse_count = false; break; }" in asrc
+    assert ("if (ra != rb || ca == cb || k >= (1u << 30) || rp[static_cast<size_t>(ra)] != -1) { c->fuse_count = false; break; }"
+            in asrc)
     assert "rp[static_cast<size_t>(ra)] = static_cast<int32_t>(static_cast<uint32_t>(k) | ((cb ? 1u : 2u) << 30));" in asrc
     cpp = d / "splat_host.cpp"
     cpp.write_text(HARNESS % {"math": str(math), "noise": str(noise), "abi": os.path.join(ROOT, "include", "tendrils_b200.h"),
@@ -155,7 +156,9 @@ def sh(request, tmp_path_factory):
 
 @pytest.mark.parametrize("PW,PH,W,H,speed_limit,seed", [(32, 64, 24, 16, 0.2, 1), (20, 50, 40, 40, 0.3, 2), (5, 7, 3, 2, 0.2, 3),
                                                         (48, 48, 64, 8, 0.3, 4), (9, 64, 1, 1, 0.01, 5), (8, 1, 16, 16, 0.1, 6),
-                                                        (64, 64, 8, 8, 0.5, 7), (16, 32, 24, 16, 0.01, 8)])
+                                                        (64, 64, 8, 8, 0.5, 7), (16, 32, 24, 16, 0.01, 8),
+                                                        # heights whose D6 table draws some rows TWICE: no fused count there
+                                                        (30, 47, 56, 63, 2.0, 9), (20, 83, 32, 32, 0.5, 10), (24, 23, 16, 16, 0.3, 11)])
 def test_collect_on_host_equals_oracle(sh, oracle, PW, PH, W, H, speed_limit, seed):
     rng = np.random.default_rng(seed)
     O = oracle
@@ -187,3 +190,14 @@ def test_collect_on_host_equals_oracle(sh, oracle, PW, PH, W, H, speed_limit, se
         prev, flow0, time = want_cur, want_flow, np.float32(time + dt)
     if seed in (1, 2, 4, 7):                                                # the substantial cases: many fragments, and the cut bites
         assert min(n for n, _ in stats) > 200 and any(k < n for n, k in stats), stats
+
+
+STRESS = int(os.environ.get("TB_STRESS", "0"))        # TB_STRESS=n: n extra random configurations (off in the normal run)
+
+
+@pytest.mark.parametrize("seed", range(STRESS))
+def test_stress_random_configurations(sh, oracle, seed):
+    rng = np.random.default_rng(20_000 + seed)
+    PW, PH = int(rng.integers(1, 40)), int(rng.integers(1, 90))
+    W, H = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+    test_collect_on_host_equals_oracle(sh, oracle, PW, PH, W, H, float(rng.choice([0.01, 0.1, 0.5, 2.0])), 1000 + seed)
