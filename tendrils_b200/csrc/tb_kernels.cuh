@@ -129,7 +129,9 @@ __device__ __forceinline__ uint32_t count_fragments(const float4 &sa, const floa
         const float na = xmajor ? ya : xa, nb = xmajor ? yb : xb;
         const int M = xmajor ? W : H, N = xmajor ? H : W;
         if (!(fabsf(dm) > 0.0f)) return 0u;
-        if (gmin(na, nb) >= 1.0f && gmax(na, nb) <= static_cast<float>(N - 1)) {
+        // (an endpoint so far out that its window coordinate overflowed to +-Inf makes every t NaN: the loop below
+        // then emits nothing, and so must the count)
+        if (gmin(na, nb) >= 1.0f && gmax(na, nb) <= static_cast<float>(N - 1) && is_finite(ma) && is_finite(mb)) {
             float flo = floorf(__fsub_rn(gmin(ma, mb), 0.5f)), fhi = floorf(__fsub_rn(gmax(ma, mb), 0.5f));
             if (flo < 0.0f) flo = 0.0f;
             if (fhi > static_cast<float>(M - 1)) fhi = static_cast<float>(M - 1);

@@ -104,7 +104,7 @@ def hostile_state(rng, PW, PH):
     pick = lambda k: rng.choice(n, k, replace=False)
     flat[pick(n // 10)] = (-1e6, -1e6, 0.003, -0.001)                       # inert (velocity kept)
     flat[pick(n // 20), 2:4] = 0.0                                          # motionless: 0/0 (PARITY I2)
-    for v in (np.nan, np.inf, -np.inf, 1e7, -3e6, 1e30, 2.5e6, 1.9e6):      # wild positions: the shortcuts must not apply
+    for v in (np.nan, np.inf, -np.inf, 1e7, -3e6, 1e30, 2.5e6, 1.9e6, 1e36, -3e38):   # wild positions: the shortcuts must not apply
         flat[pick(max(n // 60, 1)), rng.integers(0, 2)] = v
     flat[pick(n // 40), 2] = np.nan
     flat[pick(n // 40), 3] = np.inf

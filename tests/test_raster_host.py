@@ -98,3 +98,16 @@ def test_closed_form_count_equals_enumeration(rh, W, H, vs, seed):
     bad = rh.rh_check(n, seg.ctypes.data_as(C.POINTER(C.c_float)), vs[0], vs[1], W, H, C.byref(total), C.byref(first_bad))
     assert bad == 0, (bad, first_bad.value, seg[first_bad.value] if first_bad.value >= 0 else None)
     assert total.value > n // 4 or W * H == 1                               # the segments do produce fragments
+
+
+@pytest.mark.parametrize("W,H,vs", [(64, 64, (1.0, 1.0)), (1024, 1024, (1.0, 1.0)), (56, 63, (1.0, 56 / 63))])
+def test_count_with_astronomic_coordinates(rh, W, H, vs):
+    """Finite positions so large that the WINDOW coordinate overflows to +-Inf (|pos| beyond ~1e35): every t is NaN, the
+    enumeration emits nothing and the closed form must say 0 too (it once counted the columns: stale slots)."""
+    rng = np.random.default_rng(W)
+    n = 300_000
+    big = rng.choice([1e3, 1e7, 1e20, 1e30, 1e35, 1e36, 1e37, 3e38], (n, 4)) * rng.choice([-1, 1], (n, 4))
+    seg = np.ascontiguousarray(np.where(rng.random((n, 4)) < 0.5, big, rng.uniform(-1.2, 1.2, (n, 4))).astype(np.float32))
+    total, first_bad = C.c_longlong(), C.c_longlong()
+    bad = rh.rh_check(n, seg.ctypes.data_as(C.POINTER(C.c_float)), vs[0], vs[1], W, H, C.byref(total), C.byref(first_bad))
+    assert bad == 0, (bad, first_bad.value, seg[first_bad.value] if first_bad.value >= 0 else None)
