@@ -167,3 +167,15 @@ def test_band_fold_equals_plain_fold_in_rank_order(bh, world, G, mean, hot_every
     assert rc == 0
     for r in range(world):
         assert np.array_equal(flows[r].view(np.uint32), want.view(np.uint32)), f"rank {r}"
+
+
+STRESS = int(os.environ.get("TB_STRESS", "0"))        # TB_STRESS=n: n extra random configurations (off in the normal run)
+
+
+@pytest.mark.parametrize("seed", range(STRESS))
+def test_stress_random_configurations(bh, seed):
+    rng = np.random.default_rng(30_000 + seed)
+    world = int(rng.integers(2, 17))
+    G = int(rng.integers(1, 900))
+    test_band_fold_equals_plain_fold_in_rank_order(bh, world, G, float(rng.choice([0, 0.5, 4, 15])), int(rng.choice([0, 5, 29, 101])),
+                                                   int(rng.choice([0, 1, 64])))

@@ -193,3 +193,36 @@ def test_kernel_core_on_host_equals_oracle(oracle, host_core, seed, closed, size
     assert frags > 50
     assert same(got, want)
     assert not np.array_equal(bits(want), bits(base))
+
+
+STRESS = int(os.environ.get("TB_STRESS", "0"))        # TB_STRESS=n: n extra random configurations (off in the normal run)
+
+
+@pytest.mark.parametrize("seed", range(STRESS))
+def test_stress_random_paths(oracle, host_core, seed):
+    import tendrils_b200 as T
+    rng = np.random.default_rng(50_000 + seed)
+    W, H = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+    fl = T.FlowLine(T.Device(W, H), {"closed": bool(rng.random() < 0.3)})
+    t = 1000.0
+    for p in random_path(rng, int(rng.integers(2, 40)), step=float(rng.choice([0.01, 0.1, 0.4, 1.5])), jitter=float(rng.choice([0.1, 0.9, 3.0]))):
+        t += float(rng.choice([0.0, 0.4, 16.0, 300.0]))
+        fl.add(t, p)
+        if rng.random() < 0.1:
+            fl.add(t, p)                                                     # a repeated point
+    fl.line.uniforms.update({"speedLimit": float(rng.choice([0.01, 0.2, 0.0])), "rad": float(rng.choice([0.1, 0.5, 0.01])),
+                             "speed": float(rng.choice([3, 0.1, 100])), "crestShape": float(rng.choice([0.6, 0.0, 1.0, 5.0])),
+                             "viewSize": [1.0, W / H] if rng.random() < 0.5 else [1, 1]})
+    fl.update()
+    a = {k: np.ascontiguousarray(v["data"], np.float32) for k, v in fl.line.attributes.items()}
+    u = fl.line.uniforms
+    U = oracle.flow_line_uniforms(viewSize=u["viewSize"], rad=u["rad"], speed=u["speed"], speedLimit=u["speedLimit"], crestShape=u["crestShape"])
+    base = rng.normal(0, 0.004, (H, W, 4)).astype(np.float32)
+    want, got = base.copy(), base.copy()
+    with np.errstate(all="ignore"):
+        oracle.flow_line(U, a, want)
+    u6 = np.array([u["viewSize"][0], u["viewSize"][1], u["rad"], u["speed"], u["speedLimit"], u["crestShape"]], np.float32)
+    p = lambda x: x.ctypes.data_as(_fp)
+    host_core.hh_flow_line(p(u6), a["miter"].shape[0], p(a["position"]), p(a["normal"]), p(a["miter"]), p(a["previous"]),
+                           p(a["time"]), p(a["dt"]), p(got), W, H)
+    assert same(got, want), seed

@@ -205,3 +205,25 @@ def test_harness_is_sensitive(ih, oracle):
                         flags[0], flags[1], 1, 0)
         differing[flags] = int((~((got == want) | (np.isnan(got) & np.isnan(want)))).sum())
     assert differing[(1, 1)] == 0 and differing[(1, 0)] > 100 and differing[(0, 1)] > 100, differing
+
+
+STRESS = int(os.environ.get("TB_STRESS", "0"))        # TB_STRESS=n: n extra random configurations (off in the normal run)
+
+
+@pytest.mark.parametrize("seed", range(STRESS))
+def test_stress_random_parameters(ih, oracle, seed):
+    rng = np.random.default_rng(40_000 + seed)
+    names = ["damping", "speedLimit", "forceWeight", "varyForce", "flowWeight", "varyFlow", "noiseWeight", "varyNoise", "flowDecay",
+             "noiseScale", "varyNoiseScale", "noiseSpeed", "varyNoiseSpeed", "target", "varyTarget"]
+    over = {}
+    for n in names:
+        r = rng.random()
+        if r < 0.25:
+            over[n] = 0.0
+        elif r < 0.5:
+            over[n] = float(rng.choice([1e-6, 0.01, 1.0, 50.0, 1e5, 1e7, -1.0, np.inf, np.nan]))
+    CASES.append((over, bool(rng.random() < 0.3), float(rng.choice([0.0, 16.7, 1e4, 2e9])), float(rng.choice([0.0, 16.7, 1e7]))))
+    try:
+        test_integrate_kernel_on_host_equals_oracle(ih, oracle, (int(rng.integers(1, 20)), int(rng.integers(1, 70))), len(CASES) - 1)
+    finally:
+        CASES.pop()

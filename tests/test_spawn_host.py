@@ -196,3 +196,19 @@ def test_optical_flow_and_layer_blend(ph, oracle, case):
     want2 = (layer * a + got * om).astype(np.float32)
     ph.ph_blend(p(got), p(np.ascontiguousarray(layer)), W * H)
     assert same(got, want2)
+
+
+STRESS = int(os.environ.get("TB_STRESS", "0"))        # TB_STRESS=n: n extra random configurations (off in the normal run)
+
+
+@pytest.mark.parametrize("seed", range(STRESS))
+def test_stress_random_spawners(ph, oracle, seed):
+    rng = np.random.default_rng(60_000 + seed)
+    pick = lambda xs: float(rng.choice(xs))
+    mat = tuple(float(v) for v in rng.choice([0, 1, -1, 0.5, 2.5, 1e3], 9))
+    SPAWNERS.append(((pick([1, 0.3, -2, 0]), pick([1, 0.3, -2, 1e4])), (pick([0, 0.002, 0.5, 1e3]), pick([0, 0.002, 0.5])),
+                     pick([1, 0.3, -2, 0, 1e4]), pick([1, 0, 0.2, 5, -1, np.inf]), mat, pick([0, 16.7, 9.87e5, 3.3e6, 1e9])))
+    try:
+        test_pixel_spawners(ph, oracle, sorted(VARIANTS)[seed % len(VARIANTS)], len(SPAWNERS) - 1)
+    finally:
+        SPAWNERS.pop()
