@@ -227,3 +227,27 @@ def test_stress_random_configurations(fh, seed):
     for t, d in plain_fold(seg, vals, flow0, 9.75, [t for t in range(G) if (t // 32) % world == rank]).items():
         want[t] = d
     assert np.array_equal(flow.view(np.uint32), want.view(np.uint32)), (seed, G, threshold, world, rank)
+
+
+@pytest.mark.parametrize("seed", range(STRESS))
+def test_stress_ring_chunks(fh, seed):
+    rng = np.random.default_rng(70_000 + seed)
+    G = int(rng.integers(1, 600))
+    seg, vals = make_segments(rng, G, float(rng.choice([0.5, 5, 25])), int(rng.choice([0, 7, 40])), int(rng.integers(97, 1500)))
+    chunks = int(rng.integers(1, 6))
+    per = ((G + chunks - 1) // chunks + 127) // 128 * 128                  # ring_fold: texels per chunk, CTA aligned
+    src = rng.normal(0, 0.01, (G, 4)).astype(np.float32)
+    dst, dst2 = np.full((G, 4), 7.0, np.float32), np.full((G, 4), 9.0, np.float32)
+    use2 = bool(rng.random() < 0.5)
+    want = np.full((G, 4), 7.0, np.float32)
+    for k in range(chunks):
+        t0, t1 = min(G, k * per), min(G, (k + 1) * per)
+        if t0 >= t1:
+            continue
+        run(fh, seg, vals, src, dst, dst2 if use2 else None, t0, t1, 1, 0, 1, (t1 - t0 + 127) // 128 * 4, 1.5, 96)
+        want[t0:t1] = src[t0:t1]
+        for t, d in plain_fold(seg, vals, src, 1.5, range(t0, t1)).items():
+            want[t] = d
+    assert np.array_equal(dst.view(np.uint32), want.view(np.uint32)), seed
+    if use2:
+        assert np.array_equal(dst2.view(np.uint32), want.view(np.uint32)), seed
