@@ -56,6 +56,17 @@ template <class K, class A> static void launch(K kernel, const A &args, long lon
             }
 }
 
+// the D6 pair table of the product (build_pairs), flattened: k, row_a, cur_a, row_b, cur_b per active pair
+extern "C" int sh_pairs(int PH, int *out5, int cap) {
+    const std::vector<PairEntry> pairs = build_pairs(PH);
+    if ((int)pairs.size() > cap) return -1;
+    for (size_t i = 0; i < pairs.size(); ++i) {
+        out5[5 * i] = pairs[i].k; out5[5 * i + 1] = pairs[i].row_a & 0x7fffffff; out5[5 * i + 2] = pairs[i].row_a < 0;
+        out5[5 * i + 3] = pairs[i].row_b & 0x7fffffff; out5[5 * i + 4] = pairs[i].row_b < 0;
+    }
+    return (int)pairs.size();
+}
+
 // One integrate step prev -> cur (so that the count can ride in it), then the splat of (cur, prev) into flow.
 // Returns the fragment count, -1 if the fused count disagrees with k_splat_count.
 extern "C" long long sh_step_and_splat(const float *state18, int PW, int PH, int W, int H, const float *prev, float *cur,
@@ -148,6 +159,9 @@ def sh(request, tmp_path_factory):
                     "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
                     "-I", os.path.join(ROOT, "tests", "host_harness"), "-o", str(out), str(cpp)], check=True)
     L = C.CDLL(str(out))
+    L.frag_bytes = request.param
+    L.sh_pairs.restype = C.c_int
+    L.sh_pairs.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
     L.sh_step_and_splat.restype = C.c_longlong
     L.sh_step_and_splat.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_float, C.c_float,
                                     C.POINTER(C.c_longlong)]
@@ -201,3 +215,17 @@ def test_stress_random_configurations(sh, oracle, seed):
     PW, PH = int(rng.integers(1, 40)), int(rng.integers(1, 90))
     W, H = int(rng.integers(1, 70)), int(rng.integers(1, 70))
     test_collect_on_host_equals_oracle(sh, oracle, PW, PH, W, H, float(rng.choice([0.01, 0.1, 0.5, 2.0])), 1000 + seed)
+
+
+def test_pair_table_equals_oracle_vertex_table(sh, oracle):
+    """build_pairs (tb_api.cu) against the oracle's vertex table (D6) for every height up to 3000 and the large ones."""
+    if sh.frag_bytes != 16:
+        pytest.skip("host table: independent of the fragment layout")
+    for PH in list(range(1, 3001)) + [4096, 5000, 8192, 12288, 16384, 28672, 32768, 65536, 100003]:
+        row, cur = oracle.vertex_table(PH)
+        want = [(k, int(row[2 * k]), int(cur[2 * k]), int(row[2 * k + 1]), int(cur[2 * k + 1])) for k in range(PH)
+                if not (row[2 * k] == row[2 * k + 1] and cur[2 * k] == cur[2 * k + 1])]
+        buf = (C.c_int * (5 * PH))()
+        n = sh.sh_pairs(PH, buf, PH)
+        got = [tuple(buf[5 * i:5 * i + 5]) for i in range(n)]
+        assert got == want, PH
