@@ -60,6 +60,9 @@ struct tb_ctx {
     uint32_t *prim_off = nullptr;          // n_prims+1: fragments per primitive -> exclusive offsets, [n_prims] = total
     int32_t *row_pair = nullptr;           // per texture row: pair index | kind << 30, or -1 (fused count in k_integrate)
     bool fuse_count = false;               // every pair reads one particle's prev/cur: the count can ride in k_integrate
+    bool fuse_partial = false;             // TB_FUSE_PARTIAL: all but a few pairs ride there, k_splat_count_odd counts the rest
+    int n_odd = 0;
+    int32_t *odd_pairs = nullptr;          // indices of the pairs that do not ride
     bool count_valid = false;              // prim_off/total on the host belong to the current (state, flow shape, viewSize)
     float count_vs[2] = {0.f, 0.f};
     int count_wh[2] = {0, 0};
@@ -976,15 +979,25 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
         TB_TRY(cudaStreamSynchronize(c->stream));
     }
     {
-        std::vector<int32_t> rp(static_cast<size_t>(PH), -1);
-        c->fuse_count = !pairs.empty();
+        // Row -> pair map of the count fused into k_integrate.  A pair rides there if both its vertices read ONE texel row
+        // (one particle's previous and current state) and no earlier pair has claimed that row: the D6 table of many
+        // non-power-of-two heights draws some rows twice (e.g. PH = 47: pairs 0 and 1 both draw row 0), and tall
+        // textures have a few pairs that join two different rows (3 of 4104 at PH = 8192).
+        std::vector<int32_t> rp(static_cast<size_t>(PH), -1), odd;
         for (size_t k = 0; k < pairs.size(); ++k) {
             const int ra = pairs[k].row_a & 0x7fffffff, rb = pairs[k].row_b & 0x7fffffff;
             const bool ca = pairs[k].row_a < 0, cb = pairs[k].row_b < 0;
-            // the count can ride in k_integrate only if every drawn row is drawn by exactly ONE pair: the D6 table of many
-            // non-power-of-two heights draws some rows twice (e.g. PH = 47: pairs 0 and 1 both draw row 0)
-            if (ra != rb || ca == cb || k >= (1u << 30) || rp[static_cast<size_t>(ra)] != -1) { c->fuse_count = false; break; }
-            rp[static_cast<size_t>(ra)] = static_cast<int32_t>(static_cast<uint32_t>(k) | ((cb ? 1u : 2u) << 30));   // 1: prev->cur, 2: cur->prev
+            const bool rides = ra == rb && ca != cb && k < (1u << 30) && rp[static_cast<size_t>(ra)] == -1;
+            if (rides) rp[static_cast<size_t>(ra)] = static_cast<int32_t>(static_cast<uint32_t>(k) | ((cb ? 1u : 2u) << 30));   // 1: prev->cur, 2: cur->prev
+            else odd.push_back(static_cast<int32_t>(k));
+        }
+        c->fuse_count = !pairs.empty() && odd.empty();
+        // experimental, off unless TB_FUSE_PARTIAL is set (not yet run on a GPU): ride anyway when only a few pairs cannot
+        c->fuse_partial = std::getenv("TB_FUSE_PARTIAL") != nullptr && !pairs.empty() && !odd.empty() && odd.size() * 16 <= pairs.size();
+        c->n_odd = static_cast<int>(odd.size());
+        if (c->fuse_partial) {
+            TB_TRY(cudaMalloc(&c->odd_pairs, odd.size() * sizeof(int32_t)));
+            TB_TRY(cudaMemcpyAsync(c->odd_pairs, odd.data(), odd.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         }
         TB_TRY(cudaMalloc(&c->row_pair, rp.size() * sizeof(int32_t)));
         TB_TRY(cudaMemcpyAsync(c->row_pair, rp.data(), rp.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -1013,7 +1026,7 @@ int tb_destroy(tb_ctx *c) {
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
     cudaFree(c->frames);
     cudaFree(c->line_attr); cudaFree(c->line_verts); cudaFree(c->line_bbox);
-    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off); cudaFree(c->row_pair);
+    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off); cudaFree(c->row_pair); cudaFree(c->odd_pairs);
     cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->hot); cudaFree(c->d_flag);
     for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); }
     if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -1094,7 +1107,7 @@ int tb_step(tb_ctx *c, float time, float dt) {
     A.packed_noise = scalar_noise ? 0 : 1;
     A.pk.one = 1.0f; A.pk.neg_one = -1.0f; A.pk.neg_zero = -0.0f;
     A.wander = c->wander;
-    const bool fuse = c->fuse_count && c->n_prims > 0;
+    const bool fuse = (c->fuse_count || c->fuse_partial) && c->n_prims > 0;
     A.row_pair = c->row_pair;
     A.prim_off = fuse ? c->prim_off : nullptr;
     A.n_pairs = c->n_pairs;
@@ -1126,6 +1139,11 @@ int tb_step(tb_ctx *c, float time, float dt) {
     TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     c->ev_count[0] += 1;
     c->splat_since_step = false;
+    if (fuse && c->fuse_partial) {          // the pairs that could not ride: the state buffers are final on this stream
+        const SplatArgs SA = splat_args(c);
+        k_splat_count_odd<<<blocks_for(static_cast<long long>(SA.cols) * c->n_odd, 256), 256, 0, c->stream>>>(SA, c->odd_pairs, c->n_odd);
+        if (int r = check_launch(c, "k_splat_count_odd")) return r;
+    }
     if (fuse) {
         // the scan and the 4-byte total travel to the host now, so that the next tb_splat_flow finds the
         // fragment count waiting instead of stalling the GPU on a round trip

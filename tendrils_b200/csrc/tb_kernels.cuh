@@ -314,6 +314,20 @@ __global__ void __launch_bounds__(256) k_splat_count(const SplatArgs A) {
     });
 }
 
+// Pass 1 for a SUBSET of the pairs -- the few that cannot ride in k_integrate (TB_FUSE_PARTIAL): thread = (local
+// column, odd pair).  Same count as k_splat_count (count_fragments == the enumeration, tests/test_raster_host.py).
+__global__ void __launch_bounds__(256) k_splat_count_odd(const SplatArgs A, const int32_t *__restrict__ odd, int n_odd) {
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (tid >= static_cast<long long>(A.cols) * n_odd) return;
+    const int xl = static_cast<int>(tid / n_odd);
+    const int pi = odd[tid - static_cast<long long>(xl) * n_odd];
+    const PairEntry pe = A.pairs[pi];
+    const size_t base = static_cast<size_t>(xl) * A.PH;
+    const float4 sa = __ldg(((pe.row_a < 0) ? A.cur : A.prev) + base + (pe.row_a & 0x7fffffff));
+    const float4 sb = __ldg(((pe.row_b < 0) ? A.cur : A.prev) + base + (pe.row_b & 0x7fffffff));
+    A.prim_off[static_cast<size_t>(xl) * A.n_pairs + pi] = count_fragments(sa, sb, A.vsx, A.vsy, A.W, A.H);
+}
+
 // Pass 2 (after the exclusive scan of prim_off): write (texel, colour) of every fragment at its
 // slot.  No atomics: the slot order IS the draw order.
 __global__ void __launch_bounds__(256) k_splat_emit(const SplatArgs A) {
