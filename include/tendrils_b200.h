@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TB_ABI_VERSION 1
+#define TB_ABI_VERSION 2
 
 typedef struct tb_ctx tb_ctx;
 
@@ -149,54 +149,11 @@ int tb_step(tb_ctx *ctx, float time, float dt);
 int tb_splat_flow(tb_ctx *ctx, float time);
 
 /* Split form of tb_splat_flow for column-sharded contexts: tb_splat_collect rasterises this
- * context's primitives into ordered per-texel fragment lists; tb_splat_fold blends them onto
- * the flow grid currently in the context.  Folding rank 0..P-1 in turn onto one grid equals
- * the single-context result bit for bit (primitive order = column order). */
+ * context's primitives into per-tile fragment bins (draw order inside a bin); tb_splat_fold blends
+ * them onto the flow grid currently in the context.  Folding rank 0..P-1 in turn onto one grid
+ * equals the single-context result bit for bit (primitive order = column order). */
 int tb_splat_collect(tb_ctx *ctx, float time);
 int tb_splat_fold(tb_ctx *ctx);
-
-/* The ordered fold of a column-sharded run over peer memory (one process per GPU, one node).  Every rank
- * exports IPC handles of its flow grid / inbox / flags (tb_ring_export, tb_ring_handle_bytes() bytes), the host
- * layer exchanges them (any transport), and each rank maps those of rank+1 (tb_ring_connect).  After
- * tb_splat_collect, tb_splat_fold_ring folds chunk by chunk: wait for the previous rank's chunk, blend this
- * rank's fragments onto it, write the result straight into the next rank's inbox over NVLink; the last rank's
- * result is the new grid and travels once around the ring.  Must be redone after tb_resize_flow. */
-int64_t tb_ring_handle_bytes(void);
-int tb_ring_export(tb_ctx *ctx, void *handles_out, int64_t n_bytes);
-int tb_ring_connect(tb_ctx *ctx, int32_t rank, int32_t world, const void *next_rank_handles, int64_t n_bytes);
-int tb_splat_fold_ring(tb_ctx *ctx);
-
-/* The PARALLEL ordered fold of a column-sharded run over peer memory ("bands"; one process per GPU, one node,
- * at most 16 ranks).  Every rank exports IPC handles of its sorted fragments / segment table / flow grid / flags
- * (tb_bands_export; `reserve_fragments` fixes the capacity of the fragment buffers, which the other ranks map --
- * a draw that needs more fails with TB_ERR_UNSUPPORTED), the host layer all-gathers the blobs, and each rank
- * maps all of them (tb_bands_connect, `all_handles` = world x tb_bands_handle_bytes(), rank order).  After
- * tb_splat_collect, tb_splat_fold_bands: barrier; fold the 32-texel tiles this rank owns (tile % world == rank)
- * with the fragments of source rank 0, 1, ... read straight out of their memory over NVLink (source order =
- * column order = the reference's primitive order, src/particles.js:182-186); store the finished tiles into
- * every rank's grid; barrier.  No rank waits for another rank's fold.  Must be redone after tb_resize_flow. */
-int64_t tb_bands_handle_bytes(void);
-int tb_bands_export(tb_ctx *ctx, int64_t reserve_fragments, void *handles_out, int64_t n_bytes);
-int tb_bands_connect(tb_ctx *ctx, int32_t rank, int32_t world, const void *all_handles, int64_t n_bytes);
-int tb_splat_fold_bands(tb_ctx *ctx);
-
-/* Band exchange for column-sharded runs (the scalable form of the ordered fold): the grid is cut into one band
- * of texels per rank; every rank sends each band's slice of its sorted fragments to the band's owner (an
- * all-to-all the host layer performs on the device pointers below), folds the pieces it received in source-rank
- * order = draw order onto its band (tb_splat_fold_piece), and the bands are all-gathered.  No rank waits for
- * another rank's fold; the result equals the single-GPU fold bit for bit.
- *   tb_splat_band_offsets      after tb_splat_collect: index in this rank's sorted fragment array where each
- *                              band starts (n_bands+1 values; synchronises)
- *   tb_splat_exchange_buffers  device pointers: what to send (sorted keys u32 / values of *val_bytes bytes each)
- *                              and where to receive recv_items items (grown on demand)
- *   tb_splat_fold_piece        blend items [piece_offset, +piece_items) of the receive buffers onto texels
- *                              [t_begin, t_end) of the flow grid
- *   tb_splat_exchange_done     end of the draw (timing, state) */
-int tb_splat_band_offsets(tb_ctx *ctx, int32_t n_bands, int32_t band_texels, int64_t *host_offsets);
-int tb_splat_exchange_buffers(tb_ctx *ctx, int64_t recv_items, void **send_keys, void **send_vals, void **recv_keys,
-                              void **recv_vals, int32_t *val_bytes);
-int tb_splat_fold_piece(tb_ctx *ctx, int64_t piece_offset, int64_t piece_items, int32_t t_begin, int32_t t_end);
-int tb_splat_exchange_done(tb_ctx *ctx);
 
 /* Tendrils.spawn(cpuFn) with the default initSpawner: fills ALL buffers
  * (src/index.js:425-429, src/particles.js:94-117, src/spawn/init/cpu.js:3-8). */
@@ -220,10 +177,6 @@ int tb_download(tb_ctx *ctx, tb_buffer which, float *host, int64_t n_floats);
 /* Alpha-over blend of a caller-rendered RGBA layer into the flow grid (hook for the L4
  * inputs that draw into the flow FBO: optical flow, pointer flow-lines; src/demo.main.js:1107-1159). */
 int tb_blend_into_flow(tb_ctx *ctx, const float *rgba, int32_t w, int32_t h);
-
-/* diagnostic tap: [fold begin, end) of every texel's fragment segment left by the last splat
- * (2*W*H words); used by tools/ to study fragment-list length distributions. */
-int tb_debug_segments(tb_ctx *ctx, uint32_t *host, int64_t n_words);
 
 /* OpticalFlow.update() + screen.render() with the flow FBO bound (src/optical-flow/index.frag:55-81,
  * src/optical-flow/index.js:50-58, call site src/demo.main.js:1131-1156): the gradient optical flow of two RGBA8

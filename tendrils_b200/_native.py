@@ -59,19 +59,6 @@ SYMBOLS = {
     "tb_splat_flow": (C.c_int, [_ctx, C.c_float]),
     "tb_splat_collect": (C.c_int, [_ctx, C.c_float]),
     "tb_splat_fold": (C.c_int, [_ctx]),
-    "tb_ring_handle_bytes": (C.c_int64, []),
-    "tb_ring_export": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
-    "tb_ring_connect": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
-    "tb_splat_fold_ring": (C.c_int, [_ctx]),
-    "tb_bands_handle_bytes": (C.c_int64, []),
-    "tb_bands_export": (C.c_int, [_ctx, C.c_int64, C.c_void_p, C.c_int64]),
-    "tb_bands_connect": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
-    "tb_splat_fold_bands": (C.c_int, [_ctx]),
-    "tb_splat_band_offsets": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
-    "tb_splat_exchange_buffers": (C.c_int, [_ctx, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
-    "tb_splat_fold_piece": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
-    "tb_splat_exchange_done": (C.c_int, [_ctx]),
     "tb_reset": (C.c_int, [_ctx]),
     "tb_spawn_init": (C.c_int, [_ctx, C.c_int]),
     "tb_spawn_ball": (C.c_int, [_ctx, C.c_float, C.c_float, C.c_int]),
@@ -80,7 +67,6 @@ SYMBOLS = {
     "tb_upload": (C.c_int, [_ctx, C.c_int, _fp, C.c_int64]),
     "tb_download": (C.c_int, [_ctx, C.c_int, _fp, C.c_int64]),
     "tb_blend_into_flow": (C.c_int, [_ctx, _fp, C.c_int32, C.c_int32]),
-    "tb_debug_segments": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.c_int64]),
     "tb_flow_line": (C.c_int, [_ctx, C.POINTER(TbFlowLineParams), C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp]),
     "tb_optical_flow": (C.c_int, [_ctx, C.POINTER(TbOpticalFlowParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "tb_device_ptr": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
@@ -116,7 +102,7 @@ def load():
             fn = getattr(L, name)       # AttributeError if the header and the library diverge
             fn.restype = res
             fn.argtypes = args
-        if L.tb_abi_version() != 1:
+        if L.tb_abi_version() != 2:
             raise TendrilsError("tendrils_b200: ABI version mismatch")
         _lib = L
     return _lib

@@ -4,10 +4,8 @@
 // Tendrils (src/index.js) and Particles (src/particles.js) classes: ping-pong state
 // buffers, the logic pass, the flow splat, the spawn passes.  No CPU fallback.
 #include "tb_kernels.cuh"
+#include "tb_splat.cuh"
 #include "tb_flowline.cuh"
-
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -31,12 +29,12 @@ struct tb_ctx {
     int W = 0, H = 0;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;            // low priority: noise of the next step under the previous splat
+    cudaStream_t side = nullptr;            // noise of the next step under the previous splat (TB_OVERLAP)
     cudaEvent_t ev_state = nullptr;         // last write to the state buffers (main stream)
     cudaEvent_t ev_noise = nullptr;         // noise kernel done (side stream)
     float2 *wander = nullptr;
     bool splat_since_step = false;          // something HBM-bound is queued that the noise can hide under
-    bool overlap = true;
+    bool overlap = false;
 
     float4 *buf[2] = {nullptr, nullptr};   // [0] current, [1] previous (src/particles.js:128)
     float4 *targets = nullptr;
@@ -53,77 +51,44 @@ struct tb_ctx {
     int *line_bbox = nullptr;
     int line_cap = 0;
 
-    // flow splat scratch
+    // flow splat (tb_splat.cuh)
     PairEntry *pairs = nullptr;
     int n_pairs = 0;
     long long n_prims = 0;                 // local primitives = columns * n_pairs
-    uint32_t *prim_off = nullptr;          // n_prims+1: fragments per primitive -> exclusive offsets, [n_prims] = total
-    int32_t *row_pair = nullptr;           // per texture row: pair index | kind << 30, or -1 (fused count in k_integrate)
-    bool fuse_count = false;               // every pair reads one particle's prev/cur: the count can ride in k_integrate
-    bool fuse_partial = false;             // TB_FUSE_PARTIAL: all but a few pairs ride there, k_splat_count_odd counts the rest
-    int n_odd = 0;
-    int32_t *odd_pairs = nullptr;          // indices of the pairs that do not ride
-    bool count_valid = false;              // prim_off/total on the host belong to the current (state, flow shape, viewSize)
-    float count_vs[2] = {0.f, 0.f};
-    int count_wh[2] = {0, 0};
-    void *scan_tmp = nullptr;
-    size_t scan_tmp_bytes = 0;
-    uint32_t *keys[2] = {nullptr, nullptr};   // texel of each fragment (draw order / sorted)
-    FragVal *vals[2] = {nullptr, nullptr};
-    void *sort_tmp = nullptr;
-    size_t sort_tmp_bytes = 0;
-    uint32_t frag_cap = 0;
-    uint32_t *seg = nullptr;               // 2*G: [begin,end) of every texel's sorted segment
-    uint32_t *hot = nullptr;               // [0] = count, [1] = cursor, [2..G+1] = worklist of hot texels
-    int n_sms = 148;
-    uint32_t hot_threshold = kFoldHot;
-
-    // sharded ring fold over peer memory (tb_ring_*): my inbox + flags, the next rank's mapped over NVLink
-    static constexpr int kRingMaxChunks = 64;
-    int ring_chunks = 16;
-    int ring_rank = 0, ring_world = 1;
-    float4 *inbox = nullptr;               // the previous rank writes its folded chunks here
-    uint32_t *ring_flags = nullptr;        // [0..C): inbox chunk ready (epoch), [C..2C): final chunk in my grid (epoch)
-    uint32_t *ring_hot_counts = nullptr;   // per chunk hot-texel counters
-    float4 *next_inbox = nullptr, *next_flow = nullptr;
-    uint32_t *next_flags = nullptr;
-    bool ring_connected = false;
-    uint32_t ring_epoch = 0;
-    cudaStream_t ring_stream = nullptr;    // forwards final chunks around the ring
-    cudaEvent_t ev_ring_fwd = nullptr, ev_ring_begin = nullptr;
-    // band fold over peer memory (tb_bands_*): every rank maps every rank's sorted fragments, segments, grid, flags
-    bool bands_connected = false;
-    bool frag_fixed = false;               // keys/vals are exported through IPC handles: they must not be reallocated
-    int bands_rank = 0, bands_world = 1;
-    uint32_t bands_epoch = 0;
-    uint32_t *bands_flags = nullptr;       // [kBandPhases][kMaxBandRanks]: the epoch each rank has reached
-    BandSources band_src{};                // every rank's segment table (own slot: local pointer)
-    BandSinks band_sinks{};                // every rank's merged fragment array (its vals[0]) and offset table
-    BandPeers band_peers{};                // every rank's flow grid and flags
-    int bands_mine = 0;                    // 32-texel tiles this rank folds
-    uint32_t *bands_len = nullptr;         // [mine*32*world + 1] fragments per (local texel, source), texel-major; last = 0
-    uint32_t *bands_off = nullptr;         // its exclusive scan: where each segment goes in the merged array
-    uint32_t *bands_dst = nullptr;         // [G] written by the owners: where MY segment of each texel goes in its owner's array
-    uint32_t *bands_seg = nullptr;         // 2*G: merged segment table (only this rank's texels are meaningful)
-    void *bands_scan_tmp = nullptr;
-    size_t bands_scan_bytes = 0;
-    int *bands_overflow = nullptr;         // device flag: the merged fragments did not fit
-    int *h_bands_overflow = nullptr;       // pinned copy, read at the start of the next fold
-    cudaEvent_t ev_bands = nullptr;
-    int key_bits = 1;
-    uint32_t *h_total = nullptr;           // pinned
-    cudaEvent_t ev_total = nullptr;
+    TileGeom geom{};
+    int slab_prims = 0, n_slabs = 0;       // slabs of consecutive primitives (fixed per context)
+    uint32_t *slab_hist = nullptr;         // [T][n_slabs] fragments per (tile, slab) -> per-tile exclusive scan over the slabs
+    uint32_t *tile_total = nullptr;        // [T]
+    uint32_t *bin_off = nullptr;           // [T + 1]
+    uint32_t *tickets = nullptr;           // [0] hist, [1] scatter, [2] fold work counters, [3] fold items, [4] a bin beyond 2^32
+    FoldItem *items = nullptr;
+    int max_items = 0;
+    PlanOut *d_plan = nullptr;
+    PlanOut *h_plan = nullptr;             // pinned; valid once ev_plan has completed
+    cudaEvent_t ev_plan = nullptr;
+    Frag *bins = nullptr;                  // every fragment of a draw, binned by tile, draw order inside a bin
+    uint32_t bin_cap = 0;
+    bool bin_fixed = false;                // the bin array is mapped by other ranks: it cannot grow without a reconnect
+    uint32_t hot_bin = 0xffffffffu;
+    bool pending = false;                  // a draw is queued whose capacity check has not been read yet
+    int pending_stage = 0;                 // 1: collect only, 2: collect + fold
+    float pending_time = 0.f;
     bool collected = false;
     float collect_time = 0.f;
+    int n_sms = 148;
+    int scatter_ctas = 0, fold_ctas = 0, hist_ctas = 0;
 
     int *d_flag = nullptr;                 // device scratch flag
     int *h_flag = nullptr;                 // pinned
     bool targets_finite = true;
 
-    // CUDA-event timing rings: [class][slot][begin/end]; class 0 = integrate, 1 = flow splat
+    // CUDA-event timing rings: [class][slot][begin/end]; class 0 = integrate, 1 = flow splat, 2 = noise (side stream)
     static constexpr int kTimingSlots = 512;
-    cudaEvent_t ev_ring[3][kTimingSlots][2] = {};   // 0 integrate (main stream), 1 flow splat, 2 noise (side stream)
+    cudaEvent_t ev_ring[3][kTimingSlots][2] = {};
     int64_t ev_count[3] = {0, 0, 0};
+    // finer: the five kernels of the flow splat (hist, rows + plan, scatter, fold), same slots as class 1
+    cudaEvent_t ev_stage[kTimingSlots][5] = {};
+    bool stage_timing = false;
 
     tb_state state{};
     bool have_state = false;
@@ -204,56 +169,71 @@ bool columns_are_identity(int PW) {
     return true;
 }
 
-int ring_release(tb_ctx *c);
-int bands_release(tb_ctx *c);
+// Tiles of the binning: 16 x 16 texels for small grids, grown (x first) until there are at most 1024 of them --
+// 32 x 32 at 1024^2 -- and, for grids beyond that, until at most kMaxTiles.
+TileGeom choose_geom(int W, int H) {
+    TileGeom g{};
+    g.W = W; g.H = H;
+    g.txl = 4; g.tyl = 4;
+    auto tiles = [&]() {
+        g.tiles_x = (W + (1 << g.txl) - 1) >> g.txl;
+        g.tiles_y = (H + (1 << g.tyl) - 1) >> g.tyl;
+        g.T = g.tiles_x * g.tiles_y;
+        return g.T;
+    };
+    while (tiles() > 1024 && g.txl + g.tyl < 10) { if (g.txl <= g.tyl) ++g.txl; else ++g.tyl; }
+    while (tiles() > kMaxTiles) { if (g.txl <= g.tyl) ++g.txl; else ++g.tyl; }
+    return g;
+}
+
+int tiles_release(tb_ctx *c);
 
 int alloc_flow(tb_ctx *c, int w, int h) {
-    ring_release(c);
-    bands_release(c);
-    TB_REQUIRE(c, w >= 1 && h >= 1 && static_cast<long long>(w) * h < (1LL << 31), "flow grid dimensions out of bounds");
-    if (c->flow) cudaFree(c->flow);
-    if (c->seg) cudaFree(c->seg);
-    if (c->hot) cudaFree(c->hot);
-    c->flow = nullptr; c->seg = nullptr; c->hot = nullptr;
+    tiles_release(c);
+    TB_REQUIRE(c, w >= 1 && h >= 1 && w <= 32768 && h <= 32768, "flow grid dimensions out of bounds");
+    cudaFree(c->flow); cudaFree(c->slab_hist); cudaFree(c->tile_total); cudaFree(c->bin_off); cudaFree(c->items);
+    c->flow = nullptr; c->slab_hist = nullptr; c->tile_total = nullptr; c->bin_off = nullptr; c->items = nullptr;
     c->W = w; c->H = h;
+    c->geom = choose_geom(w, h);
     const size_t G = static_cast<size_t>(w) * h;
+    const int T = c->geom.T;
     TB_CUDA(c, cudaMalloc(&c->flow, G * sizeof(float4)));
-    TB_CUDA(c, cudaMalloc(&c->seg, 2 * G * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->hot, (G + 2) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->slab_hist, static_cast<size_t>(T) * std::max(c->n_slabs, 1) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->tile_total, static_cast<size_t>(T) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->bin_off, static_cast<size_t>(T + 1) * sizeof(uint32_t)));
+    c->max_items = 64 * T;
+    TB_CUDA(c, cudaMalloc(&c->items, static_cast<size_t>(c->max_items) * sizeof(FoldItem)));
     TB_CUDA(c, cudaMemsetAsync(c->flow, 0, G * sizeof(float4), c->stream));
-    c->key_bits = 1;
-    while ((1ull << c->key_bits) < G) c->key_bits += 1;
+    // persistent grids of the splat kernels for this tile count
+    TB_CUDA(c, cudaFuncSetAttribute(k_splat_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem_bytes(T))));
+    TB_CUDA(c, cudaFuncSetAttribute(k_splat_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFoldSmemBytes)));
+    int per_sm = 0;
+    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_scatter, kEmitThreads, scatter_smem_bytes(T)));
+    c->scatter_ctas = std::max(1, per_sm) * c->n_sms;
+    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_fold, kFoldThreads, kFoldSmemBytes));
+    c->fold_ctas = std::max(1, per_sm) * c->n_sms;
+    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_hist, kHistThreads, static_cast<size_t>(T) * sizeof(uint32_t)));
+    c->hist_ctas = std::max(1, per_sm) * c->n_sms;
     c->collected = false;
+    c->pending = false;
     return TB_OK;
 }
 
-int ensure_frag_cap(tb_ctx *c, uint64_t need) {
-    if (need <= c->frag_cap) return TB_OK;
-    TB_REQUIRE(c, need < (1ull << 31), "flow splat: more than 2^31 fragments in one draw");
-    if (c->frag_fixed)
-        return fail(c, TB_ERR_UNSUPPORTED, "flow splat: " + std::to_string(need) + " fragments exceed the " +
-                    std::to_string(c->frag_cap) + " reserved by tb_bands_export (the buffers are mapped by the other ranks); "
+int ensure_bin_cap(tb_ctx *c, uint64_t need) {
+    if (need <= c->bin_cap) return TB_OK;
+    if (need >= (1ull << 31))
+        return fail(c, TB_ERR_OVERFLOW, "tendrils-b200: flow splat: " + std::to_string(need) + " fragments in one draw (limit 2^31)");
+    if (c->bin_fixed)
+        return fail(c, TB_ERR_OVERFLOW, "tendrils-b200: flow splat: " + std::to_string(need) + " fragments exceed the " +
+                    std::to_string(c->bin_cap) + " reserved by tb_tiles_export (the bins are mapped by the other ranks); "
                     "export with a larger reserve and reconnect");
     uint64_t cap = std::max<uint64_t>(need + need / 4, 1u << 16);
     if (cap >= (1ull << 31)) cap = (1ull << 31) - 1;
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 2; ++i) {
-        if (c->keys[i]) cudaFree(c->keys[i]);
-        if (c->vals[i]) cudaFree(c->vals[i]);
-        c->keys[i] = nullptr; c->vals[i] = nullptr;
-    }
-    if (c->sort_tmp) cudaFree(c->sort_tmp);
-    c->sort_tmp = nullptr;
-    c->frag_cap = 0;
-    for (int i = 0; i < 2; ++i) {
-        TB_CUDA(c, cudaMalloc(&c->keys[i], cap * sizeof(uint32_t)));
-        TB_CUDA(c, cudaMalloc(&c->vals[i], cap * sizeof(FragVal)));
-    }
-    c->sort_tmp_bytes = 0;
-    TB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, c->sort_tmp_bytes, c->keys[0], c->keys[1], c->vals[0], c->vals[1],
-                                               static_cast<int64_t>(cap), 0, 32, c->stream));
-    TB_CUDA(c, cudaMalloc(&c->sort_tmp, c->sort_tmp_bytes));
-    c->frag_cap = static_cast<uint32_t>(cap);
+    cudaFree(c->bins);
+    c->bins = nullptr; c->bin_cap = 0;
+    TB_CUDA(c, cudaMalloc(&c->bins, cap * sizeof(Frag)));
+    c->bin_cap = static_cast<uint32_t>(cap);
     return TB_OK;
 }
 
@@ -272,104 +252,163 @@ int check_launch(tb_ctx *c, const char *what) {
     return TB_OK;
 }
 
-SplatArgs splat_args(tb_ctx *c) {
-    SplatArgs A{};
-    A.cur = c->buf[0];
-    A.prev = c->buf[1];
-    A.pairs = c->pairs;
-    A.n_pairs = c->n_pairs;
-    A.PH = c->PH;
-    A.cols = c->col1 - c->col0;
-    A.W = c->W;
-    A.H = c->H;
-    A.vsx = c->state.viewSize[0];
-    A.vsy = c->state.viewSize[1];
-    A.speedLimit = c->state.speedLimit;
-    A.prim_off = c->prim_off;
-    A.keys = c->keys[0];
-    A.vals = c->vals[0];
-    A.cap = c->frag_cap;
-    A.total = c->prim_off + c->n_prims;      // slot n_prims holds the total after the scan
-    return A;
+PrimSource prim_source(tb_ctx *c) {
+    PrimSource S{};
+    S.cur = c->buf[0];
+    S.prev = c->buf[1];
+    S.pairs = c->pairs;
+    S.n_pairs = c->n_pairs;
+    S.PH = c->PH;
+    S.n_prims = c->n_prims;
+    return S;
 }
 
-// exclusive scan of the per-primitive counts in place and the total to the host (async; ev_total)
-int scan_counts(tb_ctx *c) {
-    const long long threads = c->n_prims;
-    TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp, c->scan_tmp_bytes, c->prim_off, c->prim_off,
-                                             static_cast<int>(threads + 1), c->stream));
-    c->launches += 2;    // DeviceScanInitKernel + DeviceScanKernel
-    TB_CUDA(c, cudaMemcpyAsync(c->h_total, c->prim_off + threads, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaEventRecord(c->ev_total, c->stream));
+// Collect: rasterise this context's primitives into per-tile bins, draw order inside every bin.  Four launches, nothing
+// comes back to the host on the way: the plan (fragment total, overflow flag) is copied out behind the kernels and read
+// by resolve_pending() at the next API call.
+int launch_collect(tb_ctx *c, float time) {
+    const int T = c->geom.T;
+    cudaEvent_t *stage = c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots];
+    if (c->n_prims > 0) {
+        HistArgs HA{};
+        HA.src = prim_source(c);
+        HA.g = c->geom;
+        HA.vsx = c->state.viewSize[0]; HA.vsy = c->state.viewSize[1];
+        HA.slab_prims = c->slab_prims; HA.n_slabs = c->n_slabs;
+        HA.slab_hist = c->slab_hist;
+        HA.ticket = c->tickets + 0;
+        k_splat_hist<<<std::min(c->n_slabs, c->hist_ctas), kHistThreads, static_cast<size_t>(T) * sizeof(uint32_t), c->stream>>>(HA);
+        if (int r = check_launch(c, "k_splat_hist")) return r;
+        if (c->stage_timing) cudaEventRecord(stage[1], c->stream);
+        k_splat_rows<<<blocks_for(T, 8), 256, 0, c->stream>>>(c->slab_hist, T, c->n_slabs, c->tile_total, c->tickets + 4);
+        if (int r = check_launch(c, "k_splat_rows")) return r;
+    } else {
+        TB_CUDA(c, cudaMemsetAsync(c->tile_total, 0, static_cast<size_t>(T) * sizeof(uint32_t), c->stream));
+    }
+    PlanArgs PA{};
+    PA.g = c->geom;
+    PA.tile_total = c->tile_total;
+    PA.bin_off = c->bin_off;
+    PA.items = c->items; PA.max_items = c->max_items;
+    PA.cap = c->bin_cap;
+    PA.hot_bin = c->hot_bin;
+    PA.too_many = c->tickets + 4;
+    PA.tickets = c->tickets;
+    PA.out = c->d_plan;
+    k_splat_plan<<<1, kPlanThreads, 0, c->stream>>>(PA);
+    if (int r = check_launch(c, "k_splat_plan")) return r;
+    TB_CUDA(c, cudaMemcpyAsync(c->h_plan, c->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaEventRecord(c->ev_plan, c->stream));
+    if (c->stage_timing) cudaEventRecord(stage[2], c->stream);
+    if (c->n_prims > 0) {
+        ScatterArgs SA{};
+        SA.src = prim_source(c);
+        SA.g = c->geom;
+        SA.vsx = c->state.viewSize[0]; SA.vsy = c->state.viewSize[1];
+        SA.speedLimit = c->state.speedLimit;
+        SA.time = time;
+        SA.slab_prims = c->slab_prims; SA.n_slabs = c->n_slabs;
+        SA.slab_hist = c->slab_hist;
+        SA.bin_off = c->bin_off;
+        SA.plan = c->d_plan;
+        SA.ticket = c->tickets + 1;
+        SA.bins[0] = c->bins;
+        SA.tile_owner = nullptr;
+        k_splat_scatter<<<std::min(c->n_slabs, c->scatter_ctas), kEmitThreads, scatter_smem_bytes(T), c->stream>>>(SA);
+        if (int r = check_launch(c, "k_splat_scatter")) return r;
+    }
+    if (c->stage_timing) cudaEventRecord(stage[3], c->stream);
     return TB_OK;
 }
 
-// Rasterise this context's primitives into per-texel fragment segments in draw order:
-//   count per primitive -> exclusive scan -> emit in draw order (no atomics) -> stable radix
-//   sort by texel -> segment bounds.
+int launch_fold(tb_ctx *c, float time) {
+    FoldArgs FA{};
+    FA.g = c->geom;
+    FA.time = time;
+    FA.bins = c->bins;
+    FA.items = c->items;
+    FA.n_items = c->tickets + 3;
+    FA.ticket = c->tickets + 2;
+    FA.flow[0] = c->flow;
+    FA.n_flow = 1;
+    k_splat_fold<<<std::min(c->fold_ctas, c->max_items), kFoldThreads, kFoldSmemBytes, c->stream>>>(FA);
+    return check_launch(c, "k_splat_fold");
+}
+
+int queue_splat(tb_ctx *c, float time, int stage) {
+    cudaEvent_t *ev = c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots];
+    if (stage >= 1) {
+        TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
+        if (c->stage_timing) cudaEventRecord(c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots][0], c->stream);
+        if (int r = launch_collect(c, time)) return r;
+    }
+    if (stage == 2) {
+        if (int r = launch_fold(c, time)) return r;
+        if (c->stage_timing) cudaEventRecord(c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots][4], c->stream);
+        TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    }
+    return TB_OK;
+}
+
+// The capacity check of the last queued draw.  Its kernels did nothing if the fragments did not fit (the plan kernel
+// saw that on the device): grow the bin array and queue the draw again -- the state buffers and the grid are as they
+// were, because every entry point comes through here before it touches either.
+int resolve_pending(tb_ctx *c) {
+    if (!c->pending) return TB_OK;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        TB_CUDA(c, cudaEventSynchronize(c->ev_plan));
+        c->last_frags = static_cast<int64_t>(c->h_plan->total);
+        if (!c->h_plan->overflow) {
+            c->pending = false;
+            return TB_OK;
+        }
+        if (int r = ensure_bin_cap(c, c->h_plan->total)) { c->pending = false; c->collected = false; return r; }
+        if (c->pending_stage == 2) c->ev_count[1] -= 1;              // the retry re-records the same timing slot
+        const int r = queue_splat(c, c->pending_time, c->pending_stage);
+        if (c->pending_stage == 2) c->ev_count[1] += 1;
+        if (r) { c->pending = false; return r; }
+    }
+    c->pending = false;
+    return fail(c, TB_ERR_OVERFLOW, "tendrils-b200: flow splat: the fragment bins could not be sized");
+}
+
 int collect(tb_ctx *c, float time) {
     TB_REQUIRE(c, c->have_state, "tb_set_state must be called before the flow splat");
-    const size_t G = static_cast<size_t>(c->W) * c->H;
-    const long long threads = c->n_prims;
+    if (int r = resolve_pending(c)) return r;
     c->collect_time = time;
     c->collected = false;
-    c->last_frags = 0;
     c->splat_since_step = true;
-    // splat timing: from the start of the collect to the end of the fold (in a sharded run this
-    // includes waiting for the grid from the previous rank)
-    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][0], c->stream));
-    if (threads <= 0) *c->h_total = 0;
-    if (threads > 0) {
-        const bool have_count = c->count_valid && c->count_wh[0] == c->W && c->count_wh[1] == c->H &&
-                                c->count_vs[0] == c->state.viewSize[0] && c->count_vs[1] == c->state.viewSize[1];
-        if (!have_count) {      // the count did not ride in k_integrate (or the draw parameters changed since)
-            TB_CUDA(c, cudaMemsetAsync(c->prim_off, 0, (threads + 1) * sizeof(uint32_t), c->stream));
-            SplatArgs A = splat_args(c);
-            k_splat_count<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
-            if (int r = check_launch(c, "k_splat_count")) return r;
-            if (int r = scan_counts(c)) return r;
-        }
-        c->count_valid = false;                                // consumed: the offsets are about to be used
-        TB_CUDA(c, cudaEventSynchronize(c->ev_total));        // the sort needs the count on the host
-        if (int r = ensure_frag_cap(c, *c->h_total)) return r;
-        c->last_frags = *c->h_total;
-    }
-    const uint32_t F = *c->h_total;
-    if (F > 0) {
-        SplatArgs A = splat_args(c);
-        k_splat_emit<<<blocks_for(threads, 256), 256, 0, c->stream>>>(A);
-        if (int r = check_launch(c, "k_splat_emit")) return r;
-        TB_CUDA(c, cub::DeviceRadixSort::SortPairs(c->sort_tmp, c->sort_tmp_bytes, c->keys[0], c->keys[1], c->vals[0],
-                                                   c->vals[1], static_cast<int64_t>(F), 0, c->key_bits, c->stream));
-        c->launches += 1 + (c->key_bits + 7) / 8;   // histogram + one onesweep pass per 8 key bits (+ scan, not counted)
-        TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * G * sizeof(uint32_t), c->stream));
-        k_splat_bounds<<<blocks_for((static_cast<long long>(F) + 3) / 4, 256), 256, 0, c->stream>>>(c->keys[1], F, c->seg);
-        if (int r = check_launch(c, "k_splat_bounds")) return r;
-    } else if (c->bands_connected) {
-        TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * G * sizeof(uint32_t), c->stream));   // the other ranks read this table
-    }
+    c->pending_time = time;
+    c->pending_stage = 1;
+    if (int r = queue_splat(c, time, 1)) return r;
+    c->pending = true;
     c->collected = true;
     return TB_OK;
 }
 
 int fold(tb_ctx *c) {
     TB_REQUIRE(c, c->collected, "tb_splat_fold without a preceding tb_splat_collect");
-    const int G = c->W * c->H;
-    if (c->last_frags > 0) {
-        FoldIO io{};
-        io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
-        io.t_begin = 0; io.t_end = G; io.copy_all = 0;
-        TB_CUDA(c, cudaMemsetAsync(c->hot, 0, 2 * sizeof(uint32_t), c->stream));       // [0] count, [1] cursor
-        k_splat_fold<<<blocks_for(G, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
-            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
-        if (int r = check_launch(c, "k_splat_fold")) return r;
-        k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
-            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->hot, c->hot + 2, c->hot + 1);
-        if (int r = check_launch(c, "k_splat_fold_hot")) return r;
-    }
+    if (int r = resolve_pending(c)) return r;          // the split form is not on the single-GPU hot path: check the collect now
+    if (int r = launch_fold(c, c->collect_time)) return r;
     TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
+    if (c->stage_timing) cudaEventRecord(c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots][4], c->stream);
     c->ev_count[1] += 1;
     c->collected = false;
+    return TB_OK;
+}
+
+// tb_splat_flow: collect + fold queued back to back, checked lazily.
+int splat(tb_ctx *c, float time) {
+    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before the flow splat");
+    if (int r = resolve_pending(c)) return r;
+    c->collect_time = time;
+    c->collected = false;
+    c->splat_since_step = true;
+    c->pending_time = time;
+    c->pending_stage = 2;
+    if (int r = queue_splat(c, time, 2)) return r;
+    c->pending = true;
+    c->ev_count[1] += 1;
     return TB_OK;
 }
 
@@ -377,7 +416,6 @@ int fold(tb_ctx *c) {
 // buffers[0]; explicit targets FBO -> no rotation.  `particles` is buffers[1] either way.
 float4 *spawn_out(tb_ctx *c, tb_target target) {
     if (target == TB_TARGET_TARGETS) return c->targets;
-    c->count_valid = false;
     std::swap(c->buf[0], c->buf[1]);
     return c->buf[0];
 }
@@ -398,507 +436,11 @@ int after_targets_write(tb_ctx *c, tb_target target) {
 
 bool tame(float v, float lim) { return std::isfinite(v) && std::fabs(v) < lim; }
 
-}  // namespace
-
-// ------------------------------------------------------------------------------------------------
-// Sharded ring fold over peer memory
-// ------------------------------------------------------------------------------------------------
-namespace {
-
-struct RingHandles {                 // what tb_ring_export hands to the neighbour (3 x 64 bytes + sizes)
-    cudaIpcMemHandle_t flow, inbox, flags;
-    int32_t w, h, chunks, pad;
-};
-
-int ring_release(tb_ctx *c) {
-    if (c->next_inbox) cudaIpcCloseMemHandle(c->next_inbox);
-    if (c->next_flow) cudaIpcCloseMemHandle(c->next_flow);
-    if (c->next_flags) cudaIpcCloseMemHandle(c->next_flags);
-    c->next_inbox = c->next_flow = nullptr;
-    c->next_flags = nullptr;
-    c->ring_connected = false;
-    return TB_OK;
-}
-
-// The ordered fold of a column-sharded run, chunk by chunk:
-//   rank r waits for chunk k of its inbox (rank 0: reads its own grid), folds its fragments onto it and
-//   writes the result straight into rank r+1's inbox over NVLink, then raises that rank's flag;
-//   the last rank's result is final: it goes to its own grid and to rank 0's, and travels on around the
-//   ring (ring_stream) so that every rank ends the step with the same grid.
-// Fold order = rank order = primitive order, so the result equals the single-GPU fold bit for bit.
-int ring_fold(tb_ctx *c) {
-    TB_REQUIRE(c, c->collected, "tb_splat_fold_ring without a preceding tb_splat_collect");
-    TB_REQUIRE(c, c->ring_connected, "tb_ring_connect must be called first");
-    const int G = c->W * c->H, C = c->ring_chunks;
-    const int r = c->ring_rank, P = c->ring_world;
-    const bool first = r == 0, last = r == P - 1;
-    const uint32_t epoch = ++c->ring_epoch;
-    const int per = ((G + C - 1) / C + 127) / 128 * 128;                 // texels per chunk, CTA aligned
-    constexpr int S = tb_ctx::kRingMaxChunks;                              // flag stride: [0,S) inbox ready, [S,2S) final ready
-    uint32_t *in_flag = c->ring_flags, *fin_flag = c->ring_flags + S;
-    TB_CUDA(c, cudaMemsetAsync(c->ring_hot_counts, 0, 2 * tb_ctx::kRingMaxChunks * sizeof(uint32_t), c->stream));   // counts, cursors
-    if (c->last_frags == 0)   // no fragments on this rank: collect() left the segments of an earlier draw behind
-        TB_CUDA(c, cudaMemsetAsync(c->seg, 0, 2 * static_cast<size_t>(G) * sizeof(uint32_t), c->stream));
-    TB_CUDA(c, cudaEventRecord(c->ev_ring_begin, c->stream));
-    TB_CUDA(c, cudaStreamWaitEvent(c->ring_stream, c->ev_ring_begin, 0));
-    // TB_RING_DEBUG=<epoch>: time the phases of that ring fold on every rank (diagnostics, stderr)
-    static const int dbg_epoch = std::getenv("TB_RING_DEBUG") ? std::atoi(std::getenv("TB_RING_DEBUG")) : -1;
-    const bool dbg = static_cast<int>(epoch) == dbg_epoch;
-    static cudaEvent_t dbg_ev[tb_ctx::kRingMaxChunks][5];
-    if (dbg)
-        for (int k = 0; k < C; ++k)
-            for (int j = 0; j < 5; ++j) cudaEventCreate(&dbg_ev[k][j]);
-    for (int k = 0; k < C; ++k) {
-        const int t0 = std::min(G, k * per), t1 = std::min(G, (k + 1) * per);
-        if (t0 >= t1) continue;
-        FoldIO io{};
-        if (dbg) cudaEventRecord(dbg_ev[k][0], c->stream);
-        io.src = first ? c->flow : c->inbox;
-        io.dst = last ? c->flow : c->next_inbox;
-        io.dst2 = (last && P > 1) ? c->next_flow : nullptr;             // rank 0's grid
-        io.t_begin = t0; io.t_end = t1; io.copy_all = 1;
-        if (!first) {
-            k_ring_wait<<<1, 1, 0, c->stream>>>(in_flag + k, epoch);
-            if (int e = check_launch(c, "k_ring_wait")) return e;
-        }
-        if (dbg) cudaEventRecord(dbg_ev[k][1], c->stream);
-        k_splat_fold<<<blocks_for(t1 - t0, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
-            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2,
-            c->last_frags > 0 ? c->hot_threshold : 0xffffffffu);
-        if (int e = check_launch(c, "k_splat_fold")) return e;
-        if (dbg) cudaEventRecord(dbg_ev[k][2], c->stream);
-        k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
-            io, reinterpret_cast<const uint2 *>(c->seg), c->vals[1], c->collect_time, c->ring_hot_counts + k, c->hot + 2,
-            c->ring_hot_counts + tb_ctx::kRingMaxChunks + k);
-        if (int e = check_launch(c, "k_splat_fold_hot")) return e;
-        // chunk k of the next rank's inbox (or, from the last rank, of rank 0's grid) is complete
-        if (dbg) cudaEventRecord(dbg_ev[k][3], c->stream);
-        k_ring_signal<<<1, 1, 0, c->stream>>>(last ? c->next_flags + S + k : c->next_flags + k, epoch);
-        if (int e = check_launch(c, "k_ring_signal")) return e;
-        if (dbg) cudaEventRecord(dbg_ev[k][4], c->stream);
-    }
-    if (dbg) {
-        cudaStreamSynchronize(c->stream);
-        for (int k = 0; k < C; ++k) {
-            float w = 0, m = 0, h = 0, sgl = 0;
-            cudaEventElapsedTime(&w, dbg_ev[k][0], dbg_ev[k][1]);
-            cudaEventElapsedTime(&m, dbg_ev[k][1], dbg_ev[k][2]);
-            cudaEventElapsedTime(&h, dbg_ev[k][2], dbg_ev[k][3]);
-            cudaEventElapsedTime(&sgl, dbg_ev[k][3], dbg_ev[k][4]);
-            std::fprintf(stderr, "[ring dbg] rank %d chunk %d: wait %.0f us, fold %.0f us, hot %.0f us, signal %.0f us (frags %lld)\n",
-                         r, k, w * 1e3f, m * 1e3f, h * 1e3f, sgl * 1e3f, static_cast<long long>(c->last_frags));
-        }
-    }
-    // final chunks travel 0 -> 1 -> ... -> P-2 (the last rank already has them)
-    if (!last) {
-        for (int k = 0; k < C; ++k) {
-            const int t0 = std::min(G, k * per), t1 = std::min(G, (k + 1) * per);
-            if (t0 >= t1) continue;
-            k_ring_wait<<<1, 1, 0, c->ring_stream>>>(fin_flag + k, epoch);
-            if (int e = check_launch(c, "k_ring_wait")) return e;
-            if (r < P - 2) {
-                TB_CUDA(c, cudaMemcpyAsync(c->next_flow + t0, c->flow + t0, static_cast<size_t>(t1 - t0) * sizeof(float4),
-                                           cudaMemcpyDeviceToDevice, c->ring_stream));
-                k_ring_signal<<<1, 1, 0, c->ring_stream>>>(c->next_flags + S + k, epoch);
-                if (int e = check_launch(c, "k_ring_signal")) return e;
-            }
-        }
-        TB_CUDA(c, cudaEventRecord(c->ev_ring_fwd, c->ring_stream));
-        TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_ring_fwd, 0));    // the next integrate reads the final grid
-    }
-    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
-    c->ev_count[1] += 1;
-    c->collected = false;
-    return TB_OK;
-}
+int tiles_release(tb_ctx *) { return TB_OK; }
 
 }  // namespace
 
 extern "C" {
-
-int tb_ring_export(tb_ctx *c, void *out, int64_t n_bytes) {
-    TB_REQUIRE(c, c && out, "null argument");
-    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(RingHandles)), "tb_ring_export: buffer must be tb_ring_handle_bytes() long");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    const size_t G = static_cast<size_t>(c->W) * c->H;
-    if (const char *e = std::getenv("TB_RING_CHUNKS")) c->ring_chunks = std::max(1, std::min<int>(tb_ctx::kRingMaxChunks, std::atoi(e)));
-    else c->ring_chunks = 0;      // chosen from the world size in tb_ring_connect
-    const int C = tb_ctx::kRingMaxChunks;
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
-    ring_release(c);
-    if (c->inbox) cudaFree(c->inbox);
-    if (c->ring_flags) cudaFree(c->ring_flags);
-    if (c->ring_hot_counts) cudaFree(c->ring_hot_counts);
-    c->inbox = nullptr; c->ring_flags = nullptr; c->ring_hot_counts = nullptr;
-    TB_CUDA(c, cudaMalloc(&c->inbox, G * sizeof(float4)));
-    TB_CUDA(c, cudaMalloc(&c->ring_flags, 2 * C * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->ring_hot_counts, 2 * C * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMemset(c->ring_flags, 0, 2 * C * sizeof(uint32_t)));
-    c->ring_epoch = 0;
-    if (!c->ring_stream) {
-        TB_CUDA(c, cudaStreamCreateWithFlags(&c->ring_stream, cudaStreamNonBlocking));
-        TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_ring_fwd, cudaEventDisableTiming));
-        TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_ring_begin, cudaEventDisableTiming));
-    }
-    RingHandles hnd{};
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flow, c->flow));
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.inbox, c->inbox));
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flags, c->ring_flags));
-    hnd.w = c->W; hnd.h = c->H; hnd.chunks = c->ring_chunks;
-    std::memcpy(out, &hnd, sizeof(hnd));
-    return TB_OK;
-}
-
-int64_t tb_ring_handle_bytes(void) { return static_cast<int64_t>(sizeof(RingHandles)); }
-
-int tb_ring_connect(tb_ctx *c, int32_t rank, int32_t world, const void *next_rank_handles, int64_t n_bytes) {
-    TB_REQUIRE(c, c && next_rank_handles, "null argument");
-    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(RingHandles)), "tb_ring_connect: bad handle size");
-    TB_REQUIRE(c, world >= 2 && rank >= 0 && rank < world, "tb_ring_connect: bad rank/world");
-    TB_REQUIRE(c, c->inbox != nullptr, "tb_ring_export must be called before tb_ring_connect");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    RingHandles hnd;
-    std::memcpy(&hnd, next_rank_handles, sizeof(hnd));
-    TB_REQUIRE(c, hnd.w == c->W && hnd.h == c->H && hnd.chunks == c->ring_chunks, "tb_ring_connect: the next rank's flow grid has another shape");
-    // Measured on 8xB200 (profiles/r01_multi_gpu.txt): every chunk adds the tail of its own hot texels, so few
-    // chunks win on short rings and about world/2 on long ones.
-    if (c->ring_chunks == 0) c->ring_chunks = std::max(1, world / 2);
-    ring_release(c);
-    TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_flow), hnd.flow, cudaIpcMemLazyEnablePeerAccess));
-    TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_inbox), hnd.inbox, cudaIpcMemLazyEnablePeerAccess));
-    TB_CUDA(c, cudaIpcOpenMemHandle(reinterpret_cast<void **>(&c->next_flags), hnd.flags, cudaIpcMemLazyEnablePeerAccess));
-    c->ring_rank = rank; c->ring_world = world;
-    c->ring_connected = true;
-    // a rank waiting for its predecessor's grid has idle SMs: let the next step's noise run there
-    c->overlap = true;
-    return TB_OK;
-}
-
-}  // extern "C"
-
-// ------------------------------------------------------------------------------------------------
-// Band fold over peer memory: all ranks fold in parallel, each its own tiles of the grid
-// ------------------------------------------------------------------------------------------------
-namespace {
-
-struct BandHandles {                 // what tb_bands_export hands to every other rank
-    cudaIpcMemHandle_t seg, merged, dst, flow, flags;
-    int32_t w, h;
-    uint32_t frag_cap, pad;
-};
-
-int bands_release(tb_ctx *c) {
-    for (int j = 0; j < kMaxBandRanks; ++j) {
-        if (j != c->bands_rank || !c->bands_connected) {
-            if (c->band_src.seg[j]) cudaIpcCloseMemHandle(const_cast<uint2 *>(c->band_src.seg[j]));
-            if (c->band_sinks.merged[j]) cudaIpcCloseMemHandle(c->band_sinks.merged[j]);
-            if (c->band_sinks.dst[j]) cudaIpcCloseMemHandle(c->band_sinks.dst[j]);
-            if (c->band_peers.flow[j]) cudaIpcCloseMemHandle(c->band_peers.flow[j]);
-            if (c->band_peers.flags[j]) cudaIpcCloseMemHandle(c->band_peers.flags[j]);
-        }
-        c->band_src.seg[j] = nullptr;
-        c->band_sinks.merged[j] = nullptr; c->band_sinks.dst[j] = nullptr;
-        c->band_peers.flow[j] = nullptr; c->band_peers.flags[j] = nullptr;
-    }
-    cudaFree(c->bands_len); cudaFree(c->bands_off); cudaFree(c->bands_seg); cudaFree(c->bands_scan_tmp);
-    c->bands_len = c->bands_off = c->bands_seg = nullptr;
-    c->bands_scan_tmp = nullptr;
-    c->bands_connected = false;
-    c->frag_fixed = false;
-    return TB_OK;
-}
-
-// Every rank folds the tiles it owns (tile % world == rank).  The fragments of those tiles are first brought
-// together in one local array -- per texel the sources side by side in rank order = column order = primitive
-// order, and inside a source the stable sort kept the draw order -- then the local fold runs on it.
-// The result equals the single-GPU fold bit for bit, and no rank waits for another rank's fold.
-int bands_fold(tb_ctx *c) {
-    TB_REQUIRE(c, c->collected, "tb_splat_fold_bands without a preceding tb_splat_collect");
-    TB_REQUIRE(c, c->bands_connected, "tb_bands_connect must be called first");
-    const int G = c->W * c->H, P = c->bands_world, r = c->bands_rank, mine = c->bands_mine;
-    if (c->bands_epoch > 0) {                        // the previous fold's overflow flag has long arrived
-        TB_CUDA(c, cudaEventSynchronize(c->ev_bands));
-        if (*c->h_bands_overflow)
-            return fail(c, TB_ERR_UNSUPPORTED, "flow splat (bands): the fragments of this rank's tiles exceeded the reserve of " +
-                        std::to_string(c->frag_cap) + "; export with a larger reserve (TB_BANDS_RESERVE) and reconnect");
-    }
-    const uint32_t epoch = ++c->bands_epoch;
-    // TB_RING_DEBUG=<epoch>: time the phases of that fold on every rank (diagnostics, stderr)
-    static const int dbg_epoch = std::getenv("TB_RING_DEBUG") ? std::atoi(std::getenv("TB_RING_DEBUG")) : -1;
-    const bool dbg = static_cast<int>(epoch) == dbg_epoch;
-    static cudaEvent_t dbg_ev[12];
-    int dbg_n = 0;
-    auto mark = [&]() { if (dbg) { cudaEventCreate(&dbg_ev[dbg_n]); cudaEventRecord(dbg_ev[dbg_n++], c->stream); } };
-    auto barrier = [&](int phase) -> int {
-        k_bands_barrier<<<1, 32, 0, c->stream>>>(c->band_peers, c->bands_flags, phase, epoch);
-        return check_launch(c, "k_bands_barrier");
-    };
-    mark();
-    // barrier 0: every rank's sorted fragments and segment table of this step are in place (and every rank is done
-    // with the merged array and the grid of the previous step)
-    if (int e = barrier(0)) return e;
-    mark();
-    const long long warps = static_cast<long long>(mine) * P;
-    const int n_seg = mine * 32 * P + 1;
-    k_bands_lengths<<<blocks_for(warps * 32, 256), 256, 0, c->stream>>>(c->band_src, P, r, mine, G, c->bands_len);
-    if (int e = check_launch(c, "k_bands_lengths")) return e;
-    TB_CUDA(c, cub::DeviceScan::ExclusiveSum(c->bands_scan_tmp, c->bands_scan_bytes, c->bands_len, c->bands_off, n_seg, c->stream));
-    c->launches += 2;
-    k_bands_offsets<<<blocks_for(warps * 32, 256), 256, 0, c->stream>>>(c->band_sinks, P, r, mine, G, c->bands_off, c->frag_cap,
-                                                                           c->bands_seg, c->bands_overflow);
-    if (int e = check_launch(c, "k_bands_offsets")) return e;
-    TB_CUDA(c, cudaMemcpyAsync(c->h_bands_overflow, c->bands_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaEventRecord(c->ev_bands, c->stream));
-    mark();
-    // barrier 1: every owner has told every source where its segments go
-    if (int e = barrier(1)) return e;
-    mark();
-    if (c->last_frags > 0) {
-        const uint32_t F = static_cast<uint32_t>(c->last_frags);
-        k_bands_push<<<blocks_for(F, 256), 256, 0, c->stream>>>(c->keys[1], c->vals[1], F, reinterpret_cast<const uint2 *>(c->seg),
-                                                                  c->bands_dst, c->band_sinks, P, c->frag_cap);
-        if (int e = check_launch(c, "k_bands_push")) return e;
-    }
-    mark();
-    // barrier 2: every source's fragments have landed in the owners' merged arrays
-    if (int e = barrier(2)) return e;
-    mark();
-    FoldIO io{};
-    io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
-    io.t_begin = 0; io.t_end = G; io.copy_all = 0;
-    io.tile_first = r; io.tile_stride = P;
-    TB_CUDA(c, cudaMemsetAsync(c->hot, 0, 2 * sizeof(uint32_t), c->stream));       // [0] count, [1] cursor
-    k_splat_fold<<<blocks_for(mine, kFoldWarps), kFoldWarps * 32, 0, c->stream>>>(
-        io, reinterpret_cast<const uint2 *>(c->bands_seg), c->vals[0], c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
-    if (int e = check_launch(c, "k_splat_fold")) return e;
-    k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
-        io, reinterpret_cast<const uint2 *>(c->bands_seg), c->vals[0], c->collect_time, c->hot, c->hot + 2, c->hot + 1);
-    if (int e = check_launch(c, "k_splat_fold_hot")) return e;
-    mark();
-    k_bands_publish<<<blocks_for(static_cast<long long>(mine) * 32, 256), 256, 0, c->stream>>>(c->flow, c->band_peers, G);
-    if (int e = check_launch(c, "k_bands_publish")) return e;
-    mark();
-    // barrier 3: every tile has landed in every grid
-    if (int e = barrier(3)) return e;
-    mark();
-    if (dbg) {
-        cudaStreamSynchronize(c->stream);
-        float ms[8] = {};
-        for (int k = 0; k < 8; ++k) cudaEventElapsedTime(&ms[k], dbg_ev[k], dbg_ev[k + 1]);
-        std::fprintf(stderr, "[bands dbg] rank %d: barrier0 %.0f us, lengths+scan+offsets %.0f us, barrier1 %.0f us, push %.0f us, "
-                             "barrier2 %.0f us, fold+hot %.0f us, publish %.0f us, barrier3 %.0f us (own frags %lld)\n",
-                     r, 1e3 * ms[0], 1e3 * ms[1], 1e3 * ms[2], 1e3 * ms[3], 1e3 * ms[4], 1e3 * ms[5], 1e3 * ms[6], 1e3 * ms[7],
-                     static_cast<long long>(c->last_frags));
-        for (int k = 0; k < 9; ++k) cudaEventDestroy(dbg_ev[k]);
-    }
-    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
-    c->ev_count[1] += 1;
-    c->collected = false;
-    return TB_OK;
-}
-
-}  // namespace
-
-extern "C" {
-
-int64_t tb_bands_handle_bytes(void) { return static_cast<int64_t>(sizeof(BandHandles)); }
-
-int tb_bands_export(tb_ctx *c, int64_t reserve_fragments, void *out, int64_t n_bytes) {
-    TB_REQUIRE(c, c && out, "null argument");
-    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(BandHandles)), "tb_bands_export: buffer must be tb_bands_handle_bytes() long");
-    TB_REQUIRE(c, reserve_fragments >= 0 && reserve_fragments < (1ll << 31), "tb_bands_export: reserve out of range");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
-    bands_release(c);
-    if (int e = ensure_frag_cap(c, std::max<uint64_t>(static_cast<uint64_t>(reserve_fragments), 1u << 16))) return e;
-    if (!c->bands_flags) {
-        TB_CUDA(c, cudaMalloc(&c->bands_flags, kBandPhases * kMaxBandRanks * sizeof(uint32_t)));
-        TB_CUDA(c, cudaMalloc(&c->bands_overflow, sizeof(int)));
-        TB_CUDA(c, cudaMallocHost(&c->h_bands_overflow, sizeof(int)));
-        TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_bands, cudaEventDisableTiming));
-    }
-    TB_CUDA(c, cudaMemset(c->bands_overflow, 0, sizeof(int)));
-    *c->h_bands_overflow = 0;
-    TB_CUDA(c, cudaMemset(c->bands_flags, 0, kBandPhases * kMaxBandRanks * sizeof(uint32_t)));
-    c->bands_epoch = 0;
-    if (c->bands_dst) cudaFree(c->bands_dst);
-    c->bands_dst = nullptr;
-    TB_CUDA(c, cudaMalloc(&c->bands_dst, static_cast<size_t>(c->W) * c->H * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMemset(c->bands_dst, 0, static_cast<size_t>(c->W) * c->H * sizeof(uint32_t)));
-    BandHandles hnd{};
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.seg, c->seg));
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.merged, c->vals[0]));
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.dst, c->bands_dst));
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flow, c->flow));
-    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flags, c->bands_flags));
-    hnd.w = c->W; hnd.h = c->H; hnd.frag_cap = c->frag_cap;
-    std::memcpy(out, &hnd, sizeof(hnd));
-    c->frag_fixed = true;
-    return TB_OK;
-}
-
-int tb_bands_connect(tb_ctx *c, int32_t rank, int32_t world, const void *all_handles, int64_t n_bytes) {
-    TB_REQUIRE(c, c && all_handles, "null argument");
-    TB_REQUIRE(c, world >= 2 && world <= kMaxBandRanks && rank >= 0 && rank < world, "tb_bands_connect: bad rank/world");
-    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(BandHandles)) * world, "tb_bands_connect: expected world x tb_bands_handle_bytes()");
-    TB_REQUIRE(c, c->frag_fixed && c->bands_flags, "tb_bands_export must be called before tb_bands_connect");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    const bool fixed = c->frag_fixed;
-    bands_release(c);
-    c->frag_fixed = fixed;
-    c->bands_rank = rank; c->bands_world = world;
-    c->bands_connected = true;                 // from here on bands_release skips this rank's own slots
-    const auto *h = static_cast<const unsigned char *>(all_handles);
-    for (int j = 0; j < world; ++j) {
-        if (j == rank) {
-            c->band_src.seg[j] = reinterpret_cast<const uint2 *>(c->seg);
-            c->band_sinks.merged[j] = c->vals[0];
-            c->band_sinks.dst[j] = c->bands_dst;
-            c->band_peers.flow[j] = c->flow;
-            c->band_peers.flags[j] = c->bands_flags;
-            continue;
-        }
-        BandHandles hnd;
-        std::memcpy(&hnd, h + sizeof(BandHandles) * j, sizeof(hnd));
-        if (hnd.w != c->W || hnd.h != c->H) {
-            bands_release(c);
-            return fail(c, TB_ERR_INVALID, "tendrils-b200: tb_bands_connect: rank " + std::to_string(j) + " has another flow grid shape");
-        }
-        void *p[5] = {};
-        const cudaIpcMemHandle_t *hs[5] = {&hnd.seg, &hnd.merged, &hnd.dst, &hnd.flow, &hnd.flags};
-        for (int k = 0; k < 5; ++k) {
-            cudaError_t e = cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess);
-            // keep what was opened so far where bands_release will find it
-            if (k == 0) c->band_src.seg[j] = static_cast<const uint2 *>(p[0]);
-            if (k == 1) c->band_sinks.merged[j] = static_cast<FragVal *>(p[1]);
-            if (k == 2) c->band_sinks.dst[j] = static_cast<uint32_t *>(p[2]);
-            if (k == 3) c->band_peers.flow[j] = static_cast<float4 *>(p[3]);
-            if (k == 4) c->band_peers.flags[j] = static_cast<uint32_t *>(p[4]);
-            if (e != cudaSuccess) {
-                bands_release(c);
-                return fail(c, TB_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(j) + "): " + cudaGetErrorString(e));
-            }
-        }
-    }
-    c->band_peers.n = world; c->band_peers.me = rank;
-    // barriers, NVLink-bound pushes and latency-bound blend chains leave SMs idle: let the next step's noise run there
-    c->overlap = true;
-    // scratch of the owner side: lengths / offsets per (local texel, source), the merged segment table
-    const size_t G = static_cast<size_t>(c->W) * c->H;
-    const int tiles = static_cast<int>((G + 31) / 32);
-    c->bands_mine = (tiles - rank + world - 1) / world;
-    const size_t n_seg = static_cast<size_t>(c->bands_mine) * 32 * world + 1;
-    TB_CUDA(c, cudaMalloc(&c->bands_len, n_seg * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->bands_off, n_seg * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->bands_seg, 2 * G * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMemset(c->bands_len, 0, n_seg * sizeof(uint32_t)));
-    c->bands_scan_bytes = 0;
-    TB_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, c->bands_scan_bytes, c->bands_len, c->bands_off, static_cast<int>(n_seg), c->stream));
-    TB_CUDA(c, cudaMalloc(&c->bands_scan_tmp, std::max<size_t>(c->bands_scan_bytes, 16)));
-    return TB_OK;
-}
-
-int tb_splat_fold_bands(tb_ctx *c) {
-    TB_REQUIRE(c, c, "null context");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    return bands_fold(c);
-}
-
-}  // extern "C"
-
-extern "C" {
-
-// ---- band exchange ("a2a"): every rank folds ONE band of the grid with the fragments of ALL ranks -------------
-int tb_splat_band_offsets(tb_ctx *c, int32_t n_bands, int32_t band_texels, int64_t *host_offsets) {
-    TB_REQUIRE(c, c && host_offsets, "null argument");
-    TB_REQUIRE(c, c->collected, "tb_splat_band_offsets without a preceding tb_splat_collect");
-    TB_REQUIRE(c, n_bands >= 1 && n_bands <= 64, "bad band count");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    const uint32_t F = static_cast<uint32_t>(c->last_frags);
-    uint32_t *d_out = c->hot;                                  // scratch: free between collect and fold
-    if (F > 0) {
-        k_band_offsets<<<1, 128, 0, c->stream>>>(c->keys[1], F, band_texels, n_bands, d_out);
-        if (int r = check_launch(c, "k_band_offsets")) return r;
-        uint32_t tmp[65];
-        TB_CUDA(c, cudaMemcpyAsync(tmp, d_out, (n_bands + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        TB_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (int b = 0; b <= n_bands; ++b) host_offsets[b] = tmp[b];
-    } else {
-        for (int b = 0; b <= n_bands; ++b) host_offsets[b] = 0;
-    }
-    return TB_OK;
-}
-
-// pointers for the exchange: send = the sorted fragments, recv = the (now free) pre-sort buffers, grown if needed
-int tb_splat_exchange_buffers(tb_ctx *c, int64_t recv_items, void **send_keys, void **send_vals, void **recv_keys,
-                              void **recv_vals, int32_t *val_bytes) {
-    TB_REQUIRE(c, c && send_keys && send_vals && recv_keys && recv_vals && val_bytes, "null argument");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    if (static_cast<uint64_t>(recv_items) > c->frag_cap) {
-        // growing reallocates all four buffers: keep the sorted fragments
-        const uint32_t F = static_cast<uint32_t>(c->last_frags);
-        uint32_t *k_old = nullptr; FragVal *v_old = nullptr;
-        TB_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (F > 0) {
-            TB_CUDA(c, cudaMalloc(&k_old, F * sizeof(uint32_t)));
-            TB_CUDA(c, cudaMalloc(&v_old, F * sizeof(FragVal)));
-            TB_CUDA(c, cudaMemcpy(k_old, c->keys[1], F * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
-            TB_CUDA(c, cudaMemcpy(v_old, c->vals[1], F * sizeof(FragVal), cudaMemcpyDeviceToDevice));
-        }
-        if (int r = ensure_frag_cap(c, static_cast<uint64_t>(recv_items))) return r;
-        if (F > 0) {
-            TB_CUDA(c, cudaMemcpy(c->keys[1], k_old, F * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
-            TB_CUDA(c, cudaMemcpy(c->vals[1], v_old, F * sizeof(FragVal), cudaMemcpyDeviceToDevice));
-            cudaFree(k_old); cudaFree(v_old);
-        }
-    }
-    *send_keys = c->keys[1]; *send_vals = c->vals[1];
-    *recv_keys = c->keys[0]; *recv_vals = c->vals[0];
-    *val_bytes = static_cast<int32_t>(sizeof(FragVal));
-    return TB_OK;
-}
-
-// blend one received piece (fragments of ONE source rank, sorted, in draw order) onto texels [t_begin, t_end)
-int tb_splat_fold_piece(tb_ctx *c, int64_t piece_offset, int64_t piece_items, int32_t t_begin, int32_t t_end) {
-    TB_REQUIRE(c, c, "null context");
-    TB_REQUIRE(c, t_begin >= 0 && t_begin <= t_end && t_end <= c->W * c->H, "bad texel range");
-    TB_REQUIRE(c, piece_offset >= 0 && piece_items >= 0 && piece_offset + piece_items <= static_cast<int64_t>(c->frag_cap), "bad piece");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    if (piece_items == 0 || t_begin == t_end) return TB_OK;
-    const uint32_t n = static_cast<uint32_t>(piece_items);
-    const uint32_t *keys = c->keys[0] + piece_offset;
-    const FragVal *vals = c->vals[0] + piece_offset;
-    TB_CUDA(c, cudaMemsetAsync(c->seg + 2ull * t_begin, 0, 2ull * (t_end - t_begin) * sizeof(uint32_t), c->stream));
-    k_splat_bounds<<<blocks_for((static_cast<long long>(n) + 3) / 4, 256), 256, 0, c->stream>>>(keys, n, c->seg);
-    if (int r = check_launch(c, "k_splat_bounds")) return r;
-    FoldIO io{};
-    io.src = c->flow; io.dst = c->flow; io.dst2 = nullptr;
-    io.t_begin = t_begin; io.t_end = t_end; io.copy_all = 0;
-    TB_CUDA(c, cudaMemsetAsync(c->hot, 0, 2 * sizeof(uint32_t), c->stream));
-    k_splat_fold<<<blocks_for(t_end - t_begin, kFoldWarps * 32), kFoldWarps * 32, 0, c->stream>>>(
-        io, reinterpret_cast<const uint2 *>(c->seg), vals, c->collect_time, c->hot, c->hot + 2, c->hot_threshold);
-    if (int r = check_launch(c, "k_splat_fold")) return r;
-    k_splat_fold_hot<<<c->n_sms * 4, kHotWarps * 32, 0, c->stream>>>(
-        io, reinterpret_cast<const uint2 *>(c->seg), vals, c->collect_time, c->hot, c->hot + 2, c->hot + 1);
-    if (int r = check_launch(c, "k_splat_fold_hot")) return r;
-    return TB_OK;
-}
-
-// closes the splat timing span of a band-exchange draw and marks the collect as consumed
-int tb_splat_exchange_done(tb_ctx *c) {
-    TB_REQUIRE(c, c, "null context");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    TB_CUDA(c, cudaEventRecord(c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots][1], c->stream));
-    c->ev_count[1] += 1;
-    c->collected = false;
-    return TB_OK;
-}
-
-int tb_splat_fold_ring(tb_ctx *c) {
-    TB_REQUIRE(c, c, "null context");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    return ring_fold(c);
-}
 
 int tb_abi_version(void) { return TB_ABI_VERSION; }
 
@@ -954,7 +496,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     // Opt-in (TB_OVERLAP=1): measured +4.7 % step throughput at cfg3, but the low-priority noise launch is
     // time-sliced under the sort, which makes its own duration meaningless as a roofline input.
     c->overlap = std::getenv("TB_OVERLAP") != nullptr;
-    if (const char *e = std::getenv("TB_FOLD_HOT")) c->hot_threshold = static_cast<uint32_t>(std::max(1, std::atoi(e)));
+    if (const char *e = std::getenv("TB_HOT_BIN")) c->hot_bin = static_cast<uint32_t>(std::max(1, std::atoi(e)));
+    c->stage_timing = std::getenv("TB_STAGE_TIMING") != nullptr;
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));
@@ -966,8 +509,16 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     TB_TRY(cudaMemsetAsync(c->buf[1], 0, bytes, c->stream));
     TB_TRY(cudaMalloc(&c->d_flag, sizeof(int)));
     TB_TRY(cudaMallocHost(&c->h_flag, sizeof(int)));
-    TB_TRY(cudaMallocHost(&c->h_total, sizeof(uint32_t)));
-    TB_TRY(cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming));
+    TB_TRY(cudaMallocHost(&c->h_plan, sizeof(PlanOut)));
+    std::memset(c->h_plan, 0, sizeof(PlanOut));
+    TB_TRY(cudaMalloc(&c->d_plan, sizeof(PlanOut)));
+    TB_TRY(cudaMemsetAsync(c->d_plan, 0, sizeof(PlanOut), c->stream));
+    TB_TRY(cudaMalloc(&c->tickets, 8 * sizeof(uint32_t)));
+    TB_TRY(cudaMemsetAsync(c->tickets, 0, 8 * sizeof(uint32_t), c->stream));
+    TB_TRY(cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming));
+    if (c->stage_timing)
+        for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
+            for (int j = 0; j < 5; ++j) TB_TRY(cudaEventCreate(&c->ev_stage[i][j]));
     for (int k = 0; k < 3; ++k)
         for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
             for (int j = 0; j < 2; ++j) TB_TRY(cudaEventCreate(&c->ev_ring[k][i][j]));
@@ -978,41 +529,18 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
         TB_TRY(cudaMemcpyAsync(c->pairs, pairs.data(), pairs.size() * sizeof(PairEntry), cudaMemcpyHostToDevice, c->stream));
         TB_TRY(cudaStreamSynchronize(c->stream));
     }
-    {
-        // Row -> pair map of the count fused into k_integrate.  A pair rides there if both its vertices read ONE texel row
-        // (one particle's previous and current state) and no earlier pair has claimed that row: the D6 table of many
-        // non-power-of-two heights draws some rows twice (e.g. PH = 47: pairs 0 and 1 both draw row 0), and tall
-        // textures have a few pairs that join two different rows (3 of 4104 at PH = 8192).
-        std::vector<int32_t> rp(static_cast<size_t>(PH), -1), odd;
-        for (size_t k = 0; k < pairs.size(); ++k) {
-            const int ra = pairs[k].row_a & 0x7fffffff, rb = pairs[k].row_b & 0x7fffffff;
-            const bool ca = pairs[k].row_a < 0, cb = pairs[k].row_b < 0;
-            const bool rides = ra == rb && ca != cb && k < (1u << 30) && rp[static_cast<size_t>(ra)] == -1;
-            if (rides) rp[static_cast<size_t>(ra)] = static_cast<int32_t>(static_cast<uint32_t>(k) | ((cb ? 1u : 2u) << 30));   // 1: prev->cur, 2: cur->prev
-            else odd.push_back(static_cast<int32_t>(k));
-        }
-        c->fuse_count = !pairs.empty() && odd.empty();
-        // experimental, off unless TB_FUSE_PARTIAL is set (not yet run on a GPU): ride anyway when only a few pairs cannot
-        c->fuse_partial = std::getenv("TB_FUSE_PARTIAL") != nullptr && !pairs.empty() && !odd.empty() && odd.size() * 16 <= pairs.size();
-        c->n_odd = static_cast<int>(odd.size());
-        if (c->fuse_partial) {
-            TB_TRY(cudaMalloc(&c->odd_pairs, odd.size() * sizeof(int32_t)));
-            TB_TRY(cudaMemcpyAsync(c->odd_pairs, odd.data(), odd.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        }
-        TB_TRY(cudaMalloc(&c->row_pair, rp.size() * sizeof(int32_t)));
-        TB_TRY(cudaMemcpyAsync(c->row_pair, rp.data(), rp.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        TB_TRY(cudaStreamSynchronize(c->stream));
-    }
     c->n_prims = static_cast<long long>(col1 - col0) * c->n_pairs;
     if (c->n_prims >= (1LL << 31)) { c->err = "tendrils-b200: too many primitives per context"; return bail(TB_ERR_INVALID); }
-    TB_TRY(cudaMalloc(&c->prim_off, (c->n_prims + 1) * sizeof(uint32_t)));
-    TB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, c->scan_tmp_bytes, c->prim_off, c->prim_off,
-                                         static_cast<int>(c->n_prims + 1), c->stream));
-    TB_TRY(cudaMalloc(&c->scan_tmp, c->scan_tmp_bytes));
+    // slabs of consecutive primitives: the unit of work of the count and emit passes (about eight per SM)
+    {
+        const long long want = (c->n_prims + 8LL * c->n_sms - 1) / (8LL * c->n_sms);
+        c->slab_prims = static_cast<int>(std::max<long long>(kEmitThreads, (want + kEmitThreads - 1) / kEmitThreads * kEmitThreads));
+        c->n_slabs = static_cast<int>((c->n_prims + c->slab_prims - 1) / c->slab_prims);
+    }
 #undef TB_TRY
     const int fw = cfg->flow_w > 0 ? cfg->flow_w : 1, fh = cfg->flow_h > 0 ? cfg->flow_h : 1;
     if (int r = alloc_flow(c, fw, fh)) return bail(r);
-    if (int r = ensure_frag_cap(c, static_cast<uint64_t>(c->n_prims) * 2)) return bail(r);
+    if (int r = ensure_bin_cap(c, static_cast<uint64_t>(c->n_prims) * 6)) return bail(r);
     if (int r = tb_reset(c)) return bail(r);
     *out = c;
     return TB_OK;
@@ -1023,28 +551,23 @@ int tb_destroy(tb_ctx *c) {
     cudaSetDevice(c->device);
     if (c->side) cudaStreamSynchronize(c->side);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    tiles_release(c);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
     cudaFree(c->frames);
     cudaFree(c->line_attr); cudaFree(c->line_verts); cudaFree(c->line_bbox);
-    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->prim_off); cudaFree(c->row_pair); cudaFree(c->odd_pairs);
-    cudaFree(c->scan_tmp); cudaFree(c->sort_tmp); cudaFree(c->seg); cudaFree(c->hot); cudaFree(c->d_flag);
-    for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); }
+    cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->d_flag);
+    cudaFree(c->slab_hist); cudaFree(c->tile_total); cudaFree(c->bin_off); cudaFree(c->tickets); cudaFree(c->items);
+    cudaFree(c->d_plan); cudaFree(c->bins);
     if (c->h_flag) cudaFreeHost(c->h_flag);
-    if (c->h_total) cudaFreeHost(c->h_total);
-    if (c->ev_total) cudaEventDestroy(c->ev_total);
+    if (c->h_plan) cudaFreeHost(c->h_plan);
+    if (c->ev_plan) cudaEventDestroy(c->ev_plan);
     for (int k = 0; k < 3; ++k)
         for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
             for (int j = 0; j < 2; ++j)
                 if (c->ev_ring[k][i][j]) cudaEventDestroy(c->ev_ring[k][i][j]);
-    ring_release(c);
-    bands_release(c);
-    cudaFree(c->bands_flags); cudaFree(c->bands_overflow); cudaFree(c->bands_dst);
-    if (c->h_bands_overflow) cudaFreeHost(c->h_bands_overflow);
-    if (c->ev_bands) cudaEventDestroy(c->ev_bands);
-    cudaFree(c->inbox); cudaFree(c->ring_flags); cudaFree(c->ring_hot_counts);
-    if (c->ring_stream) { cudaStreamSynchronize(c->ring_stream); cudaStreamDestroy(c->ring_stream); }
-    if (c->ev_ring_fwd) cudaEventDestroy(c->ev_ring_fwd);
-    if (c->ev_ring_begin) cudaEventDestroy(c->ev_ring_begin);
+    for (int i = 0; i < tb_ctx::kTimingSlots; ++i)
+        for (int j = 0; j < 5; ++j)
+            if (c->ev_stage[i][j]) cudaEventDestroy(c->ev_stage[i][j]);
     if (c->ev_state) cudaEventDestroy(c->ev_state);
     if (c->ev_noise) cudaEventDestroy(c->ev_noise);
     if (c->side) cudaStreamDestroy(c->side);
@@ -1064,6 +587,7 @@ int tb_set_state(tb_ctx *c, const tb_state *s) {
 int tb_resize_flow(tb_ctx *c, int32_t w, int32_t h) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return alloc_flow(c, w, h);
 }
@@ -1071,6 +595,7 @@ int tb_resize_flow(tb_ctx *c, int32_t w, int32_t h) {
 int tb_clear_flow(tb_ctx *c) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     TB_CUDA(c, cudaMemsetAsync(c->flow, 0, static_cast<size_t>(c->W) * c->H * sizeof(float4), c->stream));
     return TB_OK;
 }
@@ -1079,6 +604,7 @@ int tb_step(tb_ctx *c, float time, float dt) {
     TB_REQUIRE(c, c, "null context");
     TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_step");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     std::swap(c->buf[0], c->buf[1]);                       // utils.step(buffers), src/particles.js:128
     const tb_state &S = c->state;
     IntegrateArgs A{};
@@ -1107,12 +633,6 @@ int tb_step(tb_ctx *c, float time, float dt) {
     A.packed_noise = scalar_noise ? 0 : 1;
     A.pk.one = 1.0f; A.pk.neg_one = -1.0f; A.pk.neg_zero = -0.0f;
     A.wander = c->wander;
-    const bool fuse = (c->fuse_count || c->fuse_partial) && c->n_prims > 0;
-    A.row_pair = c->row_pair;
-    A.prim_off = fuse ? c->prim_off : nullptr;
-    A.n_pairs = c->n_pairs;
-    c->count_valid = false;
-    if (fuse) TB_CUDA(c, cudaMemsetAsync(c->prim_off, 0, (c->n_prims + 1) * sizeof(uint32_t), c->stream));
     const dim3 grid(blocks_for(c->PH, 256), static_cast<unsigned>(A.cols));
     if (A.use_noise && c->overlap && c->splat_since_step) {
         // The noise does not read the flow grid: evaluate it on the low-priority side stream, where it
@@ -1139,19 +659,6 @@ int tb_step(tb_ctx *c, float time, float dt) {
     TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     c->ev_count[0] += 1;
     c->splat_since_step = false;
-    if (fuse && c->fuse_partial) {          // the pairs that could not ride: the state buffers are final on this stream
-        const SplatArgs SA = splat_args(c);
-        k_splat_count_odd<<<blocks_for(static_cast<long long>(SA.cols) * c->n_odd, 256), 256, 0, c->stream>>>(SA, c->odd_pairs, c->n_odd);
-        if (int r = check_launch(c, "k_splat_count_odd")) return r;
-    }
-    if (fuse) {
-        // the scan and the 4-byte total travel to the host now, so that the next tb_splat_flow finds the
-        // fragment count waiting instead of stalling the GPU on a round trip
-        if (int r = scan_counts(c)) return r;
-        c->count_valid = true;
-        c->count_wh[0] = c->W; c->count_wh[1] = c->H;
-        c->count_vs[0] = S.viewSize[0]; c->count_vs[1] = S.viewSize[1];
-    }
     return TB_OK;
 }
 
@@ -1170,14 +677,13 @@ int tb_splat_fold(tb_ctx *c) {
 int tb_splat_flow(tb_ctx *c, float time) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
-    if (int r = collect(c, time)) return r;
-    return fold(c);
+    return splat(c, time);
 }
 
 int tb_reset(tb_ctx *c) {
     TB_REQUIRE(c, c, "null context");
-    c->count_valid = false;
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     for (int b = 0; b < 2; ++b) {
         k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(c->buf[b], c->n_local);
         if (int r = check_launch(c, "k_spawn_init")) return r;
@@ -1189,6 +695,7 @@ int tb_reset(tb_ctx *c) {
 int tb_spawn_init(tb_ctx *c, tb_target target) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     float4 *out = spawn_out(c, target);
     k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(out, c->n_local);
     if (int r = check_launch(c, "k_spawn_init")) return r;
@@ -1198,6 +705,7 @@ int tb_spawn_init(tb_ctx *c, tb_target target) {
 int tb_spawn_ball(tb_ctx *c, float radius, float speed, tb_target target) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     SpawnArgs A{};
     A.out = spawn_out(c, target);
     A.PW = c->PW; A.PH = c->PH;
@@ -1213,6 +721,7 @@ int tb_set_spawn_image(tb_ctx *c, const float *rgba, int32_t w, int32_t h) {
     TB_REQUIRE(c, c && rgba, "null argument");
     TB_REQUIRE(c, w >= 1 && h >= 1, "gl-texture2d: Texture dimensions are out of bounds");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     const size_t need = static_cast<size_t>(w) * h;
     if (need > c->image_cap) {
         TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1232,6 +741,7 @@ int tb_spawn_pixels(tb_ctx *c, const tb_pixel_spawner *params, tb_spawn_variant 
     TB_REQUIRE(c, c && params, "null argument");
     TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_spawn_pixels");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     SpawnArgs A{};
     A.U = *params;
     A.PW = c->PW; A.PH = c->PH;
@@ -1290,10 +800,10 @@ static int buffer_of(tb_ctx *c, tb_buffer which, float4 **ptr, int64_t *n_floats
 int tb_upload(tb_ctx *c, tb_buffer which, const float *host, int64_t n_floats) {
     TB_REQUIRE(c, c && host, "null argument");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     float4 *dst; int64_t n;
     if (int r = buffer_of(c, which, &dst, &n)) return r;
     TB_REQUIRE(c, n == n_floats, "tb_upload: size mismatch");
-    if (which != TB_BUF_FLOW && which != TB_BUF_TARGETS) c->count_valid = false;
     TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaMemcpyAsync(dst, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1305,6 +815,7 @@ int tb_upload(tb_ctx *c, tb_buffer which, const float *host, int64_t n_floats) {
 int tb_download(tb_ctx *c, tb_buffer which, float *host, int64_t n_floats) {
     TB_REQUIRE(c, c && host, "null argument");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     float4 *src; int64_t n;
     if (int r = buffer_of(c, which, &src, &n)) return r;
     TB_REQUIRE(c, n == n_floats, "tb_download: size mismatch");
@@ -1317,6 +828,7 @@ int tb_blend_into_flow(tb_ctx *c, const float *rgba, int32_t w, int32_t h) {
     TB_REQUIRE(c, c && rgba, "null argument");
     TB_REQUIRE(c, w == c->W && h == c->H, "tb_blend_into_flow: layer must have the flow grid's shape");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     const size_t G = static_cast<size_t>(w) * h;
     if (G > c->layer_cap) {
         TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1339,6 +851,7 @@ int tb_flow_line(tb_ctx *c, const tb_flow_line_params *params, int32_t n_vertice
     if (n_vertices < 3) return TB_OK;                       // a strip needs three vertices to make a triangle
     TB_REQUIRE(c, position && normal && miter && previous && time && dt, "null attribute array");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     const int n = n_vertices;
     if (n > c->line_cap) {
         TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1372,20 +885,12 @@ int tb_flow_line(tb_ctx *c, const tb_flow_line_params *params, int32_t n_vertice
     return TB_OK;
 }
 
-int tb_debug_segments(tb_ctx *c, uint32_t *host, int64_t n_words) {
-    TB_REQUIRE(c, c && host, "null argument");
-    TB_REQUIRE(c, n_words == 2LL * c->W * c->H, "tb_debug_segments: size mismatch");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    TB_CUDA(c, cudaMemcpyAsync(host, c->seg, static_cast<size_t>(n_words) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    TB_CUDA(c, cudaStreamSynchronize(c->stream));
-    return TB_OK;
-}
-
 int tb_optical_flow(tb_ctx *c, const tb_optical_flow_params *params, const uint8_t *view_rgba8, const uint8_t *last_rgba8,
                     int32_t w, int32_t h) {
     TB_REQUIRE(c, c && params && view_rgba8 && last_rgba8, "null argument");
     TB_REQUIRE(c, w >= 1 && h >= 1, "gl-texture2d: Texture dimensions are out of bounds");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     const size_t n = static_cast<size_t>(w) * h;
     if (2 * n > c->frames_cap) {
         TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1424,6 +929,7 @@ int tb_stream(tb_ctx *c, void **cuda_stream) {
 int tb_sync(tb_ctx *c) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     return TB_OK;
@@ -1431,6 +937,8 @@ int tb_sync(tb_ctx *c) {
 
 int tb_stats(tb_ctx *c, int64_t *kernel_launches, int64_t *last_fragments) {
     TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     if (kernel_launches) *kernel_launches = c->launches;
     if (last_fragments) *last_fragments = c->last_frags;
     return TB_OK;
@@ -1440,6 +948,7 @@ int tb_timing(tb_ctx *c, int reset, int64_t *n_integrate, float *integrate_ms, i
               int64_t *n_noise, float *noise_ms) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
     TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     int64_t *n_out[3] = {n_integrate, n_splat, n_noise};

@@ -36,15 +36,9 @@ class Device:
         self.world_size = int(world_size)
         self.group = group
         # how the ordered flow fold is shared between ranks:
-        #   "peer" = ring over CUDA-IPC peer memory: the grid travels rank to rank inside the fold kernels' stores (default)
-        #   "a2a"  = band exchange: all-to-all of sorted fragment slices, one grid band folded per rank; no serial
-        #            dependency between ranks, but the torch.distributed all-to-all it rides on is host-bound today
-        #   "dist" = the same ring over torch.distributed send/recv/broadcast (also what the gloo tests run)
-        #   "bands" = parallel fold over CUDA-IPC peer memory: every rank owns the grid tiles t % world == rank; the
-        #            sources push their sorted fragments to the owners over NVLink, laid out per texel in rank order,
-        #            and the owners fold and publish their tiles; four all-rank barriers per step, no serial chain
-        #   default: "peer" on 2 ranks, "bands" on more (measured on 8 x B200, profiles/r01_multi_gpu.txt)
-        self.ring = ring or os.environ.get("TB_RING") or ("peer" if self.world_size <= 2 else "bands")
+        #   "dist"  = the grid travels rank 0 -> 1 -> ... over torch.distributed send/recv/broadcast, every rank folding
+        #             its own bins onto what it received (serial; also what the gloo tests run)
+        self.ring = ring or os.environ.get("TB_RING") or "dist"
 
 
 class Shader:
@@ -171,8 +165,7 @@ class Particles:
         self.render = params["render"]
         self.col0, self.col1 = shard_columns(self.shape[0], gl.rank, gl.world_size)
         self.flow_shape = [1, 1]
-        self._ring_ready = False
-        self._bands_ready = False
+        self._tiles_ready = False
         self._L = N.load()
         cfg = N.TbConfig(self.shape[0], self.shape[1], self.col0, self.col1, 1, 1, gl.device, 0)
         ctx = C.c_void_p()
@@ -206,8 +199,7 @@ class Particles:
     def _resize_flow(self, w, h):
         N.check(self._ctx, self._L.tb_resize_flow(self._ctx, w, h))
         self.flow_shape = [w, h]
-        self._ring_ready = False          # new allocation: the IPC handles must be exchanged again
-        self._bands_ready = False
+        self._tiles_ready = False         # new allocation: the IPC handles must be exchanged again
 
     def step(self, update, buffer=None):                                # src/particles.js:123-145
         """Runs `self.logic` once over the state texture.  buffer=None rotates the ping-pong
@@ -268,61 +260,11 @@ class Particles:
         if gl.world_size == 1:
             N.check(ctx, L.tb_splat_flow(ctx, float(u["time"])))
             return
-        if gl.ring == "bands":
-            self._ensure_bands()          # before the collect: the export fixes (and may reallocate) the fragment buffers
         N.check(ctx, L.tb_splat_collect(ctx, float(u["time"])))
-        G = self.flow_shape[0] * self.flow_shape[1]
-        if gl.ring == "a2a" and G % (gl.world_size * 128) == 0:
-            # band exchange: all-to-all of fragment slices, every rank folds one band (scales with the rank count)
-            from .multi_gpu import band_exchange_fold
-            band_exchange_fold(self)
-        elif gl.ring == "bands":
-            # parallel ordered fold over peer memory: every rank folds its own tiles of the grid with the fragments
-            # of all ranks, read over NVLink in rank order; no rank waits for another rank's fold
-            N.check(ctx, L.tb_splat_fold_bands(ctx))
-        elif gl.ring in ("peer", "a2a"):
-            # the ordered fold over peer memory: chunks travel rank to rank inside the fold kernels' own stores
-            self._ensure_ring()
-            N.check(ctx, L.tb_splat_fold_ring(ctx))
-        else:
-            # same protocol over torch.distributed send/recv/broadcast (NCCL or gloo): slower, but needs no IPC
-            from .multi_gpu import ordered_ring_fold
-            ordered_ring_fold(gl.rank, gl.world_size, gl.group,
-                              fold=lambda: N.check(ctx, L.tb_splat_fold(ctx)),
-                              flow_tensor=self._flow_tensor, stream=self.stream_handle())
-
-    def _ensure_ring(self):
-        """Exchange CUDA IPC handles of (flow grid, inbox, flags) once per flow-grid allocation and map the
-        next rank's.  torch.distributed is only the courier of 208 bytes per rank."""
-        if self._ring_ready:
-            return
-        from .multi_gpu import exchange_ring_handles
-        L, ctx, gl = self._L, self._ctx, self.gl
-        nbytes = L.tb_ring_handle_bytes()
-        mine = (C.c_ubyte * nbytes)()
-        N.check(ctx, L.tb_ring_export(ctx, mine, nbytes))
-        nxt = exchange_ring_handles(bytes(mine), gl.rank, gl.world_size, gl.group, gl.device)
-        buf = (C.c_ubyte * nbytes).from_buffer_copy(nxt)
-        N.check(ctx, L.tb_ring_connect(ctx, gl.rank, gl.world_size, buf, nbytes))
-        self._ring_ready = True
-
-    def _ensure_bands(self):
-        """Exchange CUDA IPC handles of (sorted fragments, segment table, flow grid, flags) once per flow-grid
-        allocation and map every rank's.  The fragment buffers are fixed at `TB_BANDS_RESERVE` (default 6)
-        fragments per local particle while mapped."""
-        if self._bands_ready:
-            return
-        from .multi_gpu import gather_handles
-        L, ctx, gl = self._L, self._ctx, self.gl
-        per = float(os.environ.get("TB_BANDS_RESERVE", "6"))
-        reserve = min(int(per * (self.col1 - self.col0) * self.shape[1]) + (1 << 16), (1 << 31) - 1)
-        nbytes = L.tb_bands_handle_bytes()
-        mine = (C.c_ubyte * nbytes)()
-        N.check(ctx, L.tb_bands_export(ctx, reserve, mine, nbytes))
-        blobs = gather_handles(bytes(mine), gl.world_size, gl.group, gl.device)
-        buf = (C.c_ubyte * (nbytes * gl.world_size)).from_buffer_copy(b"".join(blobs))
-        N.check(ctx, L.tb_bands_connect(ctx, gl.rank, gl.world_size, buf, nbytes * gl.world_size))
-        self._bands_ready = True
+        from .multi_gpu import ordered_ring_fold
+        ordered_ring_fold(gl.rank, gl.world_size, gl.group,
+                          fold=lambda: N.check(ctx, L.tb_splat_fold(ctx)),
+                          flow_tensor=self._flow_tensor, stream=self.stream_handle())
 
     # -- plumbing ------------------------------------------------------------------------
     def stream_handle(self) -> int:
