@@ -178,6 +178,12 @@ int tb_download(tb_ctx *ctx, tb_buffer which, float *host, int64_t n_floats);
  * inputs that draw into the flow FBO: optical flow, pointer flow-lines; src/demo.main.js:1107-1159). */
 int tb_blend_into_flow(tb_ctx *ctx, const float *rgba, int32_t w, int32_t h);
 
+/* diagnostic tap: the fragment bins left by the last splat.  offsets: tb_debug_max_bins() + 1 words (bin b holds
+ * offsets[b+1] - offsets[b] fragments, b < *n_bins); info: tb_debug_max_bins() words, bin -> strip | sub << 16 |
+ * log2(bins of the strip) << 24; the strip size in texels.  Used by tools/ to study the load distribution of the fold. */
+int tb_debug_max_bins(void);
+int tb_debug_bins(tb_ctx *ctx, uint32_t *offsets, uint32_t *info, int32_t *n_bins, int32_t *strip_w, int32_t *strip_h);
+
 /* OpticalFlow.update() + screen.render() with the flow FBO bound (src/optical-flow/index.frag:55-81,
  * src/optical-flow/index.js:50-58, call site src/demo.main.js:1131-1156): the gradient optical flow of two RGBA8
  * frames (view = current, last = previous; w*h*4 bytes each, texel row 0 first), written in the flow encoding

@@ -55,21 +55,28 @@ struct tb_ctx {
     PairEntry *pairs = nullptr;
     int n_pairs = 0;
     long long n_prims = 0;                 // local primitives = columns * n_pairs
-    TileGeom geom{};
+    StripGeom geom{};
     int slab_prims = 0, n_slabs = 0;       // slabs of consecutive primitives (fixed per context)
-    uint32_t *slab_hist = nullptr;         // [T][n_slabs] fragments per (tile, slab) -> per-tile exclusive scan over the slabs
-    uint32_t *tile_total = nullptr;        // [T]
-    uint32_t *bin_off = nullptr;           // [T + 1]
+    int slabs_per_seg = 1;
+    uint32_t *slab_hist = nullptr;         // [n_slabs][kMaxBins] fragments per (slab, bin) -> per-bin exclusive scan over the slabs
+    uint32_t *seg_total = nullptr;         // [2][kHistSegs][kMaxBins] the same summed over the slabs of a segment; the draws alternate
+    int seg_parity = 0;
+    uint32_t *bin_total = nullptr;         // [kMaxBins]
+    uint32_t *bin_off = nullptr;           // [kMaxBins + 1]
     uint32_t *tickets = nullptr;           // [0] hist, [1] scatter, [2] fold work counters, [3] fold items, [4] a bin beyond 2^32
-    FoldItem *items = nullptr;
-    int max_items = 0;
+    uint32_t *items = nullptr;             // [kMaxBins] fold work items, longest bins first
+    uint32_t *split_map = nullptr;         // [2][T] strip -> first bin | log2(bins) << 24; written by one draw's plan for the next
+    uint32_t *bin_info = nullptr;          // [2][kMaxBins] bin -> strip | sub << 16 | log2(bins) << 24
+    uint32_t *n_bins = nullptr;            // [2] device scalars
+    int map_parity = 0;
+    int fold_parity = 0;                   // the map the last collect used
+    uint32_t split_at = 8192;              // fragments per strip above which the next draw gives the strip 8 (32, 128) bins
     PlanOut *d_plan = nullptr;
     PlanOut *h_plan = nullptr;             // pinned; valid once ev_plan has completed
     cudaEvent_t ev_plan = nullptr;
     Frag *bins = nullptr;                  // every fragment of a draw, binned by tile, draw order inside a bin
     uint32_t bin_cap = 0;
     bool bin_fixed = false;                // the bin array is mapped by other ranks: it cannot grow without a reconnect
-    uint32_t hot_bin = 0xffffffffu;
     bool pending = false;                  // a draw is queued whose capacity check has not been read yet
     int pending_stage = 0;                 // 1: collect only, 2: collect + fold
     float pending_time = 0.f;
@@ -169,20 +176,18 @@ bool columns_are_identity(int PW) {
     return true;
 }
 
-// Tiles of the binning: 16 x 16 texels for small grids, grown (x first) until there are at most 1024 of them --
-// 32 x 32 at 1024^2 -- and, for grids beyond that, until at most kMaxTiles.
-TileGeom choose_geom(int W, int H) {
-    TileGeom g{};
+// Strips of the binning: 16 x 8 texels, grown (x first) until there are at most kMaxStrips of them.
+StripGeom choose_geom(int W, int H) {
+    StripGeom g{};
     g.W = W; g.H = H;
-    g.txl = 4; g.tyl = 4;
-    auto tiles = [&]() {
-        g.tiles_x = (W + (1 << g.txl) - 1) >> g.txl;
-        g.tiles_y = (H + (1 << g.tyl) - 1) >> g.tyl;
-        g.T = g.tiles_x * g.tiles_y;
+    g.sxl = 4; g.syl = 3;
+    auto strips = [&]() {
+        g.strips_x = (W + (1 << g.sxl) - 1) >> g.sxl;
+        g.strips_y = (H + (1 << g.syl) - 1) >> g.syl;
+        g.T = g.strips_x * g.strips_y;
         return g.T;
     };
-    while (tiles() > 1024 && g.txl + g.tyl < 10) { if (g.txl <= g.tyl) ++g.txl; else ++g.tyl; }
-    while (tiles() > kMaxTiles) { if (g.txl <= g.tyl) ++g.txl; else ++g.tyl; }
+    while (strips() > kMaxStrips) { if (g.sxl <= g.syl + 1) ++g.sxl; else ++g.syl; }
     return g;
 }
 
@@ -191,28 +196,42 @@ int tiles_release(tb_ctx *c);
 int alloc_flow(tb_ctx *c, int w, int h) {
     tiles_release(c);
     TB_REQUIRE(c, w >= 1 && h >= 1 && w <= 32768 && h <= 32768, "flow grid dimensions out of bounds");
-    cudaFree(c->flow); cudaFree(c->slab_hist); cudaFree(c->tile_total); cudaFree(c->bin_off); cudaFree(c->items);
-    c->flow = nullptr; c->slab_hist = nullptr; c->tile_total = nullptr; c->bin_off = nullptr; c->items = nullptr;
+    const StripGeom g = choose_geom(w, h);
+    TB_REQUIRE(c, (1 << (g.sxl + g.syl)) <= kFoldTexels, "flow grid too large for the strip binning (at most 8192 strips of 128 texels)");
+    cudaFree(c->flow); cudaFree(c->slab_hist); cudaFree(c->seg_total); cudaFree(c->bin_total); cudaFree(c->bin_off); cudaFree(c->items);
+    cudaFree(c->split_map); cudaFree(c->bin_info); cudaFree(c->n_bins);
+    c->flow = nullptr; c->slab_hist = nullptr; c->seg_total = nullptr; c->bin_total = nullptr; c->bin_off = nullptr; c->items = nullptr;
+    c->split_map = nullptr; c->bin_info = nullptr; c->n_bins = nullptr;
     c->W = w; c->H = h;
-    c->geom = choose_geom(w, h);
+    c->geom = g;
     const size_t G = static_cast<size_t>(w) * h;
-    const int T = c->geom.T;
+    const int T = g.T;
     TB_CUDA(c, cudaMalloc(&c->flow, G * sizeof(float4)));
-    TB_CUDA(c, cudaMalloc(&c->slab_hist, static_cast<size_t>(T) * std::max(c->n_slabs, 1) * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->tile_total, static_cast<size_t>(T) * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->bin_off, static_cast<size_t>(T + 1) * sizeof(uint32_t)));
-    c->max_items = 64 * T;
-    TB_CUDA(c, cudaMalloc(&c->items, static_cast<size_t>(c->max_items) * sizeof(FoldItem)));
+    TB_CUDA(c, cudaMalloc(&c->slab_hist, static_cast<size_t>(kMaxBins) * std::max(c->n_slabs, 1) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->seg_total, 2 * static_cast<size_t>(kMaxBins) * kHistSegs * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->bin_total, static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->bin_off, static_cast<size_t>(kMaxBins + 1) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->items, static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->split_map, 2 * static_cast<size_t>(T) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->bin_info, 2 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->n_bins, 2 * sizeof(uint32_t)));
     TB_CUDA(c, cudaMemsetAsync(c->flow, 0, G * sizeof(float4), c->stream));
-    // persistent grids of the splat kernels for this tile count
-    TB_CUDA(c, cudaFuncSetAttribute(k_splat_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem_bytes(T))));
+    TB_CUDA(c, cudaMemsetAsync(c->seg_total, 0, 2 * static_cast<size_t>(kMaxBins) * kHistSegs * sizeof(uint32_t), c->stream));
+    TB_CUDA(c, cudaMemsetAsync(c->bin_total, 0, static_cast<size_t>(kMaxBins) * sizeof(uint32_t), c->stream));
+    c->seg_parity = 0;
+    c->map_parity = 0;
+    k_splat_map_identity<<<blocks_for(T, 256), 256, 0, c->stream>>>(T, c->split_map, c->bin_info, c->n_bins);     // one bin per strip to begin with
+    if (cudaGetLastError() != cudaSuccess) return fail(c, TB_ERR_CUDA, "k_splat_map_identity failed to launch");
+    // persistent grids of the splat kernels
+    TB_CUDA(c, cudaFuncSetAttribute(k_splat_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBins * static_cast<int>(sizeof(uint32_t))));
+    TB_CUDA(c, cudaFuncSetAttribute(k_splat_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kScatterSmemBytes)));
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFoldSmemBytes)));
     int per_sm = 0;
-    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_scatter, kEmitThreads, scatter_smem_bytes(T)));
+    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_scatter, kEmitThreads, kScatterSmemBytes));
     c->scatter_ctas = std::max(1, per_sm) * c->n_sms;
     TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_fold, kFoldThreads, kFoldSmemBytes));
     c->fold_ctas = std::max(1, per_sm) * c->n_sms;
-    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_hist, kHistThreads, static_cast<size_t>(T) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_hist, kHistThreads, kMaxBins * sizeof(uint32_t)));
     c->hist_ctas = std::max(1, per_sm) * c->n_sms;
     c->collected = false;
     c->pending = false;
@@ -266,34 +285,56 @@ PrimSource prim_source(tb_ctx *c) {
 // Collect: rasterise this context's primitives into per-tile bins, draw order inside every bin.  Four launches, nothing
 // comes back to the host on the way: the plan (fragment total, overflow flag) is copied out behind the kernels and read
 // by resolve_pending() at the next API call.
+BinMap bin_map(tb_ctx *c, int parity) {
+    BinMap M{};
+    M.map = c->split_map + static_cast<size_t>(parity) * c->geom.T;
+    M.n_bins = c->n_bins + parity;
+    M.lS = c->geom.sxl + c->geom.syl;
+    return M;
+}
+
 int launch_collect(tb_ctx *c, float time) {
     const int T = c->geom.T;
     cudaEvent_t *stage = c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots];
+    const int mp = c->map_parity;                  // this draw's split map; its plan writes the other one for the next draw
+    c->map_parity ^= 1;
     if (c->n_prims > 0) {
+        uint32_t *seg_now = c->seg_total + static_cast<size_t>(c->seg_parity) * kHistSegs * kMaxBins;
+        uint32_t *seg_next = c->seg_total + static_cast<size_t>(c->seg_parity ^ 1) * kHistSegs * kMaxBins;
+        c->seg_parity ^= 1;
         HistArgs HA{};
         HA.src = prim_source(c);
         HA.g = c->geom;
+        HA.bm = bin_map(c, mp);
         HA.vsx = c->state.viewSize[0]; HA.vsy = c->state.viewSize[1];
-        HA.slab_prims = c->slab_prims; HA.n_slabs = c->n_slabs;
+        HA.slab_prims = c->slab_prims; HA.n_slabs = c->n_slabs; HA.slabs_per_seg = c->slabs_per_seg;
         HA.slab_hist = c->slab_hist;
+        HA.seg_total = seg_now;
         HA.ticket = c->tickets + 0;
-        k_splat_hist<<<std::min(c->n_slabs, c->hist_ctas), kHistThreads, static_cast<size_t>(T) * sizeof(uint32_t), c->stream>>>(HA);
+        k_splat_hist<<<std::min(c->n_slabs, c->hist_ctas), kHistThreads, kMaxBins * sizeof(uint32_t), c->stream>>>(HA);
         if (int r = check_launch(c, "k_splat_hist")) return r;
         if (c->stage_timing) cudaEventRecord(stage[1], c->stream);
-        k_splat_rows<<<blocks_for(T, 8), 256, 0, c->stream>>>(c->slab_hist, T, c->n_slabs, c->tile_total, c->tickets + 4);
+        k_splat_rows<<<dim3(kMaxBins / 256, kHistSegs), 256, 0, c->stream>>>(c->slab_hist, seg_now, seg_next, c->n_bins + mp, c->n_slabs,
+                                                                             c->slabs_per_seg, c->bin_total, c->tickets + 4);
         if (int r = check_launch(c, "k_splat_rows")) return r;
     } else {
-        TB_CUDA(c, cudaMemsetAsync(c->tile_total, 0, static_cast<size_t>(T) * sizeof(uint32_t), c->stream));
+        TB_CUDA(c, cudaMemsetAsync(c->bin_total, 0, static_cast<size_t>(kMaxBins) * sizeof(uint32_t), c->stream));
     }
     PlanArgs PA{};
-    PA.g = c->geom;
-    PA.tile_total = c->tile_total;
+    PA.T = T;
+    PA.lS = c->geom.sxl + c->geom.syl;
+    PA.bm = bin_map(c, mp);
+    PA.bin_info = c->bin_info + static_cast<size_t>(mp) * kMaxBins;
+    PA.bin_total = c->bin_total;
     PA.bin_off = c->bin_off;
-    PA.items = c->items; PA.max_items = c->max_items;
+    PA.items = c->items;
     PA.cap = c->bin_cap;
-    PA.hot_bin = c->hot_bin;
+    PA.split_at = c->split_at;
     PA.too_many = c->tickets + 4;
     PA.tickets = c->tickets;
+    PA.map_next = c->split_map + static_cast<size_t>(mp ^ 1) * T;
+    PA.bin_info_next = c->bin_info + static_cast<size_t>(mp ^ 1) * kMaxBins;
+    PA.n_bins_next = c->n_bins + (mp ^ 1);
     PA.out = c->d_plan;
     k_splat_plan<<<1, kPlanThreads, 0, c->stream>>>(PA);
     if (int r = check_launch(c, "k_splat_plan")) return r;
@@ -304,6 +345,7 @@ int launch_collect(tb_ctx *c, float time) {
         ScatterArgs SA{};
         SA.src = prim_source(c);
         SA.g = c->geom;
+        SA.bm = bin_map(c, mp);
         SA.vsx = c->state.viewSize[0]; SA.vsy = c->state.viewSize[1];
         SA.speedLimit = c->state.speedLimit;
         SA.time = time;
@@ -313,11 +355,12 @@ int launch_collect(tb_ctx *c, float time) {
         SA.plan = c->d_plan;
         SA.ticket = c->tickets + 1;
         SA.bins[0] = c->bins;
-        SA.tile_owner = nullptr;
-        k_splat_scatter<<<std::min(c->n_slabs, c->scatter_ctas), kEmitThreads, scatter_smem_bytes(T), c->stream>>>(SA);
+        SA.bin_owner = nullptr;
+        k_splat_scatter<<<std::min(c->n_slabs, c->scatter_ctas), kEmitThreads, kScatterSmemBytes, c->stream>>>(SA);
         if (int r = check_launch(c, "k_splat_scatter")) return r;
     }
     if (c->stage_timing) cudaEventRecord(stage[3], c->stream);
+    c->fold_parity = mp;
     return TB_OK;
 }
 
@@ -326,12 +369,14 @@ int launch_fold(tb_ctx *c, float time) {
     FA.g = c->geom;
     FA.time = time;
     FA.bins = c->bins;
+    FA.bin_off = c->bin_off;
+    FA.bin_info = c->bin_info + static_cast<size_t>(c->fold_parity) * kMaxBins;
     FA.items = c->items;
     FA.n_items = c->tickets + 3;
     FA.ticket = c->tickets + 2;
     FA.flow[0] = c->flow;
     FA.n_flow = 1;
-    k_splat_fold<<<std::min(c->fold_ctas, c->max_items), kFoldThreads, kFoldSmemBytes, c->stream>>>(FA);
+    k_splat_fold<<<c->fold_ctas, kFoldThreads, kFoldSmemBytes, c->stream>>>(FA);
     return check_launch(c, "k_splat_fold");
 }
 
@@ -496,8 +541,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     // Opt-in (TB_OVERLAP=1): measured +4.7 % step throughput at cfg3, but the low-priority noise launch is
     // time-sliced under the sort, which makes its own duration meaningless as a roofline input.
     c->overlap = std::getenv("TB_OVERLAP") != nullptr;
-    if (const char *e = std::getenv("TB_HOT_BIN")) c->hot_bin = static_cast<uint32_t>(std::max(1, std::atoi(e)));
     c->stage_timing = std::getenv("TB_STAGE_TIMING") != nullptr;
+    if (const char *e = std::getenv("TB_SPLIT_AT")) c->split_at = static_cast<uint32_t>(std::max(64, std::atoi(e)));
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));
@@ -533,9 +578,10 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     if (c->n_prims >= (1LL << 31)) { c->err = "tendrils-b200: too many primitives per context"; return bail(TB_ERR_INVALID); }
     // slabs of consecutive primitives: the unit of work of the count and emit passes (about eight per SM)
     {
-        const long long want = (c->n_prims + 8LL * c->n_sms - 1) / (8LL * c->n_sms);
-        c->slab_prims = static_cast<int>(std::max<long long>(kEmitThreads, (want + kEmitThreads - 1) / kEmitThreads * kEmitThreads));
+        const long long want = (c->n_prims + 6LL * c->n_sms - 1) / (6LL * c->n_sms);
+        c->slab_prims = static_cast<int>(std::max<long long>(4 * kEmitThreads, (want + kEmitThreads - 1) / kEmitThreads * kEmitThreads));
         c->n_slabs = static_cast<int>((c->n_prims + c->slab_prims - 1) / c->slab_prims);
+        c->slabs_per_seg = std::max(1, (c->n_slabs + kHistSegs - 1) / kHistSegs);
     }
 #undef TB_TRY
     const int fw = cfg->flow_w > 0 ? cfg->flow_w : 1, fh = cfg->flow_h > 0 ? cfg->flow_h : 1;
@@ -556,7 +602,8 @@ int tb_destroy(tb_ctx *c) {
     cudaFree(c->frames);
     cudaFree(c->line_attr); cudaFree(c->line_verts); cudaFree(c->line_bbox);
     cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->d_flag);
-    cudaFree(c->slab_hist); cudaFree(c->tile_total); cudaFree(c->bin_off); cudaFree(c->tickets); cudaFree(c->items);
+    cudaFree(c->slab_hist); cudaFree(c->seg_total); cudaFree(c->bin_total); cudaFree(c->bin_off); cudaFree(c->tickets); cudaFree(c->items);
+    cudaFree(c->split_map); cudaFree(c->bin_info); cudaFree(c->n_bins);
     cudaFree(c->d_plan); cudaFree(c->bins);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_plan) cudaFreeHost(c->h_plan);
@@ -909,6 +956,24 @@ int tb_optical_flow(tb_ctx *c, const tb_optical_flow_params *params, const uint8
     k_optical_flow<<<blocks_for(static_cast<long long>(c->W) * c->H, 256), 256, 0, c->stream>>>(A);
     if (int r = check_launch(c, "k_optical_flow")) return r;
     if (!resident) TB_CUDA(c, cudaStreamSynchronize(c->stream));       // host frames are only borrowed
+    return TB_OK;
+}
+
+int tb_debug_max_bins(void) { return kMaxBins; }
+
+int tb_debug_bins(tb_ctx *c, uint32_t *offsets, uint32_t *info, int32_t *n_bins, int32_t *strip_w, int32_t *strip_h) {
+    TB_REQUIRE(c, c && offsets && info && n_bins, "null argument");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
+    uint32_t nb = 0;
+    TB_CUDA(c, cudaMemcpyAsync(&nb, c->n_bins + c->fold_parity, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(offsets, c->bin_off, static_cast<size_t>(kMaxBins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(info, c->bin_info + static_cast<size_t>(c->fold_parity) * kMaxBins, static_cast<size_t>(kMaxBins) * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_bins = static_cast<int32_t>(nb);
+    if (strip_w) *strip_w = 1 << c->geom.sxl;
+    if (strip_h) *strip_h = 1 << c->geom.syl;
     return TB_OK;
 }
 

@@ -1,20 +1,23 @@
-// tb_splat.cuh -- the ordered flow splat (a7-a10) as a tile-binned pipeline, sm_100a.
+// tb_splat.cuh -- the ordered flow splat (a7-a10) as a binned pipeline, sm_100a.
 //
 // The reference draws every particle as a GL_LINES segment prev -> cur into the flow FBO under
 // blendFunc(SRC_ALPHA, ONE_MINUS_SRC_ALPHA), in primitive order p = x*PH + k
 // (src/index.js:267-268,278-303, src/particles.js:147-158,182-186).  The blend is not
 // commutative, so per texel the fragments must be applied in draw order.  This file does that
-// without a global sort:
+// without a global sort.  The grid is cut into STRIPS (16 x 8 texels at 1024^2); a strip is one BIN
+// of the fragment array, or -- where the previous draw found it crowded -- 8, 32 or 128 bins, one
+// per range of its texels (the split map; any map gives the same result, it only balances the work):
 //
-//   k_splat_hist     per slab of consecutive primitives: fragments per grid TILE            (count)
-//   k_splat_rows     per tile: exclusive scan over the slabs, tile totals                    (scan)
-//   k_splat_plan     tile totals -> bin offsets, the fold work list, capacity check          (scan)
-//   k_splat_scatter  re-rasterise; every fragment goes straight to its slot of its tile's bin,
-//                    bins filled in draw order (a stable multi-split: warp match + per-warp
-//                    counters, no global atomics on the data path)                           (emit)
-//   k_splat_fold     per tile: stream the bin through shared memory (cp.async.bulk + mbarrier,
-//                    double buffered), blend in order onto the tile held in shared memory,
-//                    write the tile back                                                     (fold)
+//   k_splat_hist     per slab of consecutive primitives: fragments per bin                    (count)
+//   k_splat_rows     per bin: exclusive scan over the slabs                                    (scan)
+//   k_splat_plan     bin totals -> bin offsets, the fold work list, capacity check, and the
+//                    split map of the NEXT draw                                                (scan)
+//   k_splat_scatter  rasterise; every fragment goes straight to its slot of its bin, bins filled
+//                    in draw order: the warps of a CTA take 32 consecutive primitives each and
+//                    claim bin slots from shared-memory cursors one warp after the other (a token
+//                    passed over named barriers), in slot order inside the warp                (emit)
+//   k_splat_fold     one warp per bin: the bin's texels live in shared memory, the bin streams
+//                    past (cp.async.bulk + mbarrier) in batches of 32 fragments, blended in order
 //
 // A fragment is written once (16 B) and read once; nothing is sorted, nothing returns to the host.
 // Compiled with -fmad=false; see tb_math.cuh for the arithmetic contract.
@@ -25,38 +28,43 @@
 namespace tb {
 
 // ------------------------------------------------------------------------------------------
-// Geometry of the binning: the grid is cut into tiles of (1 << txl) x (1 << tyl) texels.
+// Geometry of the binning: strips of (1 << sxl) x (1 << syl) texels, at most kFoldTexels each.
 // ------------------------------------------------------------------------------------------
-constexpr int kMaxTiles = 2048;           // bins per grid (k_splat_scatter keeps per-warp counters per tile in shared memory)
-constexpr int kFoldTexels = 1024;         // texels one fold work item holds in shared memory
+constexpr int kMaxStrips = 8192;
+constexpr int kMaxBins = 12288;           // bins per grid: k_splat_scatter keeps one cursor per bin in shared memory
+constexpr int kFoldTexels = 128;          // texels of a strip = the most one warp of k_splat_fold holds
+constexpr int kHistSegs = 16;             // the slabs are scanned in this many segments (k_splat_rows)
 constexpr uint32_t kKeyLocalMask = 0x000fffffu;
-constexpr uint32_t kKeyTame = 0x40000000u;     // cx, cy finite and 0 <= a <= 1
-constexpr uint32_t kKeyOpaque = 0x80000000u;   // a == 1 and no colour channel is -0: the fragment overwrites its texel
 
-struct TileGeom {
+struct StripGeom {
     int W, H;
-    int txl, tyl;            // log2 of the tile width / height
-    int tiles_x, tiles_y;
-    int T;                   // tiles_x * tiles_y <= kMaxTiles
+    int sxl, syl;            // log2 of the strip width / height
+    int strips_x, strips_y;
+    int T;                   // strips_x * strips_y <= kMaxStrips
 };
 
-__host__ __device__ __forceinline__ int tile_of(const TileGeom &g, int gx, int gy) { return (gy >> g.tyl) * g.tiles_x + (gx >> g.txl); }
-__host__ __device__ __forceinline__ uint32_t local_of(const TileGeom &g, int gx, int gy) {
-    return (static_cast<uint32_t>(gy & ((1 << g.tyl) - 1)) << g.txl) | static_cast<uint32_t>(gx & ((1 << g.txl) - 1));
+__host__ __device__ __forceinline__ int strip_of(const StripGeom &g, int gx, int gy) { return (gy >> g.syl) * g.strips_x + (gx >> g.sxl); }
+__host__ __device__ __forceinline__ uint32_t local_of(const StripGeom &g, int gx, int gy) {
+    return (static_cast<uint32_t>(gy & ((1 << g.syl) - 1)) << g.sxl) | static_cast<uint32_t>(gx & ((1 << g.sxl) - 1));
+}
+
+// The split map: map[strip] = first bin | log2(bins of the strip) << 24; bin_info[bin] = strip | sub << 16 | log2(bins) << 24.
+// Sub-bin `sub` of a strip split 2^ls ways holds local texel indices [sub * (S >> ls), (sub + 1) * (S >> ls)).
+struct BinMap {
+    const uint32_t *__restrict__ map;        // [T]
+    const uint32_t *__restrict__ n_bins;     // device scalar, <= kMaxBins
+    int lS;                                  // log2 of the texels per strip
+};
+__device__ __forceinline__ uint32_t bin_of(const BinMap &M, uint32_t strip, uint32_t local) {
+    const uint32_t m = __ldg(M.map + strip);
+    return (m & 0xffffffu) + (local >> (M.lS - (m >> 24)));
 }
 
 // One fragment in a bin: the interpolated colour's (vel.xy, alpha) -- the time channel is the uniform
-// `time` -- and where it goes inside its tile.
+// `time` -- and where it goes inside its strip.
 struct __align__(16) Frag {
     float cx, cy, a;
-    uint32_t key;            // local texel index | kKeyTame | kKeyOpaque
-};
-
-// One unit of fold work: texels [lo, hi) (local indices) of tile `tile`, fed by bin [begin, end).
-struct FoldItem {
-    uint32_t tile, lo, hi, pad;
-    uint32_t begin, end;     // fragment range in the bin array
-    uint32_t pad2[2];
+    uint32_t key;            // texel index inside the strip
 };
 
 // What the plan kernel leaves for the host (read lazily, never waited for on the hot path).
@@ -145,79 +153,13 @@ struct PrimSource {
     long long n_prims;
 };
 __device__ __forceinline__ void load_prim(const PrimSource &S, long long p, float4 &sa, float4 &sb) {
-    const int xl = static_cast<int>(p / S.n_pairs);
-    const int4 pv = __ldg(reinterpret_cast<const int4 *>(S.pairs + (p - static_cast<long long>(xl) * S.n_pairs)));
-    PairEntry pe;
-    pe.k = pv.x; pe.row_a = pv.y; pe.row_b = pv.z; pe.pad = pv.w;
+    const uint32_t xl = static_cast<uint32_t>(p) / static_cast<uint32_t>(S.n_pairs);            // n_prims < 2^31
+    const int4 pv = __ldg(reinterpret_cast<const int4 *>(S.pairs + (static_cast<uint32_t>(p) - xl * static_cast<uint32_t>(S.n_pairs))));
     const size_t base = static_cast<size_t>(xl) * S.PH;
-    sa = __ldg(((pe.row_a < 0) ? S.cur : S.prev) + base + (pe.row_a & 0x7fffffff));
-    sb = __ldg(((pe.row_b < 0) ? S.cur : S.prev) + base + (pe.row_b & 0x7fffffff));
+    sa = __ldg(((pv.y < 0) ? S.cur : S.prev) + base + (pv.y & 0x7fffffff));
+    sb = __ldg(((pv.z < 0) ? S.cur : S.prev) + base + (pv.z & 0x7fffffff));
 }
 
-// ------------------------------------------------------------------------------------------
-// Pass 1: fragments per (tile, slab).  A slab is a fixed range of consecutive primitives; CTAs take
-// slabs from a ticket counter.  hist[tile * n_slabs + slab].
-// ------------------------------------------------------------------------------------------
-constexpr int kHistThreads = 256;
-
-struct HistArgs {
-    PrimSource src;
-    TileGeom g;
-    float vsx, vsy;
-    int slab_prims, n_slabs;
-    uint32_t *__restrict__ slab_hist;
-    uint32_t *ticket;
-};
-
-__global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);              // [T]
-    __shared__ int s_slab;
-    const int T = A.g.T;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_slab = static_cast<int>(atomicAdd(A.ticket, 1u));
-        for (int t = threadIdx.x; t < T; t += kHistThreads) hist[t] = 0u;
-        __syncthreads();
-        const int slab = s_slab;
-        if (slab >= A.n_slabs) break;
-        const long long p0 = static_cast<long long>(slab) * A.slab_prims;
-        const long long p1 = (p0 + A.slab_prims < A.src.n_prims) ? p0 + A.slab_prims : A.src.n_prims;
-        for (long long p = p0 + threadIdx.x; p < p1; p += kHistThreads) {
-            float4 sa, sb;
-            load_prim(A.src, p, sa, sb);
-            PrimGeom P;
-            const uint32_t n = prim_setup(sa, sb, A.vsx, A.vsy, A.g.W, A.g.H, P);
-            // runs of fragments in one tile are added at once
-            int run_tile = -1;
-            uint32_t run = 0;
-            if (n != 0u && !(P.flags & 2u)) {
-                const bool xmajor = (P.flags & 1u) != 0u;
-                raster_line(xmajor ? P.ma : P.na, xmajor ? P.na : P.ma, xmajor ? P.mb : P.nb, xmajor ? P.nb : P.mb, A.g.W, A.g.H,
-                            [&](int gx, int gy, float) {
-                                const int tl = tile_of(A.g, gx, gy);
-                                if (tl != run_tile) { if (run) atomicAdd(&hist[run_tile], run); run_tile = tl; run = 0; }
-                                ++run;
-                            });
-            } else {
-                for (uint32_t j = 0; j < n; ++j) {
-                    int gx, gy; float t;
-                    prim_fragment(P, j, A.g.W, A.g.H, gx, gy, t);
-                    const int tl = tile_of(A.g, gx, gy);
-                    if (tl != run_tile) { if (run) atomicAdd(&hist[run_tile], run); run_tile = tl; run = 0; }
-                    ++run;
-                }
-            }
-            if (run) atomicAdd(&hist[run_tile], run);
-        }
-        __syncthreads();
-        for (int t = threadIdx.x; t < T; t += kHistThreads) A.slab_hist[static_cast<size_t>(t) * A.n_slabs + slab] = hist[t];
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Pass 2a: per tile (one warp each) the exclusive scan of its row of slab counts, in place, and the tile's total.
-// ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -227,41 +169,175 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) k_splat_rows(uint32_t *__restrict__ slab_hist, int T, int n_slabs,
-                                                    uint32_t *__restrict__ tile_total, uint32_t *__restrict__ too_many) {
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (t >= T) return;
-    uint32_t *row = slab_hist + static_cast<size_t>(t) * n_slabs;
-    unsigned long long carry = 0ull;
-    for (int s0 = 0; s0 < n_slabs; s0 += 32) {
-        const int s = s0 + lane;
-        const uint32_t v = (s < n_slabs) ? row[s] : 0u;
-        const uint32_t inc = warp_incl_scan(v, lane);
-        if (s < n_slabs) row[s] = static_cast<uint32_t>(carry) + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+// ------------------------------------------------------------------------------------------
+// Pass 1: fragments per (slab, bin).  A slab is a fixed range of consecutive primitives; CTAs take
+// slabs from a ticket counter.  slab_hist[slab * kMaxBins + bin]; seg_total[seg * kMaxBins + bin] accumulates
+// the slabs of a segment (zeroed by k_splat_rows of the previous draw).
+// ------------------------------------------------------------------------------------------
+constexpr int kHistThreads = 256;
+
+struct HistArgs {
+    PrimSource src;
+    StripGeom g;
+    BinMap bm;
+    float vsx, vsy;
+    int slab_prims, n_slabs, slabs_per_seg;
+    uint32_t *__restrict__ slab_hist;
+    uint32_t *__restrict__ seg_total;
+    uint32_t *ticket;
+};
+
+// Texel of fragment j of a closed-form primitive without the exact division where the answer cannot depend on it: the
+// major coordinate is exact, the minor one is first estimated with a reciprocal; only an estimate within `eps` of a
+// texel boundary is redone exactly.
+__device__ __forceinline__ void prim_fragment_texel(const PrimGeom &P, uint32_t j, float inv_dm, float eps, int &gx, int &gy) {
+    const int i = P.c0 + static_cast<int>(j);
+    const float ic = __fadd_rn(static_cast<float>(i), 0.5f);
+    const float dn = __fsub_rn(P.nb, P.na);
+    const float est = __fadd_rn(P.na, __fmul_rn(__fmul_rn(__fsub_rn(ic, P.ma), inv_dm), dn));
+    const float fl = floorf(est);
+    int jj = static_cast<int>(fl);
+    if (__fsub_rn(est, fl) < eps || __fsub_rn(__fadd_rn(fl, 1.0f), est) < eps) {
+        const float t = __fdiv_rn(__fsub_rn(ic, P.ma), __fsub_rn(P.mb, P.ma));
+        jj = static_cast<int>(floorf(__fadd_rn(P.na, __fmul_rn(t, dn))));
     }
-    if (lane == 0) {
-        tile_total[t] = static_cast<uint32_t>(carry);
-        if (carry > 0xffffffffull) *too_many = 1u;          // a single bin beyond 2^32 fragments: reported as overflow
+    gx = (P.flags & 1u) ? i : jj;
+    gy = (P.flags & 1u) ? jj : i;
+}
+
+__global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);              // [n_bins]
+    __shared__ int s_slab;
+    const int B = static_cast<int>(*A.bm.n_bins);
+    for (int t = threadIdx.x; t < B; t += kHistThreads) hist[t] = 0u;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_slab = static_cast<int>(atomicAdd(A.ticket, 1u));
+        __syncthreads();
+        const int slab = s_slab;
+        if (slab >= A.n_slabs) break;
+        const long long p0 = static_cast<long long>(slab) * A.slab_prims;
+        const long long p1 = (p0 + A.slab_prims < A.src.n_prims) ? p0 + A.slab_prims : A.src.n_prims;
+        // two primitives in flight per thread: the vertex loads of the second hide behind the first
+        for (long long pb = p0 + threadIdx.x; pb < p1; pb += 2 * kHistThreads) {
+            float4 sa[2], sb[2];
+            const bool have1 = pb + kHistThreads < p1;
+            load_prim(A.src, pb, sa[0], sb[0]);
+            if (have1) load_prim(A.src, pb + kHistThreads, sa[1], sb[1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !have1) break;
+                PrimGeom P;
+                const uint32_t n = prim_setup(sa[u], sb[u], A.vsx, A.vsy, A.g.W, A.g.H, P);
+                if (n == 0u) continue;
+                const bool xmajor = (P.flags & 1u) != 0u;
+                int run_bin = -1;
+                uint32_t run = 0;
+                auto count = [&](int gx, int gy) {
+                    const int b = static_cast<int>(bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), local_of(A.g, gx, gy)));
+                    if (b != run_bin) { if (run) atomicAdd(&hist[run_bin], run); run_bin = b; run = 0; }
+                    ++run;
+                };
+                if (P.flags & 2u) {
+                    // closed form.  All fragments lie in the box spanned by the two vertices (the minor coordinate up to a few
+                    // ulps): when that box, widened by 1/16 texel, sits in one unsplit strip, so do they.
+                    const float mlo = gmin(P.ma, P.mb), mhi = gmax(P.ma, P.mb), nlo = __fsub_rn(gmin(P.na, P.nb), 0.0625f), nhi = __fadd_rn(gmax(P.na, P.nb), 0.0625f);
+                    const int M = xmajor ? A.g.W : A.g.H, N = xmajor ? A.g.H : A.g.W;
+                    int m0 = static_cast<int>(floorf(mlo)), m1 = static_cast<int>(floorf(mhi));
+                    int q0 = static_cast<int>(floorf(nlo)), q1 = static_cast<int>(floorf(nhi));
+                    m0 = m0 < 0 ? 0 : m0; m1 = m1 > M - 1 ? M - 1 : m1;
+                    q0 = q0 < 0 ? 0 : q0; q1 = q1 > N - 1 ? N - 1 : q1;
+                    const int s0 = xmajor ? strip_of(A.g, m0, q0) : strip_of(A.g, q0, m0);
+                    const int s1 = xmajor ? strip_of(A.g, m1, q1) : strip_of(A.g, q1, m1);
+                    const uint32_t m = __ldg(A.bm.map + s0);
+                    if (s0 == s1 && (m >> 24) == 0u) {
+                        atomicAdd(&hist[m & 0xffffffu], n);
+                        continue;
+                    }
+                    const float inv_dm = __fdiv_rn(1.0f, __fsub_rn(P.mb, P.ma));
+                    const float eps = __fmul_rn(__fadd_rn(__fadd_rn(fabsf(P.na), fabsf(__fsub_rn(P.nb, P.na))), 1.0f), 1.9073486328125e-06f);   // 2^-19
+                    for (uint32_t j = 0; j < n; ++j) {
+                        int gx, gy;
+                        prim_fragment_texel(P, j, inv_dm, eps, gx, gy);
+                        count(gx, gy);
+                    }
+                } else {
+                    raster_line(xmajor ? P.ma : P.na, xmajor ? P.na : P.ma, xmajor ? P.mb : P.nb, xmajor ? P.nb : P.mb, A.g.W, A.g.H,
+                                [&](int gx, int gy, float) { count(gx, gy); });
+                }
+                if (run) atomicAdd(&hist[run_bin], run);
+            }
+        }
+        __syncthreads();
+        uint32_t *row = A.slab_hist + static_cast<size_t>(slab) * kMaxBins;
+        uint32_t *seg = A.seg_total + static_cast<size_t>(slab / A.slabs_per_seg) * kMaxBins;
+        for (int t = threadIdx.x; t < B; t += kHistThreads) {
+            const uint32_t h = hist[t];
+            row[t] = h;
+            if (h) { atomicAdd(&seg[t], h); hist[t] = 0u; }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Pass 2b (single GPU): bin offsets, the fold work list (largest bins first), the capacity check.  One CTA.
+// Pass 2a: per bin the exclusive scan of its slab counts (in place), segment by segment: thread (bin, segment)
+// starts from the totals of the earlier segments.  Segment 0 also writes the bin's total.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_splat_rows(uint32_t *__restrict__ slab_hist, const uint32_t *__restrict__ seg_total,
+                                                    uint32_t *__restrict__ seg_total_next, const uint32_t *__restrict__ n_bins, int n_slabs,
+                                                    int slabs_per_seg, uint32_t *__restrict__ bin_total, uint32_t *__restrict__ too_many) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int seg = blockIdx.y;
+    seg_total_next[static_cast<size_t>(seg) * kMaxBins + t] = 0u;   // the next draw accumulates into the other buffer (grid covers kMaxBins)
+    if (t >= static_cast<int>(*n_bins)) return;
+    unsigned long long base = 0ull, all = 0ull;
+#pragma unroll
+    for (int s = 0; s < kHistSegs; ++s) {
+        const uint32_t v = seg_total[static_cast<size_t>(s) * kMaxBins + t];
+        if (s < seg) base += v;
+        all += v;
+    }
+    if (seg == 0) {
+        bin_total[t] = static_cast<uint32_t>(all);
+        if (all > 0xffffffffull) *too_many = 1u;            // a single bin beyond 2^32 fragments: reported as overflow
+    }
+    const int s0 = seg * slabs_per_seg, s1 = (s0 + slabs_per_seg < n_slabs) ? s0 + slabs_per_seg : n_slabs;
+    uint32_t run = static_cast<uint32_t>(base);
+    for (int s = s0; s < s1; s += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (s + k < s1) ? __ldcs(slab_hist + static_cast<size_t>(s + k) * kMaxBins + t) : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (s + k < s1) slab_hist[static_cast<size_t>(s + k) * kMaxBins + t] = run;
+            run += v[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass 2b (single GPU): bin offsets, the fold work list (longest bins first), the capacity check -- and the split map
+// of the next draw, from this draw's fragments per strip.  One CTA.
 // ------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 1024;
+constexpr int kPlanBins = kMaxBins / kPlanThreads;       // bins per thread
+constexpr int kPlanStrips = kMaxStrips / kPlanThreads;   // strips per thread
 
 struct PlanArgs {
-    TileGeom g;
-    const uint32_t *__restrict__ tile_total;   // [T]
-    uint32_t *__restrict__ bin_off;            // [T + 1]
-    FoldItem *__restrict__ items;              // [max_items]
-    int max_items;
+    int T, lS;                                 // strips, log2 of the texels per strip
+    BinMap bm;                                 // this draw's map
+    const uint32_t *__restrict__ bin_info;     // [n_bins] strip | sub << 16 | log2(bins of the strip) << 24
+    const uint32_t *__restrict__ bin_total;    // [n_bins]
+    uint32_t *__restrict__ bin_off;            // [n_bins + 1]
+    uint32_t *__restrict__ items;              // [kMaxBins] bins with fragments, longest first
     uint32_t cap;                              // capacity of the bin array (fragments)
-    uint32_t hot_bin;                          // bins longer than this are split into sub-items by texel rows
+    uint32_t split_at;                         // a strip with more fragments than this gets 8 bins next time, 4x: 32, 16x: 128
     uint32_t *too_many;                        // set by k_splat_rows; reset here
     uint32_t *tickets;                         // [0] hist (reset for the next draw), [1] scatter, [2] fold, [3] items
+    uint32_t *map_next;                        // [T]   the next draw's map ...
+    uint32_t *bin_info_next;                   // [kMaxBins]
+    uint32_t *n_bins_next;                     // ... and its bin count
     PlanOut *out;
 };
 
@@ -294,26 +370,21 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
     return r;
 }
 
-// sub-items a bin of `n` fragments over `L` local texels is cut into (powers of two; each scans the whole bin)
-__device__ __forceinline__ uint32_t fold_splits(uint32_t n, uint32_t L, uint32_t hot_bin) {
-    uint32_t s = (L + kFoldTexels - 1) / kFoldTexels;
-    if (s == 0) s = 1;
-    uint32_t per = L / s;
-    while (n > hot_bin && per > 32u && s < 64u) { s *= 4u; per /= 4u; n /= 4u; }
-    return s;
-}
-
 __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
     __shared__ uint32_t s_bucket[33];
     __shared__ uint32_t s_ok;
-    const int T = A.g.T;
-    const uint32_t L = 1u << (A.g.txl + A.g.tyl);
-    // two tiles per thread (T <= 2048)
-    const int t0 = threadIdx.x * 2, t1 = t0 + 1;
-    const uint32_t n0 = (t0 < T) ? A.tile_total[t0] : 0u, n1 = (t1 < T) ? A.tile_total[t1] : 0u;
-    const unsigned long long ex = block_excl_scan64(static_cast<unsigned long long>(n0) + n1, s_warp, &s_total);
+    const int B = static_cast<int>(*A.bm.n_bins);
+    const int t0 = threadIdx.x * kPlanBins;
+    uint32_t n[kPlanBins];
+    unsigned long long mine = 0ull;
+#pragma unroll
+    for (int k = 0; k < kPlanBins; ++k) {
+        n[k] = (t0 + k < B) ? A.bin_total[t0 + k] : 0u;
+        mine += n[k];
+    }
+    const unsigned long long ex = block_excl_scan64(mine, s_warp, &s_total);
     if (threadIdx.x == 0) {
         const bool ok = s_total <= static_cast<unsigned long long>(A.cap) && *A.too_many == 0u;
         s_ok = ok ? 1u : 0u;
@@ -325,96 +396,129 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     if (threadIdx.x < 33) s_bucket[threadIdx.x] = 0u;
     __syncthreads();
     const bool ok = s_ok != 0u;
-    if (t0 < T) A.bin_off[t0] = ok ? static_cast<uint32_t>(ex) : 0u;
-    if (t1 < T) A.bin_off[t1] = ok ? static_cast<uint32_t>(ex + n0) : 0u;
-    if (threadIdx.x == 0) A.bin_off[T] = ok ? static_cast<uint32_t>(s_total) : 0u;
-    // work list, longest bins first (bucketed by log2 of the length): the tail of the fold is short items
-    const uint32_t sp0 = (ok && n0) ? fold_splits(n0, L, A.hot_bin) : 0u, sp1 = (ok && n1) ? fold_splits(n1, L, A.hot_bin) : 0u;
-    const int b0 = n0 ? 31 - __clz(n0 / (sp0 ? sp0 : 1u) | 1u) : 0, b1 = n1 ? 31 - __clz(n1 / (sp1 ? sp1 : 1u) | 1u) : 0;
-    uint32_t r0 = 0, r1 = 0;
-    if (sp0) r0 = atomicAdd(&s_bucket[31 - b0], sp0);
-    if (sp1) r1 = atomicAdd(&s_bucket[31 - b1], sp1);
+    unsigned long long run = ex;
+    uint32_t rank[kPlanBins];
+    int bucket[kPlanBins];
+#pragma unroll
+    for (int k = 0; k < kPlanBins; ++k) {
+        if (t0 + k < B) A.bin_off[t0 + k] = ok ? static_cast<uint32_t>(run) : 0u;
+        run += n[k];
+        // work list, longest bins first (bucketed by log2 of the length): the tail of the fold is short bins
+        bucket[k] = __clz(n[k] | 1u);
+        rank[k] = (ok && n[k]) ? atomicAdd(&s_bucket[bucket[k]], 1u) : 0u;
+    }
+    if (threadIdx.x == 0) A.bin_off[B] = ok ? static_cast<uint32_t>(s_total) : 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int b = 0; b < 32; ++b) { const uint32_t c = s_bucket[b]; s_bucket[b] = run; run += c; }
-        s_bucket[32] = run;
-        const uint32_t n_items = run <= static_cast<uint32_t>(A.max_items) ? run : 0u;
-        A.out->n_items = n_items;
-        A.tickets[3] = n_items;
-        if (run > static_cast<uint32_t>(A.max_items)) A.out->overflow = 1u;      // cannot happen with max_items = 64 * T
+        uint32_t r = 0;
+        for (int b = 0; b < 32; ++b) { const uint32_t c = s_bucket[b]; s_bucket[b] = r; r += c; }
+        A.out->n_items = r;
+        A.tickets[3] = r;
     }
     __syncthreads();
-    if (s_bucket[32] > static_cast<uint32_t>(A.max_items)) return;
-    auto put = [&](int t, uint32_t n, uint32_t sp, int b, uint32_t r, uint32_t begin) {
-        const uint32_t per = L / sp;
-        for (uint32_t k = 0; k < sp; ++k) {
-            FoldItem it{};
-            it.tile = static_cast<uint32_t>(t);
-            it.lo = k * per; it.hi = (k + 1) * per;
-            it.begin = begin; it.end = begin + n;
-            A.items[s_bucket[31 - b] + r + k] = it;
+#pragma unroll
+    for (int k = 0; k < kPlanBins; ++k)
+        if (ok && n[k]) A.items[s_bucket[bucket[k]] + rank[k]] = static_cast<uint32_t>(t0 + k);
+
+    // ---- the next draw's split map: per strip its fragments now, 1 / 8 / 32 / 128 bins then (as far as kMaxBins allows)
+    const int u0 = threadIdx.x * kPlanStrips;
+    uint32_t ns[kPlanStrips];
+#pragma unroll
+    for (int k = 0; k < kPlanStrips; ++k) {
+        ns[k] = 0u;
+        if (u0 + k < A.T) {
+            const uint32_t m = A.bm.map[u0 + k], first = m & 0xffffffu, cnt = 1u << (m >> 24);
+            for (uint32_t b = 0; b < cnt; ++b) ns[k] += A.bin_total[first + b];
         }
+    }
+    auto want = [&](uint32_t frags, uint32_t cap_ls) -> uint32_t {
+        uint32_t ls = 0;
+        if (frags > A.split_at) ls = 3;
+        if (frags > 4u * A.split_at) ls = 5;
+        if (frags > 16u * A.split_at) ls = 7;
+        if (ls > static_cast<uint32_t>(A.lS)) ls = static_cast<uint32_t>(A.lS);
+        return ls < cap_ls ? ls : cap_ls;
     };
-    if (sp0) put(t0, n0, sp0, b0, r0, static_cast<uint32_t>(ex));
-    if (sp1) put(t1, n1, sp1, b1, r1, static_cast<uint32_t>(ex + n0));
+    uint32_t cap_ls = 7;
+    unsigned long long base = 0ull;
+    for (;;) {                                   // lower the finest split until the bins fit
+        unsigned long long bins = 0ull;
+#pragma unroll
+        for (int k = 0; k < kPlanStrips; ++k)
+            if (u0 + k < A.T) bins += 1ull << want(ns[k], cap_ls);
+        base = block_excl_scan64(bins, s_warp, &s_total);
+        if (s_total <= static_cast<unsigned long long>(kMaxBins) || cap_ls == 0u) break;
+        cap_ls = cap_ls > 5u ? 5u : (cap_ls > 3u ? 3u : 0u);
+    }
+    if (threadIdx.x == 0) *A.n_bins_next = static_cast<uint32_t>(s_total);
+#pragma unroll
+    for (int k = 0; k < kPlanStrips; ++k) {
+        if (u0 + k < A.T) {
+            const uint32_t ls = want(ns[k], cap_ls);
+            A.map_next[u0 + k] = static_cast<uint32_t>(base) | (ls << 24);
+            for (uint32_t sub = 0; sub < (1u << ls); ++sub)
+                A.bin_info_next[static_cast<uint32_t>(base) + sub] = static_cast<uint32_t>(u0 + k) | (sub << 16) | (ls << 24);
+            base += 1ull << ls;
+        }
+    }
+}
+
+// the identity map (one bin per strip): first draw, and after a resize
+__global__ void k_splat_map_identity(int T, uint32_t *map, uint32_t *bin_info, uint32_t *n_bins) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) { map[t] = static_cast<uint32_t>(t); bin_info[t] = static_cast<uint32_t>(t); }
+    if (t == 0) *n_bins = static_cast<uint32_t>(T);
 }
 
 // ------------------------------------------------------------------------------------------
-// Pass 3: emit.  Every fragment is computed once and stored once, at its final place: bin of its tile, draw order.
+// Pass 3: emit.  Every fragment is computed once and stored once, at its final place: its bin, draw order.
 //
-// A CTA takes a slab (ticket), and walks it in windows of kEmitThreads primitives (one per thread: load the two
-// vertices, set the line up, count its fragments).  The window's fragments are numbered in draw order by a block
-// scan ("slots") and handled in passes of at most kEmitSlots: the primitives expand their slot range into a table,
-// then the threads take the slots warp-striped -- warp w the w-th stretch, 32 consecutive slots per round -- so
-// that (warp, round, lane) order is slot order.  Rank of a fragment among those of its tile:
-//   within the round       __match_any_sync on the tile,
-//   within the warp        a per-warp counter per tile, advanced by the round's leader,
-//   across the warps       exclusive scan of those counters over the warps (one thread per tile pair),
-//   across passes/windows  a per-CTA cursor per tile, which starts at bin_off[tile] + (this slab's prefix).
+// A CTA takes a slab (ticket) and walks it in windows of kEmitThreads primitives; warp w takes primitives
+// [32w, 32w + 32) of the window, one per lane: load the two vertices, set the line up, count its fragments.  The warp's
+// fragments are numbered in draw order by a warp scan ("slots") and handled in passes of at most kEmitSlots: the lanes
+// expand their slot ranges into a table, then the lanes take the slots 32 at a time -- so that (round, lane) order is
+// draw order -- compute the fragment and find the lanes of the round that hit the same bin (__match_any_sync).
+// The slot in the bin comes from a shared-memory cursor per bin (atomicAdd by the group's first lane): the warps
+// advance the cursors strictly one after the other, warp 0, 1, ... 7, 0, ... -- a token handed on over named barriers
+// -- which is the draw order.  Only the claims are serial; computing and storing overlap between the warps.
 // ------------------------------------------------------------------------------------------
-constexpr int kEmitThreads = 512;
+constexpr int kEmitThreads = 256;
 constexpr int kEmitWarps = kEmitThreads / 32;
-constexpr int kEmitSlots = 2048;                          // slots per pass
-constexpr int kEmitRounds = kEmitSlots / kEmitThreads;    // rounds of 32 slots per warp and pass
+constexpr int kEmitRounds = 4;                            // rounds of 32 slots per pass
+constexpr int kEmitSlots = 32 * kEmitRounds;
 
 struct ScatterArgs {
     PrimSource src;
-    TileGeom g;
+    StripGeom g;
+    BinMap bm;
     float vsx, vsy, speedLimit, time;
     int slab_prims, n_slabs;
-    const uint32_t *__restrict__ slab_hist;     // scanned rows: fragments of this tile in earlier slabs
-    const uint32_t *__restrict__ bin_off;       // [T + 1] (sharded run: where this rank's fragments start in the owner's bin)
+    const uint32_t *__restrict__ slab_hist;     // scanned: fragments of this bin in earlier slabs
+    const uint32_t *__restrict__ bin_off;       // [n_bins + 1] (sharded run: where this rank's fragments start in the owner's bin)
     const PlanOut *plan;
     uint32_t *ticket;
     Frag *bins[kMaxBandRanks];                  // the bin array of every rank (single GPU: [0])
-    const uint8_t *__restrict__ tile_owner;     // null: everything goes to bins[0]
+    const uint8_t *__restrict__ bin_owner;      // null: everything goes to bins[0]
 };
 
-__host__ __device__ inline size_t scatter_smem_bytes(int T) {
-    const size_t Tp = static_cast<size_t>((T + 1) / 2);
-    return static_cast<size_t>(kEmitThreads) * 12 * 4        // primitive records (SoA)
-           + static_cast<size_t>(kEmitSlots) * 4             // slot -> (primitive, fragment) table
-           + static_cast<size_t>(kEmitWarps) * Tp * 4        // per-warp counters, two tiles per word
-           + Tp * 4                                          // per-pass totals
-           + static_cast<size_t>(T) * 4                      // cursors
-           + 64 * 4;                                         // scan scratch
-}
+constexpr size_t kScatterSmemBytes = static_cast<size_t>(kMaxBins) * 4                                   // cursors
+                                     + static_cast<size_t>(kEmitWarps) * (12 * 32 + kEmitSlots) * 4;   // per warp: primitive records (SoA), slot table
 
-__global__ void __launch_bounds__(kEmitThreads) k_splat_scatter(const ScatterArgs A) {
+// [bar-begin]  (the CPU tests swap the helpers between these markers for host equivalents)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// [bar-end]
+
+__global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const ScatterArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (A.plan->overflow) return;
-    const int T = A.g.T, Tp = (T + 1) / 2;
-    float *rec = reinterpret_cast<float *>(smem_raw);                          // [12][kEmitThreads]
-    uint32_t *owner = reinterpret_cast<uint32_t *>(rec + 12 * kEmitThreads);   // [kEmitSlots]
-    uint32_t *wh = owner + kEmitSlots;                                         // [kEmitWarps][Tp]
-    uint32_t *tot = wh + kEmitWarps * Tp;                                      // [Tp]
-    uint32_t *cur = tot + Tp;                                                  // [T]
-    uint32_t *scratch = cur + T;                                               // [64]
-    __shared__ int s_slab;
+    const int B = static_cast<int>(*A.bm.n_bins);
+    uint32_t *cur = reinterpret_cast<uint32_t *>(smem_raw);                    // [kMaxBins]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *rec = reinterpret_cast<float *>(cur + kMaxBins) + warp * (12 * 32 + kEmitSlots);    // [12][32]
+    uint32_t *owner = reinterpret_cast<uint32_t *>(rec + 12 * 32);             // [kEmitSlots]
+    __shared__ int s_slab;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const bool opaque_ok = __float_as_uint(A.time) != 0x80000000u;            // time*1 must not be -0 for the cut to be exact
 
     for (;;) {
         __syncthreads();
@@ -422,127 +526,118 @@ __global__ void __launch_bounds__(kEmitThreads) k_splat_scatter(const ScatterArg
         __syncthreads();
         const int slab = s_slab;
         if (slab >= A.n_slabs) break;
-        for (int t = tid; t < T; t += kEmitThreads) cur[t] = A.bin_off[t] + A.slab_hist[static_cast<size_t>(t) * A.n_slabs + slab];
-        for (int i = tid; i < kEmitWarps * Tp; i += kEmitThreads) wh[i] = 0u;
+        {
+            const uint32_t *row = A.slab_hist + static_cast<size_t>(slab) * kMaxBins;
+            for (int t = tid; t < B; t += kEmitThreads) cur[t] = A.bin_off[t] + row[t];
+        }
+        __syncthreads();
         const long long p0 = static_cast<long long>(slab) * A.slab_prims;
         const long long p1 = (p0 + A.slab_prims < A.src.n_prims) ? p0 + A.slab_prims : A.src.n_prims;
+        // the vertices of the next window are loaded while this one is worked on
+        float4 sa_nx = make_float4(0.f, 0.f, 0.f, 0.f), sb_nx = sa_nx;
+        if (p0 + tid < p1) load_prim(A.src, p0 + tid, sa_nx, sb_nx);
         for (long long w0 = p0; w0 < p1; w0 += kEmitThreads) {
-            // ---- window setup: one primitive per thread
+            const bool first_window = w0 == p0, last_window = w0 + kEmitThreads >= p1;
+            // ---- one primitive per lane
             const long long p = w0 + tid;
+            const float4 sa = sa_nx, sb = sb_nx;
+            if (p + kEmitThreads < p1) load_prim(A.src, p + kEmitThreads, sa_nx, sb_nx);
             uint32_t n = 0;
             if (p < p1) {
-                float4 sa, sb;
-                load_prim(A.src, p, sa, sb);
                 PrimGeom P;
                 n = prim_setup(sa, sb, A.vsx, A.vsy, A.g.W, A.g.H, P);
                 if (n) {
                     // flow(vel, speedLimit): src/flow/apply/state.glsl:5-16
                     const float aa = gmin(__fdiv_rn(glength(sa.z, sa.w), A.speedLimit), 1.0f);
                     const float ab = gmin(__fdiv_rn(glength(sb.z, sb.w), A.speedLimit), 1.0f);
-                    rec[0 * kEmitThreads + tid] = P.ma; rec[1 * kEmitThreads + tid] = P.mb;
-                    rec[2 * kEmitThreads + tid] = P.na; rec[3 * kEmitThreads + tid] = P.nb;
-                    rec[4 * kEmitThreads + tid] = __int_as_float(P.c0);
-                    rec[5 * kEmitThreads + tid] = __uint_as_float(P.flags);
-                    rec[6 * kEmitThreads + tid] = sa.z; rec[7 * kEmitThreads + tid] = sb.z;
-                    rec[8 * kEmitThreads + tid] = sa.w; rec[9 * kEmitThreads + tid] = sb.w;
-                    rec[10 * kEmitThreads + tid] = aa; rec[11 * kEmitThreads + tid] = ab;
+                    rec[0 * 32 + lane] = P.ma; rec[1 * 32 + lane] = P.mb;
+                    rec[2 * 32 + lane] = P.na; rec[3 * 32 + lane] = P.nb;
+                    rec[4 * 32 + lane] = __int_as_float(P.c0);
+                    rec[5 * 32 + lane] = __uint_as_float(P.flags);
+                    rec[6 * 32 + lane] = sa.z; rec[7 * 32 + lane] = sb.z;
+                    rec[8 * 32 + lane] = sa.w; rec[9 * 32 + lane] = sb.w;
+                    rec[10 * 32 + lane] = aa; rec[11 * 32 + lane] = ab;
                 }
             }
-            // ---- slots: exclusive scan of the counts over the window
-            uint32_t inc = warp_incl_scan(n, lane);
-            __syncthreads();                                                    // (previous window's passes are done with scratch)
-            if (lane == 31) scratch[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                const uint32_t ws = (lane < kEmitWarps) ? scratch[lane] : 0u;
-                const uint32_t wi = warp_incl_scan(ws, lane);
-                if (lane < kEmitWarps) scratch[32 + lane] = wi - ws;
-                if (lane == kEmitWarps - 1) scratch[63] = wi;
-            }
-            __syncthreads();
-            const uint32_t my_off = scratch[32 + warp] + inc - n;
-            const uint32_t n_window = scratch[63];
-            for (uint32_t s_lo = 0; s_lo < n_window; s_lo += kEmitSlots) {
-                const uint32_t cnt = (n_window - s_lo < static_cast<uint32_t>(kEmitSlots)) ? n_window - s_lo : static_cast<uint32_t>(kEmitSlots);
-                // ---- the primitives expand their slots of this pass
+            // ---- slots: exclusive scan of the counts over the warp
+            const uint32_t inc = warp_incl_scan(n, lane);
+            const uint32_t my_off = inc - n;
+            const uint32_t n_warp = __shfl_sync(0xffffffffu, inc, 31);
+            bool have_token = false;
+            // the token: warp w claims after warp w-1 of the same window, warp 0 after warp 7 of the previous window
+            auto acquire = [&]() {
+                if (warp != 0 || !first_window) named_bar_sync(1 + warp, 64);
+                have_token = true;
+            };
+            auto release = [&]() {
+                __threadfence_block();
+                const int next = (warp + 1) % kEmitWarps;
+                if (next != 0 || !last_window) named_bar_arrive(1 + next, 64);
+            };
+            for (uint32_t s_lo = 0; s_lo < n_warp; s_lo += kEmitSlots) {
+                const uint32_t cnt = (n_warp - s_lo < static_cast<uint32_t>(kEmitSlots)) ? n_warp - s_lo : static_cast<uint32_t>(kEmitSlots);
+                const bool last_pass = s_lo + kEmitSlots >= n_warp;
+                // ---- the lanes expand their slots of this pass
                 {
                     const uint32_t b = my_off > s_lo ? my_off : s_lo;
                     const uint32_t e = (my_off + n < s_lo + cnt) ? my_off + n : s_lo + cnt;
-                    for (uint32_t s = b; s < e; ++s) owner[s - s_lo] = (static_cast<uint32_t>(tid) << 20) | (s - my_off);
+                    for (uint32_t s = b; s < e; ++s) owner[s - s_lo] = (static_cast<uint32_t>(lane) << 20) | (s - my_off);
                 }
-                __syncthreads();
-                // ---- fragments, warp-striped, and their rank within the warp
-                const uint32_t per = ((cnt + kEmitWarps - 1) / kEmitWarps + 31u) & ~31u;     // slots per warp, <= kEmitRounds * 32
+                __syncwarp();
+                // ---- fragments, 32 slots per round
                 float fcx[kEmitRounds], fcy[kEmitRounds], fa[kEmitRounds];
-                uint32_t fkey[kEmitRounds], ftile[kEmitRounds], frank[kEmitRounds];
+                uint32_t fkey[kEmitRounds], fbin[kEmitRounds], fpeers[kEmitRounds];
 #pragma unroll
                 for (int r = 0; r < kEmitRounds; ++r) {
-                    const uint32_t s = warp * per + r * 32 + lane;
-                    const bool valid = static_cast<uint32_t>(r * 32) < per && s < cnt;
-                    ftile[r] = 0xffffffffu;
-                    if (static_cast<uint32_t>(r * 32) >= per || warp * per + r * 32 >= cnt) continue;   // warp-uniform
-                    if (valid) {
+                    fbin[r] = 0xffffffffu;
+                    fpeers[r] = 0u;
+                    if (static_cast<uint32_t>(r * 32) >= cnt) continue;                       // warp-uniform
+                    const uint32_t s = r * 32 + lane;
+                    if (s < cnt) {
                         const uint32_t o = owner[s];
                         const int q = static_cast<int>(o >> 20);
                         PrimGeom P;
-                        P.ma = rec[0 * kEmitThreads + q]; P.mb = rec[1 * kEmitThreads + q];
-                        P.na = rec[2 * kEmitThreads + q]; P.nb = rec[3 * kEmitThreads + q];
-                        P.c0 = __float_as_int(rec[4 * kEmitThreads + q]);
-                        P.flags = __float_as_uint(rec[5 * kEmitThreads + q]);
+                        P.ma = rec[0 * 32 + q]; P.mb = rec[1 * 32 + q];
+                        P.na = rec[2 * 32 + q]; P.nb = rec[3 * 32 + q];
+                        P.c0 = __float_as_int(rec[4 * 32 + q]);
+                        P.flags = __float_as_uint(rec[5 * 32 + q]);
                         int gx, gy; float t;
                         prim_fragment(P, o & 0xfffffu, A.g.W, A.g.H, gx, gy, t);
-                        const float za = rec[6 * kEmitThreads + q], zb = rec[7 * kEmitThreads + q];
-                        const float wa = rec[8 * kEmitThreads + q], wb = rec[9 * kEmitThreads + q];
-                        const float aa = rec[10 * kEmitThreads + q], ab = rec[11 * kEmitThreads + q];
-                        const float cx = __fadd_rn(za, __fmul_rn(t, __fsub_rn(zb, za)));
-                        const float cy = __fadd_rn(wa, __fmul_rn(t, __fsub_rn(wb, wa)));
-                        const float a = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
-                        uint32_t key = local_of(A.g, gx, gy);
-                        const bool tame = is_finite(cx) && is_finite(cy) && a >= 0.0f && a <= 1.0f;
-                        if (tame) key |= kKeyTame;
-                        if (opaque_ok && a == 1.0f && tame && __float_as_uint(cx) != 0x80000000u && __float_as_uint(cy) != 0x80000000u)
-                            key |= kKeyOpaque;
-                        fcx[r] = cx; fcy[r] = cy; fa[r] = a; fkey[r] = key;
-                        ftile[r] = static_cast<uint32_t>(tile_of(A.g, gx, gy));
+                        const float za = rec[6 * 32 + q], zb = rec[7 * 32 + q];
+                        const float wa = rec[8 * 32 + q], wb = rec[9 * 32 + q];
+                        const float aa = rec[10 * 32 + q], ab = rec[11 * 32 + q];
+                        fcx[r] = __fadd_rn(za, __fmul_rn(t, __fsub_rn(zb, za)));
+                        fcy[r] = __fadd_rn(wa, __fmul_rn(t, __fsub_rn(wb, wa)));
+                        fa[r] = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
+                        fkey[r] = local_of(A.g, gx, gy);
+                        fbin[r] = bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), fkey[r]);
                     }
-                    const uint32_t peers = __match_any_sync(0xffffffffu, ftile[r]);
-                    if (valid) {
-                        const int leader = __ffs(peers) - 1;
-                        uint32_t base = 0;
-                        const uint32_t sh = (ftile[r] & 1u) * 16u;
-                        if (lane == leader) base = (atomicAdd(&wh[warp * Tp + (ftile[r] >> 1)], static_cast<uint32_t>(__popc(peers)) << sh) >> sh) & 0xffffu;
-                        base = __shfl_sync(peers, base, leader);
-                        frank[r] = base + static_cast<uint32_t>(__popc(peers & lt_mask));
-                    }
+                    fpeers[r] = __match_any_sync(0xffffffffu, fbin[r]);
                 }
-                __syncthreads();
-                // ---- across the warps: exclusive scan of the per-warp counters, two tiles per word
-                for (int tp = tid; tp < Tp; tp += kEmitThreads) {
-                    uint32_t run = 0;
+                // ---- claim the bin slots, in draw order
+                if (!have_token) acquire();
+                uint32_t fdst[kEmitRounds];
 #pragma unroll
-                    for (int w = 0; w < kEmitWarps; ++w) {
-                        const uint32_t c = wh[w * Tp + tp];
-                        wh[w * Tp + tp] = run;
-                        run += c;
-                    }
-                    tot[tp] = run;
+                for (int r = 0; r < kEmitRounds; ++r) {
+                    if (static_cast<uint32_t>(r * 32) >= cnt) continue;                       // warp-uniform
+                    const int leader = __ffs(fpeers[r]) - 1;
+                    uint32_t base = 0;
+                    if (fbin[r] != 0xffffffffu && lane == leader) base = atomicAdd(&cur[fbin[r]], static_cast<uint32_t>(__popc(fpeers[r])));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    fdst[r] = base + static_cast<uint32_t>(__popc(fpeers[r] & lt_mask));
+                    __syncwarp();                                               // the next round's claims come after this round's
                 }
-                __syncthreads();
+                if (last_pass) release();
                 // ---- store
 #pragma unroll
                 for (int r = 0; r < kEmitRounds; ++r) {
-                    if (ftile[r] == 0xffffffffu) continue;
-                    const uint32_t tl = ftile[r], sh = (tl & 1u) * 16u;
-                    const uint32_t dst = cur[tl] + ((wh[warp * Tp + (tl >> 1)] >> sh) & 0xffffu) + frank[r];
-                    Frag *bin = A.bins[A.tile_owner ? A.tile_owner[tl] : 0];
-                    *reinterpret_cast<float4 *>(bin + dst) = make_float4(fcx[r], fcy[r], fa[r], __uint_as_float(fkey[r]));
+                    if (fbin[r] == 0xffffffffu) continue;
+                    Frag *bin = A.bins[A.bin_owner ? A.bin_owner[fbin[r]] : 0];
+                    *reinterpret_cast<float4 *>(bin + fdst[r]) = make_float4(fcx[r], fcy[r], fa[r], __uint_as_float(fkey[r]));
                 }
-                __syncthreads();
-                for (int t = tid; t < T; t += kEmitThreads) cur[t] += (tot[t >> 1] >> ((t & 1) * 16)) & 0xffffu;
-                for (int i = tid; i < kEmitWarps * Tp; i += kEmitThreads) wh[i] = 0u;
-                // (the next pass / window starts with a barrier before it touches owner, wh or cur)
-                __syncthreads();
+                __syncwarp();                                                   // the slot table is reused by the next pass
             }
+            if (n_warp == 0u) { acquire(); release(); }
         }
     }
 }
@@ -551,35 +646,43 @@ __global__ void __launch_bounds__(kEmitThreads) k_splat_scatter(const ScatterArg
 // Pass 4: fold.  blendFunc(SRC_ALPHA, ONE_MINUS_SRC_ALPHA) on all four channels in primitive order
 // (src/index.js:267-268): dst = src*a + dst*(1-a), two roundings per channel.
 //
-// A CTA takes work items (ticket): texels [lo, hi) of one tile live in shared memory while the tile's bin streams
-// through a double-buffered shared-memory window (cp.async.bulk + mbarrier).  Warp w owns an equal share of the
-// texels.  Every warp scans every chunk (one 16-byte shared load per lane and 32 fragments) and appends the
-// fragments of its texels, in order, to a small ring; whenever 32 are queued it blends them: lanes whose texels
-// differ go in parallel, lanes that share a texel (__match_any_sync) are chained in lane order = draw order, every
-// lane of the group running the same chain.  A fragment with alpha == 1 overwrites the texel: the chain starts at
-// the group's last such fragment (exact: see kKeyOpaque / kKeyTame).
+// One warp per bin (work list, longest first, ticket counter).  The bin's texels (a strip, or 16 / 4 / 1 texels of a
+// split strip) live in the warp's shared memory; the bin arrives through a double-buffered shared-memory window
+// (cp.async.bulk + mbarrier, 1 KiB per copy) and is blended 32 fragments at a time: every lane forms the
+// order-independent half of its fragment (src*a, 1-a), __match_any_sync finds the lanes that hit the same texel, and
+// the batch is applied in as many rounds as the fullest texel has fragments: round 0 blends the first fragment of every
+// texel onto the texel's value, round r blends the r-th onto what its predecessor lane produced (one shuffle), the last
+// lane of every texel stores.  Lane order = draw order is kept per texel, different texels go in parallel.  A batch
+// that piles up on few texels is chained by the first lane of each texel instead, operands staged in shared memory; there
+// a fragment with alpha == 1, which overwrites the texel, lets the chain start at the last such fragment.  Two batches
+// are in flight: the match of the second hides behind the rounds of the first.
 // ------------------------------------------------------------------------------------------
 constexpr int kFoldThreads = 256;
 constexpr int kFoldNWarps = kFoldThreads / 32;
-constexpr int kFoldChunkFrags = 2048;                    // fragments per shared-memory window (32 KiB)
-constexpr int kFoldStages = 2;
-constexpr int kFoldRing = 64;                            // queued fragments per warp
+constexpr int kFoldStage = 64;                           // fragments per bulk copy
+constexpr uint32_t kFoldRounds = 6;                      // batches whose fullest texel has more fragments are chained
 
 struct FoldArgs {
-    TileGeom g;
+    StripGeom g;
     float time;
     const Frag *__restrict__ bins;
-    const FoldItem *__restrict__ items;
+    const uint32_t *__restrict__ bin_off;    // [n_bins + 1]
+    const uint32_t *__restrict__ bin_info;   // [n_bins] strip | sub << 16 | log2(bins of the strip) << 24
+    const uint32_t *__restrict__ items;      // bins to fold
     const uint32_t *n_items;                 // device: number of work items
     uint32_t *ticket;
-    float4 *flow[kMaxBandRanks];             // [0] the grid that is read; every non-null entry is written
+    float4 *flow[kMaxBandRanks];             // [0] the grid that is read; every entry below n_flow is written
     int n_flow;
 };
 
-constexpr size_t kFoldSmemBytes = static_cast<size_t>(kFoldStages) * kFoldChunkFrags * sizeof(Frag)   // windows
-                                  + static_cast<size_t>(kFoldTexels) * sizeof(float4)                 // the tile
-                                  + static_cast<size_t>(kFoldNWarps) * kFoldRing * sizeof(Frag)       // rings
-                                  + 64;                                                               // mbarriers
+struct __align__(16) FoldWarp {             // shared memory of one warp
+    Frag stage[2][kFoldStage];
+    float4 tex[kFoldTexels];
+    float4 term[32];                         // chained batches: src*a per lane
+    float om[32];                            //                  1 - a per lane
+    unsigned long long bar[2];
+};
+constexpr size_t kFoldSmemBytes = sizeof(FoldWarp) * kFoldNWarps;
 
 // [bulk-begin]  (the CPU tests swap the helpers between these markers for plain copies)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -606,139 +709,156 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 }
 // [bulk-end]
 
-__device__ __forceinline__ void fold_batch(const Frag *ring, uint32_t head, uint32_t nb, float4 *tile, uint32_t lo, float time, int lane) {
-    const bool active = static_cast<uint32_t>(lane) < nb;
-    Frag f{};
-    if (active) f = ring[(head + lane) & (kFoldRing - 1)];
-    const uint32_t loc = active ? (f.key & kKeyLocalMask) : (0xffffff00u | static_cast<uint32_t>(lane));
+// The order-independent half of one batch: lane l holds fragment l (in draw order) if `active`.
+struct FoldPrep {
+    uint32_t rel, peers, most, cut;          // cut: lanes whose fragment overwrites the texel and may start a chain
+    float tx, ty, tz, tw, om;
+};
+__device__ __forceinline__ FoldPrep fold_prep(const Frag &f, bool active, uint32_t lo, float time, int lane) {
+    FoldPrep p;
+    p.rel = active ? (f.key & kKeyLocalMask) - lo : (0xffffff00u | static_cast<uint32_t>(lane));
     const float a = f.a;
-    const float tx = __fmul_rn(f.cx, a), ty = __fmul_rn(f.cy, a), tz = __fmul_rn(time, a), tw = __fmul_rn(a, a);
-    const float om = __fsub_rn(1.0f, a);
-    const uint32_t peers = __match_any_sync(0xffffffffu, loc);
-    const uint32_t opq = __ballot_sync(0xffffffffu, active && (f.key & kKeyOpaque)) & peers;
-    const uint32_t wild = __ballot_sync(0xffffffffu, active && !(f.key & kKeyTame)) & peers;
-    uint32_t rem = peers;
-    if (opq) {
-        const uint32_t below = (1u << (31 - __clz(opq))) - 1u;      // lanes before the group's last opaque fragment
-        if ((wild & below) == 0u) rem = peers & ~below;
-    }
-    const uint32_t cnt = static_cast<uint32_t>(__popc(rem));
-    const bool shared = __any_sync(0xffffffffu, (peers & (peers - 1u)) != 0u);   // some texel has more than one fragment here
-    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) d = tile[loc - lo];
-    if (!shared) {
-        d.x = __fadd_rn(tx, __fmul_rn(d.x, om)); d.y = __fadd_rn(ty, __fmul_rn(d.y, om));
-        d.z = __fadd_rn(tz, __fmul_rn(d.z, om)); d.w = __fadd_rn(tw, __fmul_rn(d.w, om));
-    } else {
-        const uint32_t longest = __reduce_max_sync(0xffffffffu, cnt);
-        for (uint32_t s = 0; s < longest; ++s) {
-            const int j = rem ? __ffs(rem) - 1 : lane;
-            const bool step = rem != 0u;
-            rem &= rem - 1u;
-            const float sx = __shfl_sync(0xffffffffu, tx, j), sy = __shfl_sync(0xffffffffu, ty, j);
-            const float sz = __shfl_sync(0xffffffffu, tz, j), sw = __shfl_sync(0xffffffffu, tw, j);
-            const float sm = __shfl_sync(0xffffffffu, om, j);
-            if (step) {
-                d.x = __fadd_rn(sx, __fmul_rn(d.x, sm)); d.y = __fadd_rn(sy, __fmul_rn(d.y, sm));
-                d.z = __fadd_rn(sz, __fmul_rn(d.z, sm)); d.w = __fadd_rn(sw, __fmul_rn(d.w, sm));
-            }
+    p.tx = __fmul_rn(f.cx, a); p.ty = __fmul_rn(f.cy, a); p.tz = __fmul_rn(time, a); p.tw = __fmul_rn(a, a);
+    p.om = __fsub_rn(1.0f, a);
+    p.peers = __match_any_sync(0xffffffffu, p.rel);
+    p.most = __reduce_max_sync(0xffffffffu, static_cast<uint32_t>(__popc(p.peers)));
+    p.cut = 0u;
+    if (p.most > kFoldRounds) {
+        // alpha == 1: dst = c*1 + dst*0 = c + (+-0) = c for every finite dst unless c is -0, and NaN for a non-finite dst
+        // whatever was blended before (a finite, in-range fragment never makes a non-finite texel finite or a finite one
+        // non-finite): starting the chain at such a fragment, on the texel's value as it was, is exact provided every
+        // skipped fragment is finite with 0 <= a <= 1.
+        const bool tame = is_finite(f.cx) && is_finite(f.cy) && a >= 0.0f && a <= 1.0f;
+        const bool opaque = tame && a == 1.0f && __float_as_uint(f.cx) != 0x80000000u && __float_as_uint(f.cy) != 0x80000000u &&
+                            __float_as_uint(time) != 0x80000000u;
+        const uint32_t opq = __ballot_sync(0xffffffffu, active && opaque) & p.peers;
+        const uint32_t wild = __ballot_sync(0xffffffffu, active && !tame) & p.peers;
+        if (opq) {
+            const uint32_t below = (1u << (31 - __clz(opq))) - 1u;      // lanes before the group's last opaque fragment
+            if ((wild & below) == 0u) p.cut = below;
         }
     }
-    if (active && lane == __ffs(peers) - 1) tile[loc - lo] = d;
+    return p;
+}
+
+__device__ __forceinline__ void fold_apply(FoldWarp &W, const FoldPrep &p, bool active, int lane) {
+    const uint32_t before = p.peers & ((1u << lane) - 1u);
+    const uint32_t rank = static_cast<uint32_t>(__popc(before));
+    if (p.most <= kFoldRounds) {
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) d = W.tex[p.rel];
+        d.x = __fadd_rn(p.tx, __fmul_rn(d.x, p.om)); d.y = __fadd_rn(p.ty, __fmul_rn(d.y, p.om));
+        d.z = __fadd_rn(p.tz, __fmul_rn(d.z, p.om)); d.w = __fadd_rn(p.tw, __fmul_rn(d.w, p.om));
+        const int pred = before ? 31 - __clz(before) : lane;            // the lane with the previous fragment of my texel
+        for (uint32_t r = 1; r < p.most; ++r) {
+            const float px = __shfl_sync(0xffffffffu, d.x, pred), py = __shfl_sync(0xffffffffu, d.y, pred);
+            const float pz = __shfl_sync(0xffffffffu, d.z, pred), pw = __shfl_sync(0xffffffffu, d.w, pred);
+            if (rank == r) {
+                d.x = __fadd_rn(p.tx, __fmul_rn(px, p.om)); d.y = __fadd_rn(p.ty, __fmul_rn(py, p.om));
+                d.z = __fadd_rn(p.tz, __fmul_rn(pz, p.om)); d.w = __fadd_rn(p.tw, __fmul_rn(pw, p.om));
+            }
+        }
+        if (active && (p.peers >> lane) == 1u) W.tex[p.rel] = d;        // the last fragment of the texel in this batch
+    } else {
+        W.term[lane] = make_float4(p.tx, p.ty, p.tz, p.tw);
+        W.om[lane] = p.om;
+        __syncwarp();
+        if (active && rank == 0u) {
+            float4 d = W.tex[p.rel];
+            uint32_t rem = p.peers & ~p.cut;
+            while (rem) {
+                // two steps per trip: the operand loads do not depend on d
+                const int j0 = __ffs(rem) - 1;
+                rem &= rem - 1u;
+                const int j1 = rem ? __ffs(rem) - 1 : j0;
+                const bool two = rem != 0u;
+                rem &= rem - 1u;
+                const float4 v0 = W.term[j0], v1 = W.term[j1];
+                const float m0 = W.om[j0], m1 = W.om[j1];
+                d.x = __fadd_rn(v0.x, __fmul_rn(d.x, m0)); d.y = __fadd_rn(v0.y, __fmul_rn(d.y, m0));
+                d.z = __fadd_rn(v0.z, __fmul_rn(d.z, m0)); d.w = __fadd_rn(v0.w, __fmul_rn(d.w, m0));
+                if (two) {
+                    d.x = __fadd_rn(v1.x, __fmul_rn(d.x, m1)); d.y = __fadd_rn(v1.y, __fmul_rn(d.y, m1));
+                    d.z = __fadd_rn(v1.z, __fmul_rn(d.z, m1)); d.w = __fadd_rn(v1.w, __fmul_rn(d.w, m1));
+                }
+            }
+            W.tex[p.rel] = d;
+        }
+    }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kFoldThreads) k_splat_fold(const FoldArgs A) {
+__global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Frag *win = reinterpret_cast<Frag *>(smem_raw);                                             // [kFoldStages][kFoldChunkFrags]
-    float4 *tile = reinterpret_cast<float4 *>(win + kFoldStages * kFoldChunkFrags);            // [kFoldTexels]
-    Frag *rings = reinterpret_cast<Frag *>(tile + kFoldTexels);                                 // [kFoldNWarps][kFoldRing]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(rings + kFoldNWarps * kFoldRing);   // [kFoldStages]
-    __shared__ uint32_t s_item;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    FoldWarp &W = reinterpret_cast<FoldWarp *>(smem_raw)[warp];
+    const uint32_t S = 1u << (A.g.sxl + A.g.syl);
     const uint32_t n_items = *A.n_items;
-    if (tid == 0) {
-        for (int s = 0; s < kFoldStages; ++s) mbar_init(&bars[s], 1u);
+    if (lane == 0) {
+        mbar_init(&W.bar[0], 1u);
+        mbar_init(&W.bar[1], 1u);
         mbar_fence_init();
     }
-    uint32_t phase[kFoldStages];
-#pragma unroll
-    for (int s = 0; s < kFoldStages; ++s) phase[s] = 0u;
-    Frag *ring = rings + warp * kFoldRing;
+    __syncwarp();
+    uint32_t phase0 = 0u, phase1 = 0u;
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = atomicAdd(A.ticket, 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(A.ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const FoldItem it = A.items[item];
-        const int tile_x = static_cast<int>(it.tile) % A.g.tiles_x, tile_y = static_cast<int>(it.tile) / A.g.tiles_x;
-        const int gx0 = tile_x << A.g.txl, gy0 = tile_y << A.g.tyl;
-        const uint32_t span = it.hi - it.lo;
-        const uint32_t n = it.end - it.begin, n_chunks = (n + kFoldChunkFrags - 1) / kFoldChunkFrags;
-        const Frag *bin = A.bins + it.begin;
-        auto issue = [&](uint32_t k) {
-            const uint32_t c = (n - k * kFoldChunkFrags < static_cast<uint32_t>(kFoldChunkFrags)) ? n - k * kFoldChunkFrags : static_cast<uint32_t>(kFoldChunkFrags);
-            bulk_load(win + (k % kFoldStages) * kFoldChunkFrags, bin + static_cast<size_t>(k) * kFoldChunkFrags, c * static_cast<uint32_t>(sizeof(Frag)),
-                      &bars[k % kFoldStages]);
+        const uint32_t bin_id = A.items[item];
+        const uint32_t code = A.bin_info[bin_id];
+        const uint32_t st = code & 0xffffu, sub = (code >> 16) & 0xffu, ls = code >> 24;
+        const uint32_t R = S >> ls, lo = sub * R;                     // the bin's texels: local indices [lo, lo + R)
+        const uint32_t begin = A.bin_off[bin_id], n = A.bin_off[bin_id + 1] - begin;
+        const uint32_t n_stage = (n + kFoldStage - 1) / kFoldStage;
+        const Frag *bin = A.bins + begin;
+        auto issue = [&](uint32_t j) {
+            const uint32_t c = (n - j * kFoldStage < static_cast<uint32_t>(kFoldStage)) ? n - j * kFoldStage : static_cast<uint32_t>(kFoldStage);
+            bulk_load(W.stage[j & 1u], bin + static_cast<size_t>(j) * kFoldStage, c * static_cast<uint32_t>(sizeof(Frag)), &W.bar[j & 1u]);
         };
-        if (tid == 0)
-            for (uint32_t k = 0; k < kFoldStages && k < n_chunks; ++k) issue(k);
-        // the tile's texels [lo, hi)
-        for (uint32_t l = it.lo + tid; l < it.hi; l += kFoldThreads) {
-            const int gx = gx0 + static_cast<int>(l & ((1u << A.g.txl) - 1u)), gy = gy0 + static_cast<int>(l >> A.g.txl);
+        if (lane == 0) {
+            if (n_stage > 0) issue(0);
+            if (n_stage > 1) issue(1);
+        }
+        const int gx0 = (static_cast<int>(st) % A.g.strips_x) << A.g.sxl, gy0 = (static_cast<int>(st) / A.g.strips_x) << A.g.syl;
+        for (uint32_t l = lane; l < R; l += 32) {
+            const uint32_t loc = lo + l;
+            const int gx = gx0 + static_cast<int>(loc & ((1u << A.g.sxl) - 1u)), gy = gy0 + static_cast<int>(loc >> A.g.sxl);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gx < A.g.W && gy < A.g.H) v = A.flow[0][static_cast<size_t>(gy) * A.g.W + gx];
-            tile[l - it.lo] = v;
+            W.tex[l] = v;
         }
-        __syncthreads();
-        // this warp's texels: [wlo, wlo + wspan)
-        const uint32_t wspan = (span + kFoldNWarps - 1) / kFoldNWarps;
-        const uint32_t wlo = it.lo + warp * wspan;
-        uint32_t head = 0, queued = 0;
-        for (uint32_t k = 0; k < n_chunks; ++k) {
-            const int st = static_cast<int>(k % kFoldStages);
-            const uint32_t c = (n - k * kFoldChunkFrags < static_cast<uint32_t>(kFoldChunkFrags)) ? n - k * kFoldChunkFrags : static_cast<uint32_t>(kFoldChunkFrags);
-            mbar_wait(&bars[st], phase[st]);
-            phase[st] ^= 1u;
-            const Frag *buf = win + st * kFoldChunkFrags;
-            for (uint32_t i0 = 0; i0 < c; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                Frag f{};
-                bool mine = false;
-                if (i < c) {
-                    f = buf[i];
-                    const uint32_t loc = f.key & kKeyLocalMask;
-                    mine = (loc - wlo) < wspan && loc < it.hi;
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, mine);
-                if (m == 0u) continue;
-                if (mine) ring[(head + queued + static_cast<uint32_t>(__popc(m & lt_mask))) & (kFoldRing - 1)] = f;
-                queued += static_cast<uint32_t>(__popc(m));
-                if (queued >= 32u) {
-                    __syncwarp();
-                    fold_batch(ring, head, 32u, tile, it.lo, A.time, lane);
-                    head = (head + 32u) & (kFoldRing - 1);
-                    queued -= 32u;
-                }
+        __syncwarp();
+        for (uint32_t j = 0; j < n_stage; ++j) {
+            const uint32_t s = j & 1u;
+            const uint32_t c = (n - j * kFoldStage < static_cast<uint32_t>(kFoldStage)) ? n - j * kFoldStage : static_cast<uint32_t>(kFoldStage);
+            if (s == 0u) { mbar_wait(&W.bar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&W.bar[1], phase1); phase1 ^= 1u; }
+            Frag f0{0.f, 0.f, 0.f, 0u}, f1{0.f, 0.f, 0.f, 0u};
+            const bool a0 = static_cast<uint32_t>(lane) < c, a1 = static_cast<uint32_t>(32 + lane) < c;
+            if (a0) f0 = W.stage[s][lane];
+            if (a1) f1 = W.stage[s][32 + lane];
+            const FoldPrep p0 = fold_prep(f0, a0, lo, A.time, lane);
+            if (c > 32u) {
+                const FoldPrep p1 = fold_prep(f1, a1, lo, A.time, lane);
+                fold_apply(W, p0, a0, lane);
+                fold_apply(W, p1, a1, lane);
+            } else {
+                fold_apply(W, p0, a0, lane);
             }
-            __syncthreads();                                         // every warp is done with this window
-            if (tid == 0 && k + kFoldStages < n_chunks) issue(k + kFoldStages);
+            // (fold_apply ends with __syncwarp: every lane is done with this window)
+            if (lane == 0 && j + 2 < n_stage) issue(j + 2);
         }
-        if (queued) {
-            __syncwarp();
-            fold_batch(ring, head, queued, tile, it.lo, A.time, lane);
-        }
-        __syncthreads();
-        for (uint32_t l = it.lo + tid; l < it.hi; l += kFoldThreads) {
-            const int gx = gx0 + static_cast<int>(l & ((1u << A.g.txl) - 1u)), gy = gy0 + static_cast<int>(l >> A.g.txl);
+        for (uint32_t l = lane; l < R; l += 32) {
+            const uint32_t loc = lo + l;
+            const int gx = gx0 + static_cast<int>(loc & ((1u << A.g.sxl) - 1u)), gy = gy0 + static_cast<int>(loc >> A.g.sxl);
             if (gx < A.g.W && gy < A.g.H) {
-                const float4 v = tile[l - it.lo];
+                const float4 v = W.tex[l];
                 const size_t at = static_cast<size_t>(gy) * A.g.W + gx;
                 for (int r = 0; r < A.n_flow; ++r) A.flow[r][at] = v;
             }
         }
+        __syncwarp();
     }
 }
 

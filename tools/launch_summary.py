@@ -1,12 +1,14 @@
-import csv,collections,sys
-with open(sys.argv[1]) as f:
-    lines=[l for l in f if not l.startswith('==')]
-r=csv.DictReader(lines)
-agg=collections.OrderedDict()
-for row in r:
-    if row.get('Metric Name')=='gpu__time_duration.sum':
-        v=float(row['Metric Value'].replace(',',''))
-        agg.setdefault(row['Kernel Name'][:70],[]).append(v)
-tot=sum(sum(v[-4:]) for v in agg.values())
-for k,v in agg.items():
-    print('%-72s n=%3d last4 avg %10.1f us  share %5.1f%%'%(k,len(v),sum(v[-4:])/len(v[-4:])/1e3, 100*sum(v[-4:])/tot))
+"""Per-kernel summary of an ncu launch list (--csv --metrics gpu__time_duration.sum[,smsp__inst_executed.sum])."""
+import collections
+import csv
+import sys
+
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
+t, n = collections.defaultdict(list), collections.defaultdict(list)
+for r in rows:
+    (t if r[-3] == "gpu__time_duration.sum" else n)[r[4]].append(float(r[-1].replace(",", "")))
+tot = sum(sum(v) for v in t.values())
+for k, v in t.items():
+    inst = n.get(k)
+    extra = f"  inst {sum(inst) / len(inst):12.4g}" if inst else ""
+    print(f"{k[:60]:60s} n={len(v):3d} mean={sum(v) / len(v) / 1e3:9.1f} us  min={min(v) / 1e3:9.1f} max={max(v) / 1e3:9.1f}  share={100 * sum(v) / tot:5.1f}%{extra}")
