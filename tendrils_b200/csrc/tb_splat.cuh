@@ -31,7 +31,7 @@ namespace tb {
 // Geometry of the binning: strips of (1 << sxl) x (1 << syl) texels, at most kFoldTexels each.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxStrips = 8192;
-constexpr int kMaxBins = 12288;           // bins per grid: k_splat_scatter keeps one cursor per bin in shared memory
+constexpr int kMaxBins = 11264;           // bins per grid: k_splat_scatter keeps one cursor per bin in shared memory
 constexpr int kFoldTexels = 128;          // texels of a strip = the most one warp of k_splat_fold holds
 constexpr int kHistSegs = 16;             // the slabs are scanned in this many segments (k_splat_rows)
 constexpr uint32_t kKeyLocalMask = 0x000fffffu;
@@ -484,7 +484,8 @@ __global__ void k_splat_map_identity(int T, uint32_t *map, uint32_t *bin_info, u
 // ------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 constexpr int kEmitWarps = kEmitThreads / 32;
-constexpr int kEmitRounds = 4;                            // rounds of 32 slots per pass
+constexpr int kEmitRounds = 5;                            // rounds of 32 slots per pass (a warp holds the token while it works
+                                                          // on a second pass: the slots should cover 32 lines almost always)
 constexpr int kEmitSlots = 32 * kEmitRounds;
 
 struct ScatterArgs {
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
                 __syncwarp();
                 // ---- fragments, 32 slots per round
                 float fcx[kEmitRounds], fcy[kEmitRounds], fa[kEmitRounds];
-                uint32_t fkey[kEmitRounds], fbin[kEmitRounds], fpeers[kEmitRounds];
+                uint32_t fbin[kEmitRounds], fpeers[kEmitRounds];                             // fbin: bin | texel index << 16
 #pragma unroll
                 for (int r = 0; r < kEmitRounds; ++r) {
                     fbin[r] = 0xffffffffu;
@@ -609,10 +610,10 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
                         fcx[r] = __fadd_rn(za, __fmul_rn(t, __fsub_rn(zb, za)));
                         fcy[r] = __fadd_rn(wa, __fmul_rn(t, __fsub_rn(wb, wa)));
                         fa[r] = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
-                        fkey[r] = local_of(A.g, gx, gy);
-                        fbin[r] = bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), fkey[r]);
+                        const uint32_t loc = local_of(A.g, gx, gy);
+                        fbin[r] = bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), loc) | (loc << 16);
                     }
-                    fpeers[r] = __match_any_sync(0xffffffffu, fbin[r]);
+                    fpeers[r] = __match_any_sync(0xffffffffu, fbin[r] & 0xffffu);
                 }
                 // ---- claim the bin slots, in draw order
                 if (!have_token) acquire();
@@ -622,7 +623,7 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
                     if (static_cast<uint32_t>(r * 32) >= cnt) continue;                       // warp-uniform
                     const int leader = __ffs(fpeers[r]) - 1;
                     uint32_t base = 0;
-                    if (fbin[r] != 0xffffffffu && lane == leader) base = atomicAdd(&cur[fbin[r]], static_cast<uint32_t>(__popc(fpeers[r])));
+                    if (fbin[r] != 0xffffffffu && lane == leader) base = atomicAdd(&cur[fbin[r] & 0xffffu], static_cast<uint32_t>(__popc(fpeers[r])));
                     base = __shfl_sync(0xffffffffu, base, leader);
                     fdst[r] = base + static_cast<uint32_t>(__popc(fpeers[r] & lt_mask));
                     __syncwarp();                                               // the next round's claims come after this round's
@@ -632,8 +633,8 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
 #pragma unroll
                 for (int r = 0; r < kEmitRounds; ++r) {
                     if (fbin[r] == 0xffffffffu) continue;
-                    Frag *bin = A.bins[A.bin_owner ? A.bin_owner[fbin[r]] : 0];
-                    *reinterpret_cast<float4 *>(bin + fdst[r]) = make_float4(fcx[r], fcy[r], fa[r], __uint_as_float(fkey[r]));
+                    Frag *bin = A.bins[A.bin_owner ? A.bin_owner[fbin[r] & 0xffffu] : 0];
+                    *reinterpret_cast<float4 *>(bin + fdst[r]) = make_float4(fcx[r], fcy[r], fa[r], __uint_as_float(fbin[r] >> 16));
                 }
                 __syncwarp();                                                   // the slot table is reused by the next pass
             }
