@@ -615,23 +615,24 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
                     }
                     fpeers[r] = __match_any_sync(0xffffffffu, fbin[r] & 0xffffu);
                 }
-                // ---- claim the bin slots, in draw order
+                // ---- claim the bin slots, in draw order.  This is the serial section of the CTA: the rounds' atomics are issued back
+                // to back (one warp's shared-memory atomics execute in program order, which is the round order) and the token moves
+                // on before the results are even looked at.
                 if (!have_token) acquire();
                 uint32_t fdst[kEmitRounds];
 #pragma unroll
                 for (int r = 0; r < kEmitRounds; ++r) {
+                    fdst[r] = 0u;
                     if (static_cast<uint32_t>(r * 32) >= cnt) continue;                       // warp-uniform
-                    const int leader = __ffs(fpeers[r]) - 1;
-                    uint32_t base = 0;
-                    if (fbin[r] != 0xffffffffu && lane == leader) base = atomicAdd(&cur[fbin[r] & 0xffffu], static_cast<uint32_t>(__popc(fpeers[r])));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    fdst[r] = base + static_cast<uint32_t>(__popc(fpeers[r] & lt_mask));
-                    __syncwarp();                                               // the next round's claims come after this round's
+                    if (fbin[r] != 0xffffffffu && lane == __ffs(fpeers[r]) - 1)
+                        fdst[r] = atomicAdd(&cur[fbin[r] & 0xffffu], static_cast<uint32_t>(__popc(fpeers[r])));
                 }
                 if (last_pass) release();
                 // ---- store
 #pragma unroll
                 for (int r = 0; r < kEmitRounds; ++r) {
+                    if (static_cast<uint32_t>(r * 32) >= cnt) continue;                       // warp-uniform
+                    fdst[r] = __shfl_sync(0xffffffffu, fdst[r], __ffs(fpeers[r]) - 1) + static_cast<uint32_t>(__popc(fpeers[r] & lt_mask));
                     if (fbin[r] == 0xffffffffu) continue;
                     Frag *bin = A.bins[A.bin_owner ? A.bin_owner[fbin[r] & 0xffffu] : 0];
                     *reinterpret_cast<float4 *>(bin + fdst[r]) = make_float4(fcx[r], fcy[r], fa[r], __uint_as_float(fbin[r] >> 16));
