@@ -155,6 +155,21 @@ int tb_splat_flow(tb_ctx *ctx, float time);
 int tb_splat_collect(tb_ctx *ctx, float time);
 int tb_splat_fold(tb_ctx *ctx);
 
+/* The flow half of draw() for a column-sharded run over peer memory (one process per GPU, one node, at most 16 ranks).
+ * The fragment bins are owned round-robin by the ranks.  Every rank exports IPC handles of its bin array / flow grid /
+ * totals table / flags (tb_owners_export; `reserve_fragments` fixes the capacity of the bin array, which the other ranks
+ * map -- a draw that needs more fails with TB_ERR_OVERFLOW on every rank alike), the host layer all-gathers the blobs, and
+ * each rank maps all of them (tb_owners_connect, `all_handles` = world x tb_owners_handle_bytes(), rank order).  Then
+ * tb_splat_flow_owners replaces tb_splat_flow: count, exchange the per-bin totals, rasterise straight into the owners' bins
+ * over NVLink (per bin the ranks side by side in rank order = column order = the reference's primitive order,
+ * src/particles.js:182-186), fold the bins this rank owns, store the finished texels into every rank's grid; three
+ * all-rank barriers per draw, all inside the CUDA stream.  Equal to the single-context draw bit for bit.  Must be redone
+ * after tb_resize_flow. */
+int64_t tb_owners_handle_bytes(void);
+int tb_owners_export(tb_ctx *ctx, int64_t reserve_fragments, void *handles_out, int64_t n_bytes);
+int tb_owners_connect(tb_ctx *ctx, int32_t rank, int32_t world, const void *all_handles, int64_t n_bytes);
+int tb_splat_flow_owners(tb_ctx *ctx, float time);
+
 /* Tendrils.spawn(cpuFn) with the default initSpawner: fills ALL buffers
  * (src/index.js:425-429, src/particles.js:94-117, src/spawn/init/cpu.js:3-8). */
 int tb_reset(tb_ctx *ctx);

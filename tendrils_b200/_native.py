@@ -59,6 +59,10 @@ SYMBOLS = {
     "tb_splat_flow": (C.c_int, [_ctx, C.c_float]),
     "tb_splat_collect": (C.c_int, [_ctx, C.c_float]),
     "tb_splat_fold": (C.c_int, [_ctx]),
+    "tb_owners_handle_bytes": (C.c_int64, []),
+    "tb_owners_export": (C.c_int, [_ctx, C.c_int64, C.c_void_p, C.c_int64]),
+    "tb_owners_connect": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "tb_splat_flow_owners": (C.c_int, [_ctx, C.c_float]),
     "tb_reset": (C.c_int, [_ctx]),
     "tb_spawn_init": (C.c_int, [_ctx, C.c_int]),
     "tb_spawn_ball": (C.c_int, [_ctx, C.c_float, C.c_float, C.c_int]),

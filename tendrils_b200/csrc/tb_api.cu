@@ -5,6 +5,7 @@
 // buffers, the logic pass, the flow splat, the spawn passes.  No CPU fallback.
 #include "tb_kernels.cuh"
 #include "tb_splat.cuh"
+#include "tb_owners.cuh"
 #include "tb_flowline.cuh"
 
 #include <algorithm>
@@ -77,8 +78,19 @@ struct tb_ctx {
     Frag *bins = nullptr;                  // every fragment of a draw, binned by tile, draw order inside a bin
     uint32_t bin_cap = 0;
     bool bin_fixed = false;                // the bin array is mapped by other ranks: it cannot grow without a reconnect
+    // column-sharded run over peer memory (tb_owners.cuh): every rank maps every rank's bins, grid, totals table, flags
+    bool owners_connected = false;
+    int ow_rank = 0, ow_world = 1;
+    uint32_t ow_epoch = 0;
+    uint32_t *ow_flags = nullptr;          // [kOwnerPhases][kMaxBandRanks] the epoch each rank has reached
+    uint32_t *ow_totals = nullptr;         // [kMaxBandRanks][kMaxBins] every rank's fragments per bin, written by the ranks themselves
+    OwnerPeers ow_peers{};
+    Frag *ow_bins[kMaxBandRanks] = {};
+    float4 *ow_flow[kMaxBandRanks] = {};
+    uint32_t ow_caps[kMaxBandRanks] = {};
+    uint32_t *ow_scratch = nullptr;        // [4][kMaxBins]: bin_sum, scat_off, own_begin, own_count
     bool pending = false;                  // a draw is queued whose capacity check has not been read yet
-    int pending_stage = 0;                 // 1: collect only, 2: collect + fold
+    int pending_stage = 0;                 // 1: collect only, 2: collect + fold, 3: the sharded draw
     float pending_time = 0.f;
     bool collected = false;
     float collect_time = 0.f;
@@ -244,7 +256,7 @@ int ensure_bin_cap(tb_ctx *c, uint64_t need) {
         return fail(c, TB_ERR_OVERFLOW, "tendrils-b200: flow splat: " + std::to_string(need) + " fragments in one draw (limit 2^31)");
     if (c->bin_fixed)
         return fail(c, TB_ERR_OVERFLOW, "tendrils-b200: flow splat: " + std::to_string(need) + " fragments exceed the " +
-                    std::to_string(c->bin_cap) + " reserved by tb_tiles_export (the bins are mapped by the other ranks); "
+                    std::to_string(c->bin_cap) + " reserved by tb_owners_export (the bins are mapped by the other ranks); "
                     "export with a larger reserve and reconnect");
     uint64_t cap = std::max<uint64_t>(need + need / 4, 1u << 16);
     if (cap >= (1ull << 31)) cap = (1ull << 31) - 1;
@@ -293,11 +305,9 @@ BinMap bin_map(tb_ctx *c, int parity) {
     return M;
 }
 
-int launch_collect(tb_ctx *c, float time) {
-    const int T = c->geom.T;
+// fragments per bin of this context's primitives (k_splat_hist + k_splat_rows) under split map `mp`
+int launch_count(tb_ctx *c, int mp) {
     cudaEvent_t *stage = c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots];
-    const int mp = c->map_parity;                  // this draw's split map; its plan writes the other one for the next draw
-    c->map_parity ^= 1;
     if (c->n_prims > 0) {
         uint32_t *seg_now = c->seg_total + static_cast<size_t>(c->seg_parity) * kHistSegs * kMaxBins;
         uint32_t *seg_next = c->seg_total + static_cast<size_t>(c->seg_parity ^ 1) * kHistSegs * kMaxBins;
@@ -320,6 +330,35 @@ int launch_collect(tb_ctx *c, float time) {
     } else {
         TB_CUDA(c, cudaMemsetAsync(c->bin_total, 0, static_cast<size_t>(kMaxBins) * sizeof(uint32_t), c->stream));
     }
+    return TB_OK;
+}
+
+int launch_scatter(tb_ctx *c, float time, int mp, const uint32_t *bin_off, Frag *const *bins, int n_ranks) {
+    if (c->n_prims <= 0) return TB_OK;
+    ScatterArgs SA{};
+    SA.src = prim_source(c);
+    SA.g = c->geom;
+    SA.bm = bin_map(c, mp);
+    SA.vsx = c->state.viewSize[0]; SA.vsy = c->state.viewSize[1];
+    SA.speedLimit = c->state.speedLimit;
+    SA.time = time;
+    SA.slab_prims = c->slab_prims; SA.n_slabs = c->n_slabs;
+    SA.slab_hist = c->slab_hist;
+    SA.bin_off = bin_off;
+    SA.plan = c->d_plan;
+    SA.ticket = c->tickets + 1;
+    for (int r = 0; r < n_ranks; ++r) SA.bins[r] = bins[r];
+    SA.n_ranks = n_ranks;
+    k_splat_scatter<<<std::min(c->n_slabs, c->scatter_ctas), kEmitThreads, kScatterSmemBytes, c->stream>>>(SA);
+    return check_launch(c, "k_splat_scatter");
+}
+
+int launch_collect(tb_ctx *c, float time) {
+    const int T = c->geom.T;
+    cudaEvent_t *stage = c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots];
+    const int mp = c->map_parity;                  // this draw's split map; its plan writes the other one for the next draw
+    c->map_parity ^= 1;
+    if (int r = launch_count(c, mp)) return r;
     PlanArgs PA{};
     PA.T = T;
     PA.lS = c->geom.sxl + c->geom.syl;
@@ -341,24 +380,8 @@ int launch_collect(tb_ctx *c, float time) {
     TB_CUDA(c, cudaMemcpyAsync(c->h_plan, c->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, c->stream));
     TB_CUDA(c, cudaEventRecord(c->ev_plan, c->stream));
     if (c->stage_timing) cudaEventRecord(stage[2], c->stream);
-    if (c->n_prims > 0) {
-        ScatterArgs SA{};
-        SA.src = prim_source(c);
-        SA.g = c->geom;
-        SA.bm = bin_map(c, mp);
-        SA.vsx = c->state.viewSize[0]; SA.vsy = c->state.viewSize[1];
-        SA.speedLimit = c->state.speedLimit;
-        SA.time = time;
-        SA.slab_prims = c->slab_prims; SA.n_slabs = c->n_slabs;
-        SA.slab_hist = c->slab_hist;
-        SA.bin_off = c->bin_off;
-        SA.plan = c->d_plan;
-        SA.ticket = c->tickets + 1;
-        SA.bins[0] = c->bins;
-        SA.bin_owner = nullptr;
-        k_splat_scatter<<<std::min(c->n_slabs, c->scatter_ctas), kEmitThreads, kScatterSmemBytes, c->stream>>>(SA);
-        if (int r = check_launch(c, "k_splat_scatter")) return r;
-    }
+    Frag *one[1] = {c->bins};
+    if (int r = launch_scatter(c, time, mp, c->bin_off, one, 1)) return r;
     if (c->stage_timing) cudaEventRecord(stage[3], c->stream);
     c->fold_parity = mp;
     return TB_OK;
@@ -370,6 +393,7 @@ int launch_fold(tb_ctx *c, float time) {
     FA.time = time;
     FA.bins = c->bins;
     FA.bin_off = c->bin_off;
+    FA.bin_count = nullptr;
     FA.bin_info = c->bin_info + static_cast<size_t>(c->fold_parity) * kMaxBins;
     FA.items = c->items;
     FA.n_items = c->tickets + 3;
@@ -380,7 +404,10 @@ int launch_fold(tb_ctx *c, float time) {
     return check_launch(c, "k_splat_fold");
 }
 
+int queue_owners(tb_ctx *c, float time);
+
 int queue_splat(tb_ctx *c, float time, int stage) {
+    if (stage == 3) return queue_owners(c, time);
     cudaEvent_t *ev = c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots];
     if (stage >= 1) {
         TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
@@ -407,10 +434,10 @@ int resolve_pending(tb_ctx *c) {
             c->pending = false;
             return TB_OK;
         }
-        if (int r = ensure_bin_cap(c, c->h_plan->total)) { c->pending = false; c->collected = false; return r; }
-        if (c->pending_stage == 2) c->ev_count[1] -= 1;              // the retry re-records the same timing slot
+        if (int r = ensure_bin_cap(c, c->h_plan->needed)) { c->pending = false; c->collected = false; return r; }
+        if (c->pending_stage >= 2) c->ev_count[1] -= 1;              // the retry re-records the same timing slot
         const int r = queue_splat(c, c->pending_time, c->pending_stage);
-        if (c->pending_stage == 2) c->ev_count[1] += 1;
+        if (c->pending_stage >= 2) c->ev_count[1] += 1;
         if (r) { c->pending = false; return r; }
     }
     c->pending = false;
@@ -481,7 +508,83 @@ int after_targets_write(tb_ctx *c, tb_target target) {
 
 bool tame(float v, float lim) { return std::isfinite(v) && std::fabs(v) < lim; }
 
-int tiles_release(tb_ctx *) { return TB_OK; }
+int tiles_release(tb_ctx *c) {
+    for (int j = 0; j < kMaxBandRanks; ++j) {
+        if (c->owners_connected && j != c->ow_rank) {
+            if (c->ow_bins[j]) cudaIpcCloseMemHandle(c->ow_bins[j]);
+            if (c->ow_flow[j]) cudaIpcCloseMemHandle(c->ow_flow[j]);
+            if (c->ow_peers.totals[j]) cudaIpcCloseMemHandle(c->ow_peers.totals[j]);
+            if (c->ow_peers.flags[j]) cudaIpcCloseMemHandle(c->ow_peers.flags[j]);
+        }
+        c->ow_bins[j] = nullptr; c->ow_flow[j] = nullptr;
+        c->ow_peers.totals[j] = nullptr; c->ow_peers.flags[j] = nullptr;
+    }
+    c->owners_connected = false;
+    c->bin_fixed = false;
+    return TB_OK;
+}
+
+// The sharded draw (tb_owners.cuh).  Every rank queues the same sequence; the three barriers are kernels on the stream.
+int queue_owners(tb_ctx *c, float time) {
+    const int T = c->geom.T, P = c->ow_world;
+    cudaEvent_t *ev = c->ev_ring[1][c->ev_count[1] % tb_ctx::kTimingSlots];
+    TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
+    const uint32_t epoch = ++c->ow_epoch;
+    auto barrier = [&](int phase) -> int {
+        k_owners_barrier<<<1, 32, 0, c->stream>>>(c->ow_peers, c->ow_flags, phase, epoch);
+        return check_launch(c, "k_owners_barrier");
+    };
+    const int mp = c->map_parity;
+    c->map_parity ^= 1;
+    if (int r = launch_count(c, mp)) return r;
+    k_owners_share<<<kMaxBins / 256, 256, 0, c->stream>>>(c->bin_total, c->n_bins + mp, c->ow_peers);
+    if (int r = check_launch(c, "k_owners_share")) return r;
+    if (int r = barrier(0)) return r;                      // every rank's totals are in every table
+    uint32_t *bin_sum = c->ow_scratch, *scat_off = bin_sum + kMaxBins, *own_begin = scat_off + kMaxBins, *own_count = own_begin + kMaxBins;
+    OwnerPlanArgs PA{};
+    PA.T = T;
+    PA.lS = c->geom.sxl + c->geom.syl;
+    PA.bm = bin_map(c, mp);
+    PA.bin_info = c->bin_info + static_cast<size_t>(mp) * kMaxBins;
+    PA.totals = c->ow_totals;
+    PA.n = P; PA.me = c->ow_rank;
+    for (int r = 0; r < P; ++r) PA.caps[r] = c->ow_caps[r];
+    PA.bin_sum = bin_sum; PA.scat_off = scat_off; PA.own_begin = own_begin; PA.own_count = own_count;
+    PA.items = c->items;
+    PA.split_at = c->split_at;
+    PA.tickets = c->tickets;
+    PA.map_next = c->split_map + static_cast<size_t>(mp ^ 1) * T;
+    PA.bin_info_next = c->bin_info + static_cast<size_t>(mp ^ 1) * kMaxBins;
+    PA.n_bins_next = c->n_bins + (mp ^ 1);
+    PA.out = c->d_plan;
+    k_owners_plan<<<1, kPlanThreads, 0, c->stream>>>(PA);
+    if (int r = check_launch(c, "k_owners_plan")) return r;
+    TB_CUDA(c, cudaMemcpyAsync(c->h_plan, c->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaEventRecord(c->ev_plan, c->stream));
+    if (int r = launch_scatter(c, time, mp, scat_off, c->ow_bins, P)) return r;
+    if (int r = barrier(1)) return r;                      // every rank's fragments are in their owners' bins
+    c->fold_parity = mp;
+    FoldArgs FA{};
+    FA.g = c->geom;
+    FA.time = time;
+    FA.bins = c->bins;
+    FA.bin_off = own_begin;
+    FA.bin_count = own_count;
+    FA.bin_info = c->bin_info + static_cast<size_t>(mp) * kMaxBins;
+    FA.items = c->items;
+    FA.n_items = c->tickets + 3;
+    FA.ticket = c->tickets + 2;
+    FA.flow[0] = c->flow;                                  // read here; the finished texels go to every rank's grid
+    int nf = 1;
+    for (int r = 0; r < P; ++r)
+        if (r != c->ow_rank) FA.flow[nf++] = c->ow_flow[r];
+    FA.n_flow = nf;
+    k_splat_fold<<<c->fold_ctas, kFoldThreads, kFoldSmemBytes, c->stream>>>(FA);
+    if (int r = check_launch(c, "k_splat_fold")) return r;
+    if (int r = barrier(2)) return r;                      // every grid is complete
+    TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    return TB_OK;
+}
 
 }  // namespace
 
@@ -598,6 +701,7 @@ int tb_destroy(tb_ctx *c) {
     if (c->side) cudaStreamSynchronize(c->side);
     if (c->stream) cudaStreamSynchronize(c->stream);
     tiles_release(c);
+    cudaFree(c->ow_flags); cudaFree(c->ow_totals); cudaFree(c->ow_scratch);
     cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
     cudaFree(c->frames);
     cudaFree(c->line_attr); cudaFree(c->line_verts); cudaFree(c->line_bbox);
@@ -706,6 +810,104 @@ int tb_step(tb_ctx *c, float time, float dt) {
     TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     c->ev_count[0] += 1;
     c->splat_since_step = false;
+    return TB_OK;
+}
+
+namespace {
+struct OwnerHandles {                 // what tb_owners_export hands to every other rank
+    cudaIpcMemHandle_t bins, flow, totals, flags;
+    int32_t w, h;
+    uint32_t bin_cap, pad;
+};
+}  // namespace
+
+int64_t tb_owners_handle_bytes(void) { return static_cast<int64_t>(sizeof(OwnerHandles)); }
+
+int tb_owners_export(tb_ctx *c, int64_t reserve_fragments, void *out, int64_t n_bytes) {
+    TB_REQUIRE(c, c && out, "null argument");
+    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(OwnerHandles)), "tb_owners_export: buffer must be tb_owners_handle_bytes() long");
+    TB_REQUIRE(c, reserve_fragments >= 0 && reserve_fragments < (1ll << 31), "tb_owners_export: reserve out of range");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    tiles_release(c);
+    if (int e = ensure_bin_cap(c, std::max<uint64_t>(static_cast<uint64_t>(reserve_fragments), 1u << 16))) return e;
+    if (!c->ow_flags) {
+        TB_CUDA(c, cudaMalloc(&c->ow_flags, kOwnerPhases * kMaxBandRanks * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMalloc(&c->ow_totals, static_cast<size_t>(kMaxBandRanks) * kMaxBins * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMalloc(&c->ow_scratch, 4 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+    }
+    TB_CUDA(c, cudaMemset(c->ow_flags, 0, kOwnerPhases * kMaxBandRanks * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMemset(c->ow_totals, 0, static_cast<size_t>(kMaxBandRanks) * kMaxBins * sizeof(uint32_t)));
+    c->ow_epoch = 0;
+    OwnerHandles hnd{};
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.bins, c->bins));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flow, c->flow));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.totals, c->ow_totals));
+    TB_CUDA(c, cudaIpcGetMemHandle(&hnd.flags, c->ow_flags));
+    hnd.w = c->W; hnd.h = c->H; hnd.bin_cap = c->bin_cap;
+    std::memcpy(out, &hnd, sizeof(hnd));
+    c->bin_fixed = true;
+    return TB_OK;
+}
+
+int tb_owners_connect(tb_ctx *c, int32_t rank, int32_t world, const void *all_handles, int64_t n_bytes) {
+    TB_REQUIRE(c, c && all_handles, "null argument");
+    TB_REQUIRE(c, world >= 2 && world <= kMaxBandRanks && rank >= 0 && rank < world, "tb_owners_connect: bad rank/world");
+    TB_REQUIRE(c, n_bytes == static_cast<int64_t>(sizeof(OwnerHandles)) * world, "tb_owners_connect: expected world x tb_owners_handle_bytes()");
+    TB_REQUIRE(c, c->bin_fixed && c->ow_flags, "tb_owners_export must be called before tb_owners_connect");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    const auto *h = static_cast<const unsigned char *>(all_handles);
+    c->ow_rank = rank; c->ow_world = world;
+    c->owners_connected = true;                // from here on tiles_release skips this rank's own slots
+    for (int j = 0; j < world; ++j) {
+        OwnerHandles hnd;
+        std::memcpy(&hnd, h + sizeof(OwnerHandles) * j, sizeof(hnd));
+        c->ow_caps[j] = hnd.bin_cap;
+        if (j == rank) {
+            c->ow_bins[j] = c->bins; c->ow_flow[j] = c->flow;
+            c->ow_peers.totals[j] = c->ow_totals; c->ow_peers.flags[j] = c->ow_flags;
+            continue;
+        }
+        if (hnd.w != c->W || hnd.h != c->H) {
+            tiles_release(c);
+            c->bin_fixed = true;
+            return fail(c, TB_ERR_INVALID, "tendrils-b200: tb_owners_connect: rank " + std::to_string(j) + " has another flow grid shape");
+        }
+        void *p[4] = {};
+        const cudaIpcMemHandle_t *hs[4] = {&hnd.bins, &hnd.flow, &hnd.totals, &hnd.flags};
+        for (int k = 0; k < 4; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&p[k], *hs[k], cudaIpcMemLazyEnablePeerAccess);
+            // keep what was opened so far where tiles_release will find it
+            if (k == 0) c->ow_bins[j] = static_cast<Frag *>(p[0]);
+            if (k == 1) c->ow_flow[j] = static_cast<float4 *>(p[1]);
+            if (k == 2) c->ow_peers.totals[j] = static_cast<uint32_t *>(p[2]);
+            if (k == 3) c->ow_peers.flags[j] = static_cast<uint32_t *>(p[3]);
+            if (e != cudaSuccess) {
+                tiles_release(c);
+                c->bin_fixed = true;
+                return fail(c, TB_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(j) + "): " + cudaGetErrorString(e));
+            }
+        }
+    }
+    c->ow_peers.n = world; c->ow_peers.me = rank;
+    return TB_OK;
+}
+
+int tb_splat_flow_owners(tb_ctx *c, float time) {
+    TB_REQUIRE(c, c, "null context");
+    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before the flow splat");
+    TB_REQUIRE(c, c->owners_connected, "tb_owners_connect must be called first");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
+    c->collect_time = time;
+    c->collected = false;
+    c->splat_since_step = true;
+    c->pending_time = time;
+    c->pending_stage = 3;
+    if (int r = queue_owners(c, time)) return r;
+    c->pending = true;
+    c->ev_count[1] += 1;
     return TB_OK;
 }
 

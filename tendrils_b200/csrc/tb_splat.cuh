@@ -69,7 +69,8 @@ struct __align__(16) Frag {
 
 // What the plan kernel leaves for the host (read lazily, never waited for on the hot path).
 struct PlanOut {
-    unsigned long long total;     // fragments of this draw
+    unsigned long long total;     // fragments of this draw (sharded run: of this rank)
+    unsigned long long needed;    // fragments the bin array of this context has to hold
     uint32_t overflow;            // 1: they do not fit the bin array -- scatter and fold did nothing
     uint32_t n_items;
 };
@@ -370,6 +371,53 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
     return r;
 }
 
+// The next draw's split map from this draw's fragments per bin: a strip with more than split_at fragments gets 8 bins,
+// 4x that: 32, 16x: 128 (as far as kMaxBins allows).  Called by every thread of the (single) plan CTA.
+__device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__restrict__ map, const uint32_t *__restrict__ bin_total,
+                                              uint32_t split_at, uint32_t *map_next, uint32_t *bin_info_next, uint32_t *n_bins_next,
+                                              unsigned long long *s_warp, unsigned long long *s_total) {
+    const int u0 = threadIdx.x * kPlanStrips;
+    uint32_t ns[kPlanStrips];
+#pragma unroll
+    for (int k = 0; k < kPlanStrips; ++k) {
+        ns[k] = 0u;
+        if (u0 + k < T) {
+            const uint32_t m = map[u0 + k], first = m & 0xffffffu, cnt = 1u << (m >> 24);
+            for (uint32_t b = 0; b < cnt; ++b) ns[k] += bin_total[first + b];
+        }
+    }
+    auto want = [&](uint32_t frags, uint32_t cap_ls) -> uint32_t {
+        uint32_t ls = 0;
+        if (frags > split_at) ls = 3;
+        if (frags > 4u * split_at) ls = 5;
+        if (frags > 16u * split_at) ls = 7;
+        if (ls > static_cast<uint32_t>(lS)) ls = static_cast<uint32_t>(lS);
+        return ls < cap_ls ? ls : cap_ls;
+    };
+    uint32_t cap_ls = 7;
+    unsigned long long base = 0ull;
+    for (;;) {                                   // lower the finest split until the bins fit
+        unsigned long long bins = 0ull;
+#pragma unroll
+        for (int k = 0; k < kPlanStrips; ++k)
+            if (u0 + k < T) bins += 1ull << want(ns[k], cap_ls);
+        base = block_excl_scan64(bins, s_warp, s_total);
+        if (*s_total <= static_cast<unsigned long long>(kMaxBins) || cap_ls == 0u) break;
+        cap_ls = cap_ls > 5u ? 5u : (cap_ls > 3u ? 3u : 0u);
+    }
+    if (threadIdx.x == 0) *n_bins_next = static_cast<uint32_t>(*s_total);
+#pragma unroll
+    for (int k = 0; k < kPlanStrips; ++k) {
+        if (u0 + k < T) {
+            const uint32_t ls = want(ns[k], cap_ls);
+            map_next[u0 + k] = static_cast<uint32_t>(base) | (ls << 24);
+            for (uint32_t sub = 0; sub < (1u << ls); ++sub)
+                bin_info_next[static_cast<uint32_t>(base) + sub] = static_cast<uint32_t>(u0 + k) | (sub << 16) | (ls << 24);
+            base += 1ull << ls;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
@@ -389,6 +437,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
         const bool ok = s_total <= static_cast<unsigned long long>(A.cap) && *A.too_many == 0u;
         s_ok = ok ? 1u : 0u;
         A.out->total = s_total;
+        A.out->needed = s_total;
         A.out->overflow = ok ? 0u : 1u;
         A.tickets[0] = 0u; A.tickets[1] = 0u; A.tickets[2] = 0u;
         *A.too_many = 0u;
@@ -420,47 +469,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     for (int k = 0; k < kPlanBins; ++k)
         if (ok && n[k]) A.items[s_bucket[bucket[k]] + rank[k]] = static_cast<uint32_t>(t0 + k);
 
-    // ---- the next draw's split map: per strip its fragments now, 1 / 8 / 32 / 128 bins then (as far as kMaxBins allows)
-    const int u0 = threadIdx.x * kPlanStrips;
-    uint32_t ns[kPlanStrips];
-#pragma unroll
-    for (int k = 0; k < kPlanStrips; ++k) {
-        ns[k] = 0u;
-        if (u0 + k < A.T) {
-            const uint32_t m = A.bm.map[u0 + k], first = m & 0xffffffu, cnt = 1u << (m >> 24);
-            for (uint32_t b = 0; b < cnt; ++b) ns[k] += A.bin_total[first + b];
-        }
-    }
-    auto want = [&](uint32_t frags, uint32_t cap_ls) -> uint32_t {
-        uint32_t ls = 0;
-        if (frags > A.split_at) ls = 3;
-        if (frags > 4u * A.split_at) ls = 5;
-        if (frags > 16u * A.split_at) ls = 7;
-        if (ls > static_cast<uint32_t>(A.lS)) ls = static_cast<uint32_t>(A.lS);
-        return ls < cap_ls ? ls : cap_ls;
-    };
-    uint32_t cap_ls = 7;
-    unsigned long long base = 0ull;
-    for (;;) {                                   // lower the finest split until the bins fit
-        unsigned long long bins = 0ull;
-#pragma unroll
-        for (int k = 0; k < kPlanStrips; ++k)
-            if (u0 + k < A.T) bins += 1ull << want(ns[k], cap_ls);
-        base = block_excl_scan64(bins, s_warp, &s_total);
-        if (s_total <= static_cast<unsigned long long>(kMaxBins) || cap_ls == 0u) break;
-        cap_ls = cap_ls > 5u ? 5u : (cap_ls > 3u ? 3u : 0u);
-    }
-    if (threadIdx.x == 0) *A.n_bins_next = static_cast<uint32_t>(s_total);
-#pragma unroll
-    for (int k = 0; k < kPlanStrips; ++k) {
-        if (u0 + k < A.T) {
-            const uint32_t ls = want(ns[k], cap_ls);
-            A.map_next[u0 + k] = static_cast<uint32_t>(base) | (ls << 24);
-            for (uint32_t sub = 0; sub < (1u << ls); ++sub)
-                A.bin_info_next[static_cast<uint32_t>(base) + sub] = static_cast<uint32_t>(u0 + k) | (sub << 16) | (ls << 24);
-            base += 1ull << ls;
-        }
-    }
+    plan_next_map(A.T, A.lS, A.bm.map, A.bin_total, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);
 }
 
 // the identity map (one bin per strip): first draw, and after a resize
@@ -498,8 +507,8 @@ struct ScatterArgs {
     const uint32_t *__restrict__ bin_off;       // [n_bins + 1] (sharded run: where this rank's fragments start in the owner's bin)
     const PlanOut *plan;
     uint32_t *ticket;
-    Frag *bins[kMaxBandRanks];                  // the bin array of every rank (single GPU: [0])
-    const uint8_t *__restrict__ bin_owner;      // null: everything goes to bins[0]
+    Frag *bins[kMaxBandRanks];                  // the bin array of every rank (single GPU: [0]); bin b lives on rank b % n_ranks
+    int n_ranks;
 };
 
 constexpr size_t kScatterSmemBytes = static_cast<size_t>(kMaxBins) * 4                                   // cursors
@@ -634,7 +643,7 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
                     if (static_cast<uint32_t>(r * 32) >= cnt) continue;                       // warp-uniform
                     fdst[r] = __shfl_sync(0xffffffffu, fdst[r], __ffs(fpeers[r]) - 1) + static_cast<uint32_t>(__popc(fpeers[r] & lt_mask));
                     if (fbin[r] == 0xffffffffu) continue;
-                    Frag *bin = A.bins[A.bin_owner ? A.bin_owner[fbin[r] & 0xffffu] : 0];
+                    Frag *bin = A.bins[A.n_ranks > 1 ? (fbin[r] & 0xffffu) % static_cast<uint32_t>(A.n_ranks) : 0u];
                     *reinterpret_cast<float4 *>(bin + fdst[r]) = make_float4(fcx[r], fcy[r], fa[r], __uint_as_float(fbin[r] >> 16));
                 }
                 __syncwarp();                                                   // the slot table is reused by the next pass
@@ -668,7 +677,8 @@ struct FoldArgs {
     StripGeom g;
     float time;
     const Frag *__restrict__ bins;
-    const uint32_t *__restrict__ bin_off;    // [n_bins + 1]
+    const uint32_t *__restrict__ bin_off;    // [n_bins + 1] where a bin starts (sharded run: the bins this rank owns, in its own array)
+    const uint32_t *__restrict__ bin_count;  // null: bin b ends where b + 1 starts
     const uint32_t *__restrict__ bin_info;   // [n_bins] strip | sub << 16 | log2(bins of the strip) << 24
     const uint32_t *__restrict__ items;      // bins to fold
     const uint32_t *n_items;                 // device: number of work items
@@ -812,7 +822,7 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
         const uint32_t code = A.bin_info[bin_id];
         const uint32_t st = code & 0xffffu, sub = (code >> 16) & 0xffu, ls = code >> 24;
         const uint32_t R = S >> ls, lo = sub * R;                     // the bin's texels: local indices [lo, lo + R)
-        const uint32_t begin = A.bin_off[bin_id], n = A.bin_off[bin_id + 1] - begin;
+        const uint32_t begin = A.bin_off[bin_id], n = A.bin_count ? A.bin_count[bin_id] : A.bin_off[bin_id + 1] - begin;
         const uint32_t n_stage = (n + kFoldStage - 1) / kFoldStage;
         const Frag *bin = A.bins + begin;
         auto issue = [&](uint32_t j) {

@@ -35,10 +35,13 @@ class Device:
         self.rank = int(rank)
         self.world_size = int(world_size)
         self.group = group
-        # how the ordered flow fold is shared between ranks:
-        #   "dist"  = the grid travels rank 0 -> 1 -> ... over torch.distributed send/recv/broadcast, every rank folding
-        #             its own bins onto what it received (serial; also what the gloo tests run)
-        self.ring = ring or os.environ.get("TB_RING") or "dist"
+        # how the ordered flow blend is shared between ranks:
+        #   "owners" = over CUDA-IPC peer memory (default): the fragment bins are owned round-robin by the ranks, every rank
+        #              rasterises straight into the owners' bins over NVLink, folds its own bins and stores the finished
+        #              texels into every grid; three all-rank barriers per draw, all inside the CUDA stream
+        #   "dist"   = the grid travels rank 0 -> 1 -> ... over torch.distributed send/recv/broadcast, every rank folding
+        #              its own bins onto what it received (serial; needs no peer mapping)
+        self.ring = ring or os.environ.get("TB_RING") or "owners"
 
 
 class Shader:
@@ -260,11 +263,33 @@ class Particles:
         if gl.world_size == 1:
             N.check(ctx, L.tb_splat_flow(ctx, float(u["time"])))
             return
+        if gl.ring == "owners":
+            self._ensure_owners()
+            N.check(ctx, L.tb_splat_flow_owners(ctx, float(u["time"])))
+            return
         N.check(ctx, L.tb_splat_collect(ctx, float(u["time"])))
         from .multi_gpu import ordered_ring_fold
         ordered_ring_fold(gl.rank, gl.world_size, gl.group,
                           fold=lambda: N.check(ctx, L.tb_splat_fold(ctx)),
                           flow_tensor=self._flow_tensor, stream=self.stream_handle())
+
+    def _ensure_owners(self):
+        """Exchange CUDA IPC handles of (fragment bins, flow grid, totals table, flags) once per flow-grid allocation and map
+        every rank's.  The bin array is fixed at `TB_OWNERS_RESERVE` (default 8) fragments per local particle while mapped.
+        torch.distributed is only the courier of the handle blobs."""
+        if self._tiles_ready:
+            return
+        from .multi_gpu import gather_handles
+        L, ctx, gl = self._L, self._ctx, self.gl
+        per = float(os.environ.get("TB_OWNERS_RESERVE", "8"))
+        reserve = min(int(per * (self.col1 - self.col0) * self.shape[1]) + (1 << 16), (1 << 31) - 1)
+        nbytes = L.tb_owners_handle_bytes()
+        mine = (C.c_ubyte * nbytes)()
+        N.check(ctx, L.tb_owners_export(ctx, reserve, mine, nbytes))
+        blobs = gather_handles(bytes(mine), gl.world_size, gl.group, gl.device)
+        buf = (C.c_ubyte * (nbytes * gl.world_size)).from_buffer_copy(b"".join(blobs))
+        N.check(ctx, L.tb_owners_connect(ctx, gl.rank, gl.world_size, buf, nbytes * gl.world_size))
+        self._tiles_ready = True
 
     # -- plumbing ------------------------------------------------------------------------
     def stream_handle(self) -> int:

@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, R, G, steps, out_dir, ring):
+def _worker(rank, world, port, shape, G, steps, out_dir, ring, radius):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -25,38 +25,47 @@ def _worker(rank, world, port, R, G, steps, out_dir, ring):
     import tendrils_b200 as T
     from tendrils_b200.spawn import spawnBall
     t = T.Tendrils(T.Device(G, G, device=rank, rank=rank, world_size=world, group=dist.group.WORLD, ring=ring))
-    t.setup(R); t.resize()
-    spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}}).spawn(t)
+    t.setup(shape); t.resize()
+    spawnBall(t.gl, {"uniforms": {"radius": radius, "speed": 0.005}}).spawn(t)
     for _ in range(steps):
         t.timer.tick()
         t.step().draw()
     np.save(os.path.join(out_dir, f"flow_{rank}.npy"), t.flow.download())
     np.save(os.path.join(out_dir, f"state_{rank}.npy"), t.particles.buffers[0].download())
+    np.save(os.path.join(out_dir, f"frags_{rank}.npy"), np.array([t.particles.stats()["last_fragments"]]))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ring,G", [("a2a", 64), ("peer", 64), ("dist", 64), ("bands", 64), ("bands", 50)])
-def test_two_gpu_ring_equals_oracle(oracle, tmp_path, ring, G):
+# ring, particle texture (columns, rows), flow grid, ball radius:
+#   square and ragged grids; the TALL textures of the weak-scaling bench (columns sharded, many rows); a small ball so that
+#   strips get crowded and the split map kicks in (the same map must come out on every rank)
+@pytest.mark.parametrize("ring,shape,G,radius", [("owners", (96, 96), 64, 0.3), ("owners", (96, 96), 50, 0.3), ("dist", (96, 96), 64, 0.3),
+                                                 ("owners", (16, 2048), 128, 0.3), ("owners", (64, 1024), 96, 0.02),
+                                                 ("owners", (8, 8192), 64, 0.3)])
+def test_sharded_draw_equals_oracle(oracle, tmp_path, ring, shape, G, radius):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    world, R, steps = 2, 96, 8                 # 64*64 texels: divisible by world*128, so a2a is exercised;
-    if ring == "bands":                        # 50*50: a ragged last tile; bands on as many GPUs as there are (<= 4)
-        world = min(torch.cuda.device_count(), 4)
-    mp.spawn(_worker, args=(world, _free_port(), R, G, steps, str(tmp_path), ring), nprocs=world, join=True)
+    world, steps = min(torch.cuda.device_count(), 8), 8
+    while shape[0] % world:
+        world //= 2
+    mp.spawn(_worker, args=(world, _free_port(), list(shape), G, steps, str(tmp_path), ring, radius), nprocs=world, join=True)
     O = oracle
     DT = 1000 / 60
     P = O.make_params()
-    cur, prev = O.spawn_ball(R, R, 0.3, 0.005), O.spawn_init(R, R)
-    targets, flow = np.zeros((R, R, 4), np.float32), np.zeros((G, G, 4), np.float32)
+    PW, PH = shape
+    cur, prev = O.spawn_ball(PW, PH, radius, 0.005), O.spawn_init(PW, PH)
+    targets, flow = np.zeros((PW, PH, 4), np.float32), np.zeros((G, G, 4), np.float32)
     t = DT
+    n = 0
     for _ in range(steps):
         t += DT
         new = O.integrate(P, cur, targets, flow, np.float32(t), np.float32(DT))
         prev, cur = cur, new
-        O.splat(P, cur, prev, flow, np.float32(t))
+        n = O.splat(P, cur, prev, flow, np.float32(t))
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"flow_{r}.npy"), flow), f"rank {r} flow"
     got = np.concatenate([np.load(tmp_path / f"state_{r}.npy") for r in range(world)], 0)
     assert np.array_equal(got, cur)
+    assert sum(int(np.load(tmp_path / f"frags_{r}.npy")[0]) for r in range(world)) == n
