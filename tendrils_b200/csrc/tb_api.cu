@@ -209,7 +209,7 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     tiles_release(c);
     TB_REQUIRE(c, w >= 1 && h >= 1 && w <= 32768 && h <= 32768, "flow grid dimensions out of bounds");
     const StripGeom g = choose_geom(w, h);
-    TB_REQUIRE(c, (1 << (g.sxl + g.syl)) <= kFoldTexels, "flow grid too large for the strip binning (at most 8192 strips of 128 texels)");
+    TB_REQUIRE(c, (1 << (g.sxl + g.syl)) <= kMaxStripTexels, "flow grid too large for the strip binning (at most 8192 strips of 512 texels)");
     cudaFree(c->flow); cudaFree(c->slab_hist); cudaFree(c->seg_total); cudaFree(c->bin_total); cudaFree(c->bin_off); cudaFree(c->items);
     cudaFree(c->split_map); cudaFree(c->bin_info); cudaFree(c->n_bins);
     c->flow = nullptr; c->slab_hist = nullptr; c->seg_total = nullptr; c->bin_total = nullptr; c->bin_off = nullptr; c->items = nullptr;
@@ -237,11 +237,11 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     // persistent grids of the splat kernels
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBins * static_cast<int>(sizeof(uint32_t))));
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kScatterSmemBytes)));
-    TB_CUDA(c, cudaFuncSetAttribute(k_splat_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFoldSmemBytes)));
+    TB_CUDA(c, cudaFuncSetAttribute(k_splat_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)))));
     int per_sm = 0;
     TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_scatter, kEmitThreads, kScatterSmemBytes));
     c->scatter_ctas = std::max(1, per_sm) * c->n_sms;
-    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_fold, kFoldThreads, kFoldSmemBytes));
+    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_fold, kFoldThreads, fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl))));
     c->fold_ctas = std::max(1, per_sm) * c->n_sms;
     TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_hist, kHistThreads, kMaxBins * sizeof(uint32_t)));
     c->hist_ctas = std::max(1, per_sm) * c->n_sms;
@@ -400,7 +400,7 @@ int launch_fold(tb_ctx *c, float time) {
     FA.ticket = c->tickets + 2;
     FA.flow[0] = c->flow;
     FA.n_flow = 1;
-    k_splat_fold<<<c->fold_ctas, kFoldThreads, kFoldSmemBytes, c->stream>>>(FA);
+    k_splat_fold<<<c->fold_ctas, kFoldThreads, fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)), c->stream>>>(FA);
     return check_launch(c, "k_splat_fold");
 }
 
@@ -579,7 +579,7 @@ int queue_owners(tb_ctx *c, float time) {
     for (int r = 0; r < P; ++r)
         if (r != c->ow_rank) FA.flow[nf++] = c->ow_flow[r];
     FA.n_flow = nf;
-    k_splat_fold<<<c->fold_ctas, kFoldThreads, kFoldSmemBytes, c->stream>>>(FA);
+    k_splat_fold<<<c->fold_ctas, kFoldThreads, fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)), c->stream>>>(FA);
     if (int r = check_launch(c, "k_splat_fold")) return r;
     if (int r = barrier(2)) return r;                      // every grid is complete
     TB_CUDA(c, cudaEventRecord(ev[1], c->stream));

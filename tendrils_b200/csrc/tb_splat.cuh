@@ -28,11 +28,11 @@
 namespace tb {
 
 // ------------------------------------------------------------------------------------------
-// Geometry of the binning: strips of (1 << sxl) x (1 << syl) texels, at most kFoldTexels each.
+// Geometry of the binning: strips of (1 << sxl) x (1 << syl) texels, at most kMaxStripTexels each.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxStrips = 8192;
 constexpr int kMaxBins = 11264;           // bins per grid: k_splat_scatter keeps one cursor per bin in shared memory
-constexpr int kFoldTexels = 128;          // texels of a strip = the most one warp of k_splat_fold holds
+constexpr int kMaxStripTexels = 512;      // texels of a strip = the most one warp of k_splat_fold holds (128 up to 1024^2 grids)
 constexpr int kHistSegs = 16;             // the slabs are scanned in this many segments (k_splat_rows)
 constexpr uint32_t kKeyLocalMask = 0x000fffffu;
 
@@ -687,14 +687,14 @@ struct FoldArgs {
     int n_flow;
 };
 
-struct __align__(16) FoldWarp {             // shared memory of one warp
+struct __align__(16) FoldWarp {             // shared memory of one warp, followed by the bin's texels: float4[texels per strip]
     Frag stage[2][kFoldStage];
-    float4 tex[kFoldTexels];
     float4 term[32];                         // chained batches: src*a per lane
     float om[32];                            //                  1 - a per lane
     unsigned long long bar[2];
 };
-constexpr size_t kFoldSmemBytes = sizeof(FoldWarp) * kFoldNWarps;
+__host__ __device__ inline size_t fold_warp_bytes(int strip_texels) { return sizeof(FoldWarp) + static_cast<size_t>(strip_texels) * sizeof(float4); }
+__host__ __device__ inline size_t fold_smem_bytes(int strip_texels) { return fold_warp_bytes(strip_texels) * kFoldNWarps; }
 
 // [bulk-begin]  (the CPU tests swap the helpers between these markers for plain copies)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -753,12 +753,12 @@ __device__ __forceinline__ FoldPrep fold_prep(const Frag &f, bool active, uint32
     return p;
 }
 
-__device__ __forceinline__ void fold_apply(FoldWarp &W, const FoldPrep &p, bool active, int lane) {
+__device__ __forceinline__ void fold_apply(FoldWarp &W, float4 *tex, const FoldPrep &p, bool active, int lane) {
     const uint32_t before = p.peers & ((1u << lane) - 1u);
     const uint32_t rank = static_cast<uint32_t>(__popc(before));
     if (p.most <= kFoldRounds) {
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) d = W.tex[p.rel];
+        if (active) d = tex[p.rel];
         d.x = __fadd_rn(p.tx, __fmul_rn(d.x, p.om)); d.y = __fadd_rn(p.ty, __fmul_rn(d.y, p.om));
         d.z = __fadd_rn(p.tz, __fmul_rn(d.z, p.om)); d.w = __fadd_rn(p.tw, __fmul_rn(d.w, p.om));
         const int pred = before ? 31 - __clz(before) : lane;            // the lane with the previous fragment of my texel
@@ -770,13 +770,13 @@ __device__ __forceinline__ void fold_apply(FoldWarp &W, const FoldPrep &p, bool 
                 d.z = __fadd_rn(p.tz, __fmul_rn(pz, p.om)); d.w = __fadd_rn(p.tw, __fmul_rn(pw, p.om));
             }
         }
-        if (active && (p.peers >> lane) == 1u) W.tex[p.rel] = d;        // the last fragment of the texel in this batch
+        if (active && (p.peers >> lane) == 1u) tex[p.rel] = d;        // the last fragment of the texel in this batch
     } else {
         W.term[lane] = make_float4(p.tx, p.ty, p.tz, p.tw);
         W.om[lane] = p.om;
         __syncwarp();
         if (active && rank == 0u) {
-            float4 d = W.tex[p.rel];
+            float4 d = tex[p.rel];
             uint32_t rem = p.peers & ~p.cut;
             while (rem) {
                 // two steps per trip: the operand loads do not depend on d
@@ -794,7 +794,7 @@ __device__ __forceinline__ void fold_apply(FoldWarp &W, const FoldPrep &p, bool 
                     d.z = __fadd_rn(v1.z, __fmul_rn(d.z, m1)); d.w = __fadd_rn(v1.w, __fmul_rn(d.w, m1));
                 }
             }
-            W.tex[p.rel] = d;
+            tex[p.rel] = d;
         }
     }
     __syncwarp();
@@ -803,8 +803,9 @@ __device__ __forceinline__ void fold_apply(FoldWarp &W, const FoldPrep &p, bool 
 __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    FoldWarp &W = reinterpret_cast<FoldWarp *>(smem_raw)[warp];
     const uint32_t S = 1u << (A.g.sxl + A.g.syl);
+    FoldWarp &W = *reinterpret_cast<FoldWarp *>(smem_raw + fold_warp_bytes(static_cast<int>(S)) * warp);
+    float4 *tex = reinterpret_cast<float4 *>(&W + 1);
     const uint32_t n_items = *A.n_items;
     if (lane == 0) {
         mbar_init(&W.bar[0], 1u);
@@ -839,7 +840,7 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
             const int gx = gx0 + static_cast<int>(loc & ((1u << A.g.sxl) - 1u)), gy = gy0 + static_cast<int>(loc >> A.g.sxl);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gx < A.g.W && gy < A.g.H) v = A.flow[0][static_cast<size_t>(gy) * A.g.W + gx];
-            W.tex[l] = v;
+            tex[l] = v;
         }
         __syncwarp();
         for (uint32_t j = 0; j < n_stage; ++j) {
@@ -853,10 +854,10 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
             const FoldPrep p0 = fold_prep(f0, a0, lo, A.time, lane);
             if (c > 32u) {
                 const FoldPrep p1 = fold_prep(f1, a1, lo, A.time, lane);
-                fold_apply(W, p0, a0, lane);
-                fold_apply(W, p1, a1, lane);
+                fold_apply(W, tex, p0, a0, lane);
+                fold_apply(W, tex, p1, a1, lane);
             } else {
-                fold_apply(W, p0, a0, lane);
+                fold_apply(W, tex, p0, a0, lane);
             }
             // (fold_apply ends with __syncwarp: every lane is done with this window)
             if (lane == 0 && j + 2 < n_stage) issue(j + 2);
@@ -865,7 +866,7 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
             const uint32_t loc = lo + l;
             const int gx = gx0 + static_cast<int>(loc & ((1u << A.g.sxl) - 1u)), gy = gy0 + static_cast<int>(loc >> A.g.sxl);
             if (gx < A.g.W && gy < A.g.H) {
-                const float4 v = W.tex[l];
+                const float4 v = tex[l];
                 const size_t at = static_cast<size_t>(gy) * A.g.W + gx;
                 for (int r = 0; r < A.n_flow; ++r) A.flow[r][at] = v;
             }

@@ -49,6 +49,34 @@ static inline int __any_sync(unsigned, int pred) {
     return any != 0;
 }
 static inline void __syncwarp() { tb_warp->bar.arrive_and_wait(); }
+template <class T> static inline T __shfl_up_sync(unsigned m, T v, int delta) { return __shfl_sync(m, v, tb_lane >= delta ? tb_lane - delta : tb_lane); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    tb_warp->slot[tb_lane] = pred ? 1u : 0u;
+    tb_warp->bar.arrive_and_wait();
+    uint32_t m = 0;
+    for (int i = 0; i < 32; ++i) m |= tb_warp->slot[i] << i;
+    tb_warp->bar.arrive_and_wait();
+    return m;
+}
+static inline unsigned __match_any_sync(unsigned, uint32_t v) {
+    tb_warp->slot[tb_lane] = v;
+    tb_warp->bar.arrive_and_wait();
+    uint32_t m = 0;
+    for (int i = 0; i < 32; ++i) m |= (tb_warp->slot[i] == v ? 1u : 0u) << i;
+    tb_warp->bar.arrive_and_wait();
+    return m;
+}
+static inline unsigned __reduce_max_sync(unsigned, uint32_t v) {
+    tb_warp->slot[tb_lane] = v;
+    tb_warp->bar.arrive_and_wait();
+    uint32_t m = 0;
+    for (int i = 0; i < 32; ++i) m = tb_warp->slot[i] > m ? tb_warp->slot[i] : m;
+    tb_warp->bar.arrive_and_wait();
+    return m;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
 /* run one warp: body() is called by 32 lane threads with threadIdx.x = first_thread + lane */

@@ -78,6 +78,25 @@ def test_ball_then_steps_bit_exact(T, oracle, R, G):
     assert np.isfinite(sim.cur).all() and (sim.flow != 0).any()
 
 
+@pytest.mark.parametrize("R,G,radius,steps", [(192, 1100, 0.9, 4), (160, 2048, 0.9, 3), (256, 64, 0.03, 12), (192, 2048, 0.01, 6)])
+def test_strip_sizes_and_split_maps_bit_exact(T, oracle, R, G, radius, steps):
+    """Grids beyond 1024^2 (strips of 256 / 512 texels), and balls so small that strips get crowded: the split map the plan
+    derives from one draw (8 / 32 / 128 bins per strip) must not change the next draw's result."""
+    from tendrils_b200.spawn import spawnBall
+    t = make(T, R, G)
+    sim = OracleSim(oracle, R, G, G, oracle_params(oracle, t))
+    spawnBall(t.gl, {"uniforms": {"radius": radius, "speed": 0.005}}).spawn(t)
+    sim.spawn_ball(radius, 0.005)
+    for k in range(steps):
+        t.timer.tick()
+        t.step().draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt))
+        n = sim.draw(np.float32(t.timer.time))
+        assert t.particles.stats()["last_fragments"] == n, f"fragment count at step {k}"
+        assert_bits_equal(t.flow.download(), sim.flow, f"flow after step {k}")
+    assert_bits_equal(t.particles.buffers[0].download(), sim.cur, "state")
+
+
 # ---------------------------------------------------------------------------------------------
 # spawners
 # ---------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(N.lib_path())
     for name in declared:
         assert hasattr(lib, name), name
-    assert N.load().tb_abi_version() == 1
+    assert N.load().tb_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -153,14 +153,14 @@ def test_env_knobs_are_documented():
 
 
 def test_default_transport_by_world_size(monkeypatch):
-    """2 ranks: the serial peer ring (one hop); 3 or more: the parallel band fold; TB_RING overrides."""
+    """sharded runs share the flow blend over peer memory ("owners") unless told otherwise; TB_RING overrides."""
     import tendrils_b200 as T
     monkeypatch.delenv("TB_RING", raising=False)
-    assert T.Device(4, 4, world_size=2, rank=1).ring == "peer"
-    assert T.Device(4, 4, world_size=8, rank=3).ring == "bands"
+    assert T.Device(4, 4, world_size=2, rank=1).ring == "owners"
+    assert T.Device(4, 4, world_size=8, rank=3).ring == "owners"
     assert T.Device(4, 4, world_size=8, rank=3, ring="dist").ring == "dist"
-    monkeypatch.setenv("TB_RING", "a2a")
-    assert T.Device(4, 4, world_size=8).ring == "a2a"
+    monkeypatch.setenv("TB_RING", "dist")
+    assert T.Device(4, 4, world_size=8).ring == "dist"
 
 
 def test_synthetic_video_loops_and_moves():

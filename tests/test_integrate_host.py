@@ -49,7 +49,6 @@ extern "C" void ih_integrate(const float *state18, int PW, int PH, int W, int H,
     A.pow2_res = pow2(PW) && pow2(PH);
     A.inv_resx = 1.0f / (float)PW; A.inv_resy = 1.0f / (float)PH; A.inv_n = 1.0f / ((float)PW * (float)PH);
     A.pk.one = 1.0f; A.pk.neg_one = -1.0f; A.pk.neg_zero = -0.0f;
-    A.row_pair = nullptr; A.prim_off = nullptr; A.n_pairs = 0;
     float2 *wander = new float2[(size_t)PW * PH];
     A.wander = wander;
     auto launch = [&](int mode) {
@@ -79,8 +78,7 @@ def ih(tmp_path_factory):
     noise = d / "tb_noise2_host.cuh"
     noise.write_text((nsrc[:a] + PACKED_HOST_PRIMITIVES + nsrc[b:]).replace("__device__", ""))
     ksrc = open(os.path.join(csrc, "tb_kernels.cuh")).read()
-    body = ksrc[ksrc.index("struct PairEntry {"):ksrc.index("// Flow splat (a7-a10).")]
-    body = body[:body.rindex("// ----")].replace("__device__", "")
+    body = ksrc[ksrc.index("struct PairEntry {"):ksrc.index("constexpr int kMaxBandRanks")].replace("__device__", "")
     cpp = d / "integrate_host.cpp"
     cpp.write_text(HARNESS % {"math": str(math), "noise": str(noise), "abi": os.path.join(ROOT, "include", "tendrils_b200.h"),
                               "body": body})

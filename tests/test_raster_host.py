@@ -1,7 +1,10 @@
-"""Property test of the splat's fused COUNT pass on the CPU: `count_fragments` (closed form, rides in k_integrate)
-must equal the number of fragments `raster_line` emits (what k_splat_emit writes) for every segment -- a mismatch
-would shift every later fragment's slot.  The two device functions are pure arithmetic, so the test cuts their text
-out of tendrils_b200/csrc/tb_kernels.cuh (between the [raster-begin]/[raster-end] markers), compiles it with g++
+"""Property tests of the splat's per-line arithmetic on the CPU.  The count pass (k_splat_hist) and the emit pass
+(k_splat_scatter) must agree on every line's fragments, or every later fragment of a bin lands in the wrong slot:
+  * `count_fragments` / `prim_setup` (closed form) must equal the number of fragments `raster_line` emits;
+  * `prim_fragment(j)`, j < n, must enumerate exactly raster_line's fragments (texel and interpolation parameter, bit for bit);
+  * `prim_fragment_texel` (the count pass's division-free estimate with its exact fallback) must name the same texels.
+The device functions are pure arithmetic, so the test cuts their text out of tendrils_b200/csrc/tb_kernels.cuh and
+tb_splat.cuh (between the [raster-begin]/[raster-end] and [prim-begin]/[prim-end] markers), compiles it with g++
 -ffp-contract=off against a shim of the single-operation intrinsics, and throws adversarial segments at it.
 Nothing here is used by the product."""
 import ctypes as C
@@ -17,9 +20,53 @@ HARNESS = r'''
 #include <cuda_runtime.h>
 #include "cuda_intrinsics_shim.h"
 #include "%(math)s"
+#include <algorithm>
+#include <tuple>
+#include <vector>
 namespace tb {
 static constexpr float kInert = -1000000.0f;
 %(body)s
+struct PrimGeom {
+    float ma, mb, na, nb;
+    int c0;
+    uint32_t flags;
+};
+%(prim)s
+%(texel)s
+}
+// prim_setup / prim_fragment / prim_fragment_texel against raster_line: returns the number of disagreeing segments
+extern "C" long long rh_check_prims(long long n, const float *seg, float vsx, float vsy, int W, int H, long long *first_bad) {
+    long long bad = 0;
+    *first_bad = -1;
+    for (long long i = 0; i < n; ++i) {
+        const float4 sa = make_float4(seg[4 * i], seg[4 * i + 1], 0.001f, 0.002f), sb = make_float4(seg[4 * i + 2], seg[4 * i + 3], 0.003f, 0.f);
+        tb::PrimGeom P;
+        const unsigned cnt = tb::prim_setup(sa, sb, vsx, vsy, W, H, P);
+        std::vector<std::tuple<int, int, unsigned>> want, got;
+        if (tb::splat_vertex_ok(sa) && tb::splat_vertex_ok(sb)) {
+            const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+            const float xa = (sa.x * vsx) * hw + hw, ya = (sa.y * vsy) * hh + hh, xb = (sb.x * vsx) * hw + hw, yb = (sb.y * vsy) * hh + hh;
+            tb::raster_line(xa, ya, xb, yb, W, H, [&](int gx, int gy, float t) { want.emplace_back(gx, gy, __float_as_uint(t)); });
+        }
+        bool ok = cnt == want.size() && cnt == tb::count_fragments(sa, sb, vsx, vsy, W, H);
+        for (unsigned j = 0; ok && j < cnt; ++j) {
+            int gx, gy; float t;
+            tb::prim_fragment(P, j, W, H, gx, gy, t);
+            got.emplace_back(gx, gy, __float_as_uint(t));
+            if (P.flags & 2u) {
+                const float inv_dm = 1.0f / (P.mb - P.ma);
+                const float eps = ((fabsf(P.na) + fabsf(P.nb - P.na)) + 1.0f) * 1.9073486328125e-06f;
+                int ex, ey;
+                tb::prim_fragment_texel(P, j, inv_dm, eps, ex, ey);
+                ok = ok && ex == gx && ey == gy;
+            }
+        }
+        std::sort(want.begin(), want.end());
+        std::sort(got.begin(), got.end());
+        ok = ok && want == got;
+        if (!ok) { if (*first_bad < 0) *first_bad = i; ++bad; }
+    }
+    return bad;
 }
 extern "C" long long rh_check(long long n, const float *seg /* n x 4: NDC xa ya xb yb */, float vsx, float vsy, int W, int H,
                               long long *total, long long *first_bad) {
@@ -50,7 +97,10 @@ def rh(tmp_path_factory):
     math = d / "tb_math_host.cuh"
     math.write_text(open(os.path.join(ROOT, "tendrils_b200", "csrc", "tb_math.cuh")).read().replace("__device__", ""))
     cpp = d / "raster_host.cpp"
-    cpp.write_text(HARNESS % {"math": str(math), "body": body})
+    ssrc = open(os.path.join(ROOT, "tendrils_b200", "csrc", "tb_splat.cuh")).read()
+    prim = ssrc[ssrc.index("// [prim-begin]"):ssrc.index("// [prim-end]")].replace("__device__", "")
+    texel = ssrc[ssrc.index("__device__ __forceinline__ void prim_fragment_texel("):ssrc.index("__global__ void __launch_bounds__(kHistThreads) k_splat_hist")]
+    cpp.write_text(HARNESS % {"math": str(math), "body": body, "prim": prim, "texel": texel.replace("__device__", "")})
     out = d / "libraster_host.so"
     subprocess.run(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
                     "-Wno-unknown-pragmas", "-Wno-unused-function", "-I/usr/local/cuda/include",
@@ -59,6 +109,8 @@ def rh(tmp_path_factory):
     L.rh_check.restype = C.c_longlong
     L.rh_check.argtypes = [C.c_longlong, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_int,
                            C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.rh_check_prims.restype = C.c_longlong
+    L.rh_check_prims.argtypes = [C.c_longlong, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     return L
 
 
@@ -110,4 +162,20 @@ def test_count_with_astronomic_coordinates(rh, W, H, vs):
     seg = np.ascontiguousarray(np.where(rng.random((n, 4)) < 0.5, big, rng.uniform(-1.2, 1.2, (n, 4))).astype(np.float32))
     total, first_bad = C.c_longlong(), C.c_longlong()
     bad = rh.rh_check(n, seg.ctypes.data_as(C.POINTER(C.c_float)), vs[0], vs[1], W, H, C.byref(total), C.byref(first_bad))
+    assert bad == 0, (bad, first_bad.value, seg[first_bad.value] if first_bad.value >= 0 else None)
+
+
+@pytest.mark.parametrize("W,H,vs,seed", [(64, 64, (1.0, 1.0), 11), (1024, 1024, (1.0, 1.0), 12), (40, 24, (1.0, 40 / 24), 13),
+                                         (7, 129, (129 / 7, 1.0), 14), (1, 1, (1.0, 1.0), 15), (2048, 2048, (1.0, 1.0), 16)])
+def test_emit_enumerates_what_the_count_counted(rh, W, H, vs, seed):
+    """prim_setup + prim_fragment (k_splat_scatter) and prim_fragment_texel (k_splat_hist) against raster_line."""
+    rng = np.random.default_rng(seed)
+    n = 150_000
+    seg = segments(rng, n, W, H)
+    seg[:8] = [[np.nan, 0, 0, 0], [0, 0, np.inf, 0], [-1e6, -1e6, 0, 0], [0, 0, 0, 0], [0.5, 0.5, 0.5, 0.5],
+               [-1, -1, 1, 1], [1, 1, -1, -1], [-1, 1, 1, -1]]
+    big = rng.choice([1e3, 1e20, 1e35, 1e37, 3e38], (64, 4)) * rng.choice([-1, 1], (64, 4))
+    seg[8:72] = np.where(rng.random((64, 4)) < 0.5, big, rng.uniform(-1.2, 1.2, (64, 4))).astype(np.float32)
+    first_bad = C.c_longlong()
+    bad = rh.rh_check_prims(n, seg.ctypes.data_as(C.POINTER(C.c_float)), vs[0], vs[1], W, H, C.byref(first_bad))
     assert bad == 0, (bad, first_bad.value, seg[first_bad.value] if first_bad.value >= 0 else None)

@@ -3,12 +3,13 @@ import numpy as np
 
 
 def bits_equal(a, b):
-    """Bit-exact float32 comparison that treats any NaN as equal to any NaN and -0 == +0."""
-    a = np.asarray(a, np.float32)
-    b = np.asarray(b, np.float32)
+    """Bit-exact float32 comparison: the raw 32-bit patterns must agree (so -0 differs from +0); only the payload of a
+    NaN is left open (any NaN equals any NaN)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
     assert a.shape == b.shape, (a.shape, b.shape)
     both_nan = np.isnan(a) & np.isnan(b)
-    return (a == b) | both_nan
+    return (a.view(np.uint32) == b.view(np.uint32)) | both_nan
 
 
 def assert_bits_equal(a, b, what=""):
