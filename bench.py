@@ -67,6 +67,29 @@ def algorithmic_bytes(n_particles, grid, optical=False):
     return {"integrate": 32 * n_particles + 16 * grid, "splat": 32 * grid, "step": 32 * n_particles + 48 * grid + extra}
 
 
+def config_of(name, wl, world, n_local, n_total):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": f"{name}: {wl['desc']}", "particles_per_gpu": n_local, "particles_total": n_total,
+            "flow_grid": [wl["G"], wl["G"]], "state": "reference defaults (src/index.js:29-57), noise on",
+            "splat": "exact ordered alpha-over (reference semantics)",
+            "l2": "inputs larger than L2 (state 2 x %d MiB per GPU)" % (n_local * 16 >> 20),
+            "parallelism": (f"particle columns sharded over {world} GPU(s), flow blend shared over peer memory (bins owned round-robin)"
+                            if world > 1 else "1 GPU")}
+
+
+def host_info():
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    model = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return cores, model
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -159,6 +182,50 @@ def build_sim(wl, rank, world, local_rank, group):
     return t, first, sp
 
 
+def sharded_parity_check(rank, world, local_rank, group):
+    """N > 1, before anything is timed: a small TALL texture (64 columns x 64*N rows, the shape of the weak-scaling workload)
+    stepped through the default transport must equal the CPU oracle bit for bit -- this rank's shard of the state and the
+    whole flow grid.  Returns True only if every rank agrees."""
+    import torch
+    import torch.distributed as dist
+    import tendrils_b200 as T
+    from oracle import oracle as O
+    from tendrils_b200.spawn import spawnBall
+    from util import bits_equal
+    PW, PH, G, steps = 64, 64 * world, 128, 6
+    t = T.Tendrils(T.Device(G, G, device=local_rank, rank=rank, world_size=world, group=group))
+    t.setup([PW, PH]); t.resize()
+    spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}}).spawn(t)
+    P = O.make_params()
+    cur, prev = O.spawn_ball(PW, PH, 0.3, 0.005), O.spawn_init(PW, PH)
+    targets, flow = np.zeros((PW, PH, 4), np.float32), np.zeros((G, G, 4), np.float32)
+    for _ in range(steps):
+        t.timer.tick()
+        t.step().draw()
+        new = O.integrate(P, cur, targets, flow, np.float32(t.timer.time), np.float32(t.timer.dt))
+        prev, cur = cur, new
+        O.splat(P, cur, prev, flow, np.float32(t.timer.time))
+    c0, c1 = t.particles.col0, t.particles.col1
+    ok = bool(bits_equal(t.particles.buffers[0].download(), cur[c0:c1]).all() and bits_equal(t.flow.download(), flow).all())
+    t.dispose()
+    flag = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def grids_identical(P, world):
+    """after the timed region every rank must hold the same flow grid: compare a checksum of the raw bits"""
+    import torch
+    import torch.distributed as dist
+    bits = P._flow_tensor().view(torch.int32).to(torch.int64)
+    w = torch.arange(1, bits.numel() + 1, device=bits.device, dtype=torch.int64) % 65521
+    cs = torch.stack([bits.sum(), (bits * w).sum()])
+    lo, hi = cs.clone(), cs.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool((lo == hi).all().item())
+
+
 def run_ours(args, wl, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -167,6 +234,14 @@ def run_ours(args, wl, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         group = dist.group.WORLD
     torch.cuda.set_device(local_rank)
+    parity = None
+    if world > 1:
+        parity = sharded_parity_check(rank, world, local_rank, group)
+        if not parity:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "multi-GPU parity check failed", "multi_gpu_parity": False}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(3)
     t, first, sp = build_sim(wl, rank, world, local_rank, group)
     P = t.particles
     n_local = (P.col1 - P.col0) * P.shape[1]
@@ -217,22 +292,55 @@ def run_ours(args, wl, rank, world, local_rank):
     launches = P.stats()["kernel_launches"] - launches0
     frags = P.stats()["last_fragments"]
     tm = P.timing()
+    same_grids = None
     if world > 1:
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
+        ft = torch.tensor([frags], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ft, op=dist.ReduceOp.SUM)
+        frags = int(ft.item())
+        same_grids = grids_identical(P, world)
+        if not same_grids:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "the ranks' flow grids differ after the timed region"}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(4)
 
     # ---- e2e: the same steps with the particle state crossing PCIe both ways every step -------
-    e2e_steps = max(1, min(args.steps, 6))
+    # The public call for callers that keep the state on the host: Tendrils.stepStreamed(host_in, host_out) uploads, steps and
+    # reads back in column chunks (tb_step_streamed); the state round-trips through ONE pinned buffer, every step.
+    e2e_steps = max(1, min(args.steps, 12))
     host = torch.empty((P.col1 - P.col0, P.shape[1], 4), dtype=torch.float32, pin_memory=True)
     hview = host.numpy()
     P.buffers[0].download(out=hview)
+
+    def e2e_step():
+        k = counter["k"]
+        if wl["every"] and k % wl["every"] == 0 and k > 0:
+            P.sync()                               # a respawn works on the device state: bring the host copy in first
+            P.buffers[0].upload(hview)
+            if wl.get("optical"):
+                sp.setPixels(t.video[k % len(t.video)].float() / 255.0)
+            sp.spawn(t)
+            P.buffers[0].download(out=hview)
+        t.timer.tick()
+        t.stepStreamed(hview, hview).draw()
+        if wl.get("optical"):
+            of = t.optical
+            of.setPixels(t.video[k % len(t.video)])
+            of.update({"speedLimit": t.state["speedLimit"], "time": t.timer.time, "viewSize": t.viewSize}).render(t)
+            of.step()
+        counter["k"] = k + 1
+
+    for _ in range(2):
+        e2e_step()
+    P.sync()
     barrier()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
-        P.buffers[0].upload(hview)            # H2D: this step's input state, from pinned memory
-        one_step()
-        P.buffers[0].download(out=hview)      # D2H: the step's result, straight into the pinned buffer
+        e2e_step()
+    P.sync()                                       # the last step's state is back in host memory
     barrier()
     e2e_s = time.perf_counter() - w0
     if world > 1:
@@ -252,45 +360,52 @@ def run_ours(args, wl, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    traffic = None
-    try:        # DRAM bytes of one k_integrate launch from the committed ncu --set full capture of this workload
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("k_integrate")
+    ab = algorithmic_bytes(n_local, grid, bool(wl.get("optical")))
+    traffic = {}
+    try:        # DRAM bytes per launch from the committed ncu --set full captures of this workload (profiles/traffic.json)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
     except Exception:
         pass
-    ab = algorithmic_bytes(n_local, grid, bool(wl.get("optical")))
     fin_us = 1e3 * tm["integrate_ms"] / max(tm["n_integrate"], 1)      # main-stream launch (fused, or the finish half)
     noise_us = 1e3 * tm["noise_ms"] / max(tm["n_integrate"], 1)        # side-stream noise launch, hidden under the splat
     int_us = fin_us + noise_us                                          # device time of logic.frag, all launches
     spl_us = 1e3 * tm["splat_ms"] / max(tm["n_splat"], 1)
     dom_bytes, dom_us = ab["integrate"], int_us
     achieved = dom_bytes / (dom_us * 1e-6) / 1e9
+    splat_gbs = ab["splat"] / (spl_us * 1e-6) / 1e9 if spl_us > 0 else 0.0
     step_gbs = ab["step"] / (ms / args.steps * 1e-3) / 1e9
+    cfg = config_of(args.workload, wl, world, n_local, n_total)
+    cfg["fragments_last_step"] = frags
     out = {
         "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong" if wl.get("rows") else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "particles_per_gpu": n_local, "particles_total": n_total,
-                   "flow_grid": [wl["G"], wl["G"]], "state": "reference defaults (src/index.js:29-57), noise on",
-                   "splat": "exact ordered alpha-over (reference semantics)", "fragments_last_step": frags,
-                   "l2": "inputs larger than L2 (state 2 x %d MiB per GPU)" % (n_local * 16 >> 20),
-                   "parallelism": (f"particle columns sharded over {world} GPU(s), ordered flow fold shared by transport "
-                                   f"'{t.gl.ring}'" if world > 1 else "1 GPU")},
+        "config": cfg,
         "clocks": clocks,
         "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": UNIT, "steps": e2e_steps,
-                "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 16},
+                "h2d_bytes_per_step": n_local * 16, "d2h_bytes_per_step": n_local * 16,
+                "api": "Tendrils.stepStreamed(host, host).draw(): tb_step_streamed, 16 column chunks, one pinned buffer round trip"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_integrate (logic.frag: noise launch + finish launch, device time summed)",
+        "roofline": {"bound": "hbm", "kernel": "k_integrate (logic.frag)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+                     "frac": achieved / peak, "traffic": traffic.get("k_integrate"), "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": dom_us,
                      "integrate_us": int_us, "integrate_main_stream_us": fin_us, "integrate_noise_side_stream_us": noise_us,
                      "splat_us": spl_us,
                      "note": "k_integrate is FP32-issue bound (2 simplex noises per particle), not HBM bound; see DESIGN.md section 3",
+                     "splat_pipeline": {"kernels": "k_splat_hist + k_splat_rows + k_splat_plan + k_splat_scatter + k_splat_fold",
+                                        "algorithmic_bytes": ab["splat"], "avg_us": spl_us, "achieved": splat_gbs, "frac": splat_gbs / peak,
+                                        "traffic": traffic.get("splat_pipeline"),
+                                        "note": "algorithmic bytes = flow grid read + write only; the fragments the ordered blend has to "
+                                                "materialise (16 B each, written once, read once) are implementation traffic"},
                      "whole_step": {"algorithmic_bytes": ab["step"], "achieved": step_gbs, "frac": step_gbs / peak}},
     }
+    if world > 1:
+        out["multi_gpu_parity"] = bool(parity)
+        out["grids_identical_after_timed_region"] = bool(same_grids)
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_arm(args, wl, budget_s=args.cpu_budget, as_reference=False)
+        out["cpu_baseline"] = cpu_arm(args, wl, budget_s=args.cpu_budget, as_reference=False, world=1)
     if world > 1:
         dist.destroy_process_group()
     return out
@@ -299,11 +414,13 @@ def run_ours(args, wl, rank, world, local_rank):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(args, wl, budget_s, as_reference):
+def cpu_arm(args, wl, budget_s, as_reference, world=1):
     from oracle import oracle as O
     O.build()
+    cores, cpu_model = host_info()
+    O.set_threads(cores)                     # every host core, whatever OMP_NUM_THREADS the launcher exported (torchrun: 1)
     R, G = wl["R"], wl["G"]
-    PH = wl.get("rows") or R
+    PH = wl.get("rows") or R * max(world, 1)
     cols = (0, max(min(R // 4, (1 << 22) // PH), 1))   # the bounded sample: the first columns, at most a quarter / 4M particles
     n_sample = (cols[1] - cols[0]) * PH
     Pm = O.make_params()
@@ -357,7 +474,7 @@ def cpu_arm(args, wl, budget_s, as_reference):
     for _ in range(steps):
         one_step()
     el = time.perf_counter() - t0
-    return {"value": n_sample * steps / el, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+    return {"value": n_sample * steps / el, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "nproc": cores, "cpu": cpu_model,
             "sample": f"columns [{cols[0]},{cols[1]}) of the {R}x{PH} particle texture ({n_sample} particles) on the full "
                       f"{G}^2 flow grid, {steps} steps of integrate + ordered splat (+ respawn / optical flow when due), OpenMP over "
                       f"{O.num_threads()} threads; oracle/tendrils_oracle.c",
@@ -367,13 +484,16 @@ def cpu_arm(args, wl, budget_s, as_reference):
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return None
-    cb = cpu_arm(args, wl, budget_s=0, as_reference=True)
+    cb = cpu_arm(args, wl, budget_s=0, as_reference=True, world=world)
+    R = wl["R"]
+    n_total = R * (wl.get("rows") or R * world)
+    cfg = config_of(args.workload, wl, world, n_total // world, n_total)
+    cfg["note"] = "CPU oracle port of the reference shaders (the WebGL reference cannot run here); host cores only"
     return {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "strong" if wl.get("rows") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}",
-                   "note": "CPU oracle port of the reference shaders (the WebGL reference cannot run here); host cores only"},
+        "config": cfg,
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -385,7 +505,8 @@ def main():
     ap.add_argument("--steps", type=int, default=120)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["all"],
+                    help="'all': cfg1, cfg2 and cfg3 in turn, one JSON line each (1 GPU)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -396,6 +517,11 @@ def main():
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             sys.exit("bench.py: --gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    if args.workload == "all":
+        for name in ("cfg1", "cfg2", "cfg3"):
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", str(args.steps), "--warmup", str(args.warmup),
+                            "--impl", args.impl] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []), check=False)
+        return
     wl = WORKLOADS[args.workload]
     # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. NCCL's version
     # banner) is sent to stderr while the benchmark runs

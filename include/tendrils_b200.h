@@ -143,6 +143,15 @@ int tb_clear_flow(tb_ctx *ctx);
  * time and dt in milliseconds (Timer, src/timer.js:24-60). */
 int tb_step(tb_ctx *ctx, float time, float dt);
 
+/* tb_upload(TB_BUF_CURRENT, host_in) + tb_step + tb_download(TB_BUF_CURRENT, host_out) as ONE pipelined pass for callers that
+ * keep the particle state on the host (the reference's CPU mirror Particles.pixels, src/particles.js:76-78,94-117): the
+ * columns go up in n_chunks blocks (1..64) on a copy stream, through the logic pass, and down on a second copy stream, so
+ * that PCIe runs in both directions at once and under the kernels.  ASYNCHRONOUS: returns when everything is queued;
+ * host_in must stay untouched and host_out is complete only after tb_sync (or the next call that reads state back).  Both
+ * should be pinned.  host_in == host_out (the state round-trips through one buffer) is allowed: the upload of a chunk then
+ * follows the previous step's download of that chunk. */
+int tb_step_streamed(tb_ctx *ctx, float time, float dt, const float *host_in, float *host_out, int32_t n_chunks);
+
 /* The flow half of Tendrils.draw(): particles.draw(LINES) with the flow shader into the flow
  * FBO under SRC_ALPHA/ONE_MINUS_SRC_ALPHA blending (src/index.js:278-303,267-268,
  * src/particles.js:147-158, src/flow/index.vert, src/flow/index.frag). */

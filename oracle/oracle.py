@@ -129,6 +129,8 @@ def lib():
         L.or_flow_line.restype = C.c_longlong
         L.or_flow_line.argtypes = [C.POINTER(FlowLineUniforms), C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int]
         L.or_num_threads.restype = C.c_int
+        L.or_set_threads.restype = None
+        L.or_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -143,6 +145,11 @@ def cos(x): return lib().or_cos(float(x))
 def random(cx, cy): return lib().or_random(float(cx), float(cy))
 def snoise3(x, y, z): return lib().or_snoise3(float(x), float(y), float(z))
 def num_threads(): return lib().or_num_threads()
+
+
+def set_threads(n: int):
+    """OpenMP threads of the parallel entry points (a launcher such as torchrun exports OMP_NUM_THREADS=1)."""
+    lib().or_set_threads(int(n))
 
 
 def integrate(P, state, targets, flow, time, dt, cols=None):

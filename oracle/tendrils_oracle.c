@@ -26,6 +26,14 @@ int or_num_threads(void) {
     return 1;
 #endif
 }
+void or_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 
 /* ------------------------------------------------------------------------------------
  * GLSL ES 1.00 built-ins (spec section 8), NaN behaviour as the spec's defining formulas.

@@ -118,6 +118,7 @@ long long or_flow_line(const or_flow_line_uniforms *U, int n_vertices, const flo
                        float *flow, int W, int H);
 
 int or_num_threads(void);
+void or_set_threads(int n);     /* OpenMP threads of the parallel entry points (benchmarks: all host cores) */
 
 #ifdef __cplusplus
 }

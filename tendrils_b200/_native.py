@@ -56,6 +56,7 @@ SYMBOLS = {
     "tb_resize_flow": (C.c_int, [_ctx, C.c_int32, C.c_int32]),
     "tb_clear_flow": (C.c_int, [_ctx]),
     "tb_step": (C.c_int, [_ctx, C.c_float, C.c_float]),
+    "tb_step_streamed": (C.c_int, [_ctx, C.c_float, C.c_float, _fp, _fp, C.c_int32]),
     "tb_splat_flow": (C.c_int, [_ctx, C.c_float]),
     "tb_splat_collect": (C.c_int, [_ctx, C.c_float]),
     "tb_splat_fold": (C.c_int, [_ctx]),

@@ -97,6 +97,15 @@ struct tb_ctx {
     int n_sms = 148;
     int scatter_ctas = 0, fold_ctas = 0, hist_ctas = 0;
 
+    // tb_step_streamed: column chunks over two copy streams (PCIe both ways at once) around the chunked logic pass
+    static constexpr int kMaxChunks = 64;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_int[kMaxChunks] = {}, ev_d2h[kMaxChunks] = {};
+    cudaEvent_t ev_main = nullptr;         // the main stream at the start of a streamed step
+    int chunks_inflight = 0;               // chunks of the last streamed step whose copies may still run
+    float4 *spare = nullptr;               // third state buffer: the upload of a streamed step lands here while the previous
+                                           // step's flow splat still reads the other two
+
     int *d_flag = nullptr;                 // device scratch flag
     int *h_flag = nullptr;                 // pinned
     bool targets_finite = true;
@@ -444,6 +453,16 @@ int resolve_pending(tb_ctx *c) {
     return fail(c, TB_ERR_OVERFLOW, "tendrils-b200: flow splat: the fragment bins could not be sized");
 }
 
+// Make the main stream wait for the copies of the last streamed step (it owns the state buffers again afterwards).
+int join_copies(tb_ctx *c) {
+    for (int i = 0; i < c->chunks_inflight; ++i) {
+        TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[i], 0));
+        TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_d2h[i], 0));
+    }
+    c->chunks_inflight = 0;
+    return TB_OK;
+}
+
 int collect(tb_ctx *c, float time) {
     TB_REQUIRE(c, c->have_state, "tb_set_state must be called before the flow splat");
     if (int r = resolve_pending(c)) return r;
@@ -700,9 +719,17 @@ int tb_destroy(tb_ctx *c) {
     cudaSetDevice(c->device);
     if (c->side) cudaStreamSynchronize(c->side);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->h2d) { cudaStreamSynchronize(c->h2d); cudaStreamDestroy(c->h2d); }
+    if (c->d2h) { cudaStreamSynchronize(c->d2h); cudaStreamDestroy(c->d2h); }
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    for (int i = 0; i < tb_ctx::kMaxChunks; ++i) {
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_int[i]) cudaEventDestroy(c->ev_int[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+    }
     tiles_release(c);
     cudaFree(c->ow_flags); cudaFree(c->ow_totals); cudaFree(c->ow_scratch);
-    cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->targets); cudaFree(c->flow);
+    cudaFree(c->buf[0]); cudaFree(c->buf[1]); cudaFree(c->spare); cudaFree(c->targets); cudaFree(c->flow);
     cudaFree(c->frames);
     cudaFree(c->line_attr); cudaFree(c->line_verts); cudaFree(c->line_bbox);
     cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->d_flag);
@@ -751,12 +778,8 @@ int tb_clear_flow(tb_ctx *c) {
     return TB_OK;
 }
 
-int tb_step(tb_ctx *c, float time, float dt) {
-    TB_REQUIRE(c, c, "null context");
-    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_step");
-    TB_CUDA(c, cudaSetDevice(c->device));
-    if (int r = resolve_pending(c)) return r;
-    std::swap(c->buf[0], c->buf[1]);                       // utils.step(buffers), src/particles.js:128
+namespace {
+IntegrateArgs integrate_args(tb_ctx *c, float time, float dt) {
     const tb_state &S = c->state;
     IntegrateArgs A{};
     A.S = S;
@@ -774,7 +797,6 @@ int tb_step(tb_ctx *c, float time, float dt) {
     A.use_noise = !(S.noiseWeight == 0.0f && tame(S.varyNoise, 1e6f) && tame(S.noiseScale, 1e6f) &&
                     tame(S.varyNoiseScale, 1e6f) && tame(S.noiseSpeed, 1e6f) && tame(S.varyNoiseSpeed, 1e6f) &&
                     tame(time, 1e9f) && tame(dt, 1e6f));
-    cudaEvent_t *ev = c->ev_ring[0][c->ev_count[0] % tb_ctx::kTimingSlots];
     auto is_pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
     A.pow2_res = is_pow2(c->PW) && is_pow2(c->PH) && static_cast<long long>(c->PW) * c->PH <= (1LL << 40);
     A.inv_resx = 1.0f / static_cast<float>(c->PW);
@@ -784,10 +806,23 @@ int tb_step(tb_ctx *c, float time, float dt) {
     A.packed_noise = scalar_noise ? 0 : 1;
     A.pk.one = 1.0f; A.pk.neg_one = -1.0f; A.pk.neg_zero = -0.0f;
     A.wander = c->wander;
+    return A;
+}
+}  // namespace
+
+int tb_step(tb_ctx *c, float time, float dt) {
+    TB_REQUIRE(c, c, "null context");
+    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_step");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
+    if (int r = join_copies(c)) return r;
+    std::swap(c->buf[0], c->buf[1]);                       // utils.step(buffers), src/particles.js:128
+    const IntegrateArgs A = integrate_args(c, time, dt);
+    cudaEvent_t *ev = c->ev_ring[0][c->ev_count[0] % tb_ctx::kTimingSlots];
     const dim3 grid(blocks_for(c->PH, 256), static_cast<unsigned>(A.cols));
     if (A.use_noise && c->overlap && c->splat_since_step) {
         // The noise does not read the flow grid: evaluate it on the low-priority side stream, where it
-        // runs under the previous step's sort + fold still queued on the main stream; the rest of the
+        // runs under the previous step's flow splat still queued on the main stream; the rest of the
         // shader follows on the main stream.  The side stream only waits for the state to be final.
         cudaEvent_t *evn = c->ev_ring[2][c->ev_count[2] % tb_ctx::kTimingSlots];
         TB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_state, 0));
@@ -810,6 +845,68 @@ int tb_step(tb_ctx *c, float time, float dt) {
     TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
     c->ev_count[0] += 1;
     c->splat_since_step = false;
+    return TB_OK;
+}
+
+// tb_upload(CURRENT, host_in) + tb_step + tb_download(CURRENT, host_out) as one pipelined pass over column chunks: chunk i
+// goes up on the h2d stream, through the logic pass on the main stream and down on the d2h stream while chunk i + 1 goes up.
+// Returns as soon as everything is queued; host_out is complete after tb_sync.
+int tb_step_streamed(tb_ctx *c, float time, float dt, const float *host_in, float *host_out, int32_t n_chunks) {
+    TB_REQUIRE(c, c && host_in && host_out, "null argument");
+    TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_step_streamed");
+    TB_REQUIRE(c, n_chunks >= 1 && n_chunks <= tb_ctx::kMaxChunks, "tb_step_streamed: 1..64 chunks");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
+    const int cols = c->col1 - c->col0;
+    const int C = std::min<int>(n_chunks, cols);
+    if (!c->h2d) {
+        TB_CUDA(c, cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+        TB_CUDA(c, cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+        TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        for (int i = 0; i < tb_ctx::kMaxChunks; ++i) {
+            TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_int[i], cudaEventDisableTiming));
+            TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    if (!c->spare) TB_CUDA(c, cudaMalloc(&c->spare, static_cast<size_t>(c->n_local) * sizeof(float4)));
+    // The upload goes into the spare buffer, which nothing queued reads (the previous flow splat reads the other two), so it
+    // only has to follow the previous streamed step's download chunk by chunk: on the device that download is long done
+    // with the spare buffer's former life, and when the caller round-trips the state through one host buffer it is the
+    // host memory that must be complete.  The logic pass then writes over the PREVIOUS state, in stream order after the splat.
+    const int prev_chunks = c->chunks_inflight;
+    if (prev_chunks != C) {                                 // another chunking than last time: no chunk-wise overlap across the steps
+        for (int i = 0; i < prev_chunks; ++i) TB_CUDA(c, cudaStreamWaitEvent(c->h2d, c->ev_d2h[i], 0));
+    }
+    float4 *in = c->spare, *out = c->buf[1];
+    c->spare = c->buf[0];                                   // utils.step(buffers) over three buffers
+    c->buf[0] = out;
+    c->buf[1] = in;
+    IntegrateArgs A = integrate_args(c, time, dt);
+    cudaEvent_t *ev = c->ev_ring[0][c->ev_count[0] % tb_ctx::kTimingSlots];
+    TB_CUDA(c, cudaEventRecord(ev[0], c->stream));
+    for (int i = 0; i < C; ++i) {
+        const int x0 = static_cast<int>(static_cast<long long>(cols) * i / C), x1 = static_cast<int>(static_cast<long long>(cols) * (i + 1) / C);
+        const size_t off = static_cast<size_t>(x0) * c->PH, n = static_cast<size_t>(x1 - x0) * c->PH;
+        if (prev_chunks == C) TB_CUDA(c, cudaStreamWaitEvent(c->h2d, c->ev_d2h[i], 0));
+        TB_CUDA(c, cudaMemcpyAsync(c->buf[1] + off, host_in + 4 * off, n * sizeof(float4), cudaMemcpyHostToDevice, c->h2d));
+        TB_CUDA(c, cudaEventRecord(c->ev_h2d[i], c->h2d));
+        TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_h2d[i], 0));
+        IntegrateArgs Ai = A;
+        Ai.in = A.in + off; Ai.out = A.out + off; Ai.targets = A.targets + off;
+        Ai.col0 = c->col0 + x0; Ai.cols = x1 - x0;
+        k_integrate<kFused><<<dim3(blocks_for(c->PH, 256), static_cast<unsigned>(x1 - x0)), 256, 0, c->stream>>>(Ai);
+        if (int r = check_launch(c, "k_integrate")) return r;
+        TB_CUDA(c, cudaEventRecord(c->ev_int[i], c->stream));
+        TB_CUDA(c, cudaStreamWaitEvent(c->d2h, c->ev_int[i], 0));
+        TB_CUDA(c, cudaMemcpyAsync(host_out + 4 * off, c->buf[0] + off, n * sizeof(float4), cudaMemcpyDeviceToHost, c->d2h));
+        TB_CUDA(c, cudaEventRecord(c->ev_d2h[i], c->d2h));
+    }
+    TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
+    TB_CUDA(c, cudaEventRecord(c->ev_state, c->stream));
+    c->ev_count[0] += 1;
+    c->splat_since_step = false;
+    c->chunks_inflight = C;
     return TB_OK;
 }
 
@@ -933,6 +1030,7 @@ int tb_reset(tb_ctx *c) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
     if (int r = resolve_pending(c)) return r;
+    if (int r = join_copies(c)) return r;
     for (int b = 0; b < 2; ++b) {
         k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(c->buf[b], c->n_local);
         if (int r = check_launch(c, "k_spawn_init")) return r;
@@ -945,6 +1043,7 @@ int tb_spawn_init(tb_ctx *c, tb_target target) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
     if (int r = resolve_pending(c)) return r;
+    if (int r = join_copies(c)) return r;
     float4 *out = spawn_out(c, target);
     k_spawn_init<<<blocks_for(c->n_local, 256), 256, 0, c->stream>>>(out, c->n_local);
     if (int r = check_launch(c, "k_spawn_init")) return r;
@@ -955,6 +1054,7 @@ int tb_spawn_ball(tb_ctx *c, float radius, float speed, tb_target target) {
     TB_REQUIRE(c, c, "null context");
     TB_CUDA(c, cudaSetDevice(c->device));
     if (int r = resolve_pending(c)) return r;
+    if (int r = join_copies(c)) return r;
     SpawnArgs A{};
     A.out = spawn_out(c, target);
     A.PW = c->PW; A.PH = c->PH;
@@ -991,6 +1091,7 @@ int tb_spawn_pixels(tb_ctx *c, const tb_pixel_spawner *params, tb_spawn_variant 
     TB_REQUIRE(c, c->have_state, "tb_set_state must be called before tb_spawn_pixels");
     TB_CUDA(c, cudaSetDevice(c->device));
     if (int r = resolve_pending(c)) return r;
+    if (int r = join_copies(c)) return r;
     SpawnArgs A{};
     A.U = *params;
     A.PW = c->PW; A.PH = c->PH;
@@ -1050,6 +1151,7 @@ int tb_upload(tb_ctx *c, tb_buffer which, const float *host, int64_t n_floats) {
     TB_REQUIRE(c, c && host, "null argument");
     TB_CUDA(c, cudaSetDevice(c->device));
     if (int r = resolve_pending(c)) return r;
+    if (int r = join_copies(c)) return r;
     float4 *dst; int64_t n;
     if (int r = buffer_of(c, which, &dst, &n)) return r;
     TB_REQUIRE(c, n == n_floats, "tb_upload: size mismatch");
@@ -1065,6 +1167,7 @@ int tb_download(tb_ctx *c, tb_buffer which, float *host, int64_t n_floats) {
     TB_REQUIRE(c, c && host, "null argument");
     TB_CUDA(c, cudaSetDevice(c->device));
     if (int r = resolve_pending(c)) return r;
+    if (int r = join_copies(c)) return r;
     float4 *src; int64_t n;
     if (int r = buffer_of(c, which, &src, &n)) return r;
     TB_REQUIRE(c, n == n_floats, "tb_download: size mismatch");
@@ -1199,6 +1302,8 @@ int tb_sync(tb_ctx *c) {
     if (int r = resolve_pending(c)) return r;
     TB_CUDA(c, cudaStreamSynchronize(c->side));
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->h2d) TB_CUDA(c, cudaStreamSynchronize(c->h2d));
+    if (c->d2h) TB_CUDA(c, cudaStreamSynchronize(c->d2h));
     return TB_OK;
 }
 

@@ -252,6 +252,20 @@ class Particles:
         else:
             raise N.TendrilsError(f"tendrils-b200: shader {sh!r} cannot run as a logic pass")
 
+    def step_streamed(self, update, host_in, host_out, chunks=16):
+        """The logic pass for callers that keep the state on the host: `host_in` ([columns, rows, 4] float32, ideally pinned) is
+        uploaded, stepped and read back into `host_out` chunk by chunk, PCIe busy in both directions (tb_step_streamed).
+        Asynchronous: `host_out` is complete after sync()."""
+        u = dict(update)
+        shape = (self.col1 - self.col0, self.shape[1], 4)
+        for a in (host_in, host_out):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == shape and a.flags["C_CONTIGUOUS"]):
+                raise N.TendrilsError(f"tendrils-b200: step_streamed needs C-contiguous float32 arrays of shape {shape}")
+        st = _state_struct(u)
+        N.check(self._ctx, self._L.tb_set_state(self._ctx, C.byref(st)))
+        N.check(self._ctx, self._L.tb_step_streamed(self._ctx, float(u["time"]), float(u["dt"]), host_in.ctypes.data_as(N._fp),
+                                                    host_out.ctypes.data_as(N._fp), int(chunks)))
+
     def draw(self, update, mode="LINES"):                               # src/particles.js:147-158
         """Line draw of all particles with `self.render`; only the flow shader is in scope."""
         if mode != "LINES" or not (isinstance(self.render, Shader) and self.render.kind == "flow"):
@@ -420,6 +434,18 @@ class Tendrils:
                 "flow": self.flow, "targets": self.targets,
                 "viewSize": self.viewSize, "viewRes": self.viewRes})
             self.particles.step(self.uniforms["update"])
+        return self
+
+    def stepStreamed(self, host_in, host_out, chunks=16):
+        """step() with the particle state coming from and going back to host memory (Particles.step_streamed)."""
+        if not self.timer.paused:
+            self.particles.logic = self.logicShader
+            self.uniforms["update"].update(self.state)
+            self.uniforms["update"].update({
+                "dt": self.timer.dt, "time": self.timer.time, "start": self.timer.since,
+                "flow": self.flow, "targets": self.targets,
+                "viewSize": self.viewSize, "viewRes": self.viewRes})
+            self.particles.step_streamed(self.uniforms["update"], host_in, host_out, chunks)
         return self
 
     def draw(self):                                                     # :278-303 (flow half)

@@ -97,6 +97,35 @@ def test_strip_sizes_and_split_maps_bit_exact(T, oracle, R, G, radius, steps):
     assert_bits_equal(t.particles.buffers[0].download(), sim.cur, "state")
 
 
+@pytest.mark.parametrize("R,G,chunks", [(96, 50, 16), (64, 32, 1), (40, 24, 64)])
+def test_streamed_step_bit_exact(T, oracle, R, G, chunks):
+    """Tendrils.stepStreamed: the state comes from and goes back to ONE host buffer every step (tb_step_streamed, chunked
+    copies on two streams around the chunked logic pass) -- same results as upload + step + download, flow splat included."""
+    from tendrils_b200.spawn import spawnBall
+    t = make(T, R, G)
+    sim = OracleSim(oracle, R, G, G, oracle_params(oracle, t))
+    spawnBall(t.gl, {"uniforms": {"radius": 0.3, "speed": 0.005}}).spawn(t)
+    sim.spawn_ball(0.3, 0.005)
+    host = t.particles.buffers[0].download()
+    for k in range(10):
+        t.timer.tick()
+        if k == 6:                                   # an ordinary step in between: the copies are joined, the buffers rotate as two
+            t.particles.sync()
+            t.particles.buffers[0].upload(host)
+            t.step().draw()
+            host = t.particles.buffers[0].download()
+        else:
+            t.stepStreamed(host, host, chunks).draw()
+        sim.step(np.float32(t.timer.time), np.float32(t.timer.dt))
+        sim.draw(np.float32(t.timer.time))
+        if k in (0, 5, 6, 9):
+            t.particles.sync()
+            assert_bits_equal(host, sim.cur, f"host copy of the state after step {k}")
+            assert_bits_equal(t.flow.download(), sim.flow, f"flow after step {k}")
+            assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"device state after step {k}")
+            assert_bits_equal(t.particles.buffers[1].download(), sim.prev, f"previous state after step {k}")
+
+
 # ---------------------------------------------------------------------------------------------
 # spawners
 # ---------------------------------------------------------------------------------------------
