@@ -553,12 +553,21 @@ int queue_owners(tb_ctx *c, float time) {
         k_owners_barrier<<<1, 32, 0, c->stream>>>(c->ow_peers, c->ow_flags, phase, epoch);
         return check_launch(c, "k_owners_barrier");
     };
+    // TB_OWNERS_DEBUG=<epoch>: time the phases of that draw on every rank (diagnostics, stderr)
+    static const int dbg_epoch = std::getenv("TB_OWNERS_DEBUG") ? std::atoi(std::getenv("TB_OWNERS_DEBUG")) : -1;
+    const bool dbg = static_cast<int>(epoch) == dbg_epoch;
+    static cudaEvent_t dbg_ev[12];
+    int dbg_n = 0;
+    auto mark = [&]() { if (dbg) { cudaEventCreate(&dbg_ev[dbg_n]); cudaEventRecord(dbg_ev[dbg_n++], c->stream); } };
     const int mp = c->map_parity;
     c->map_parity ^= 1;
+    mark();
     if (int r = launch_count(c, mp)) return r;
+    mark();
     k_owners_share<<<kMaxBins / 256, 256, 0, c->stream>>>(c->bin_total, c->n_bins + mp, c->ow_peers);
     if (int r = check_launch(c, "k_owners_share")) return r;
     if (int r = barrier(0)) return r;                      // every rank's totals are in every table
+    mark();
     uint32_t *bin_sum = c->ow_scratch, *scat_off = bin_sum + kMaxBins, *own_begin = scat_off + kMaxBins, *own_count = own_begin + kMaxBins;
     OwnerPlanArgs PA{};
     PA.T = T;
@@ -580,8 +589,11 @@ int queue_owners(tb_ctx *c, float time) {
     if (int r = check_launch(c, "k_owners_plan")) return r;
     TB_CUDA(c, cudaMemcpyAsync(c->h_plan, c->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, c->stream));
     TB_CUDA(c, cudaEventRecord(c->ev_plan, c->stream));
+    mark();
     if (int r = launch_scatter(c, time, mp, scat_off, c->ow_bins, P)) return r;
+    mark();
     if (int r = barrier(1)) return r;                      // every rank's fragments are in their owners' bins
+    mark();
     c->fold_parity = mp;
     FoldArgs FA{};
     FA.g = c->geom;
@@ -600,7 +612,19 @@ int queue_owners(tb_ctx *c, float time) {
     FA.n_flow = nf;
     k_splat_fold<<<c->fold_ctas, kFoldThreads, fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)), c->stream>>>(FA);
     if (int r = check_launch(c, "k_splat_fold")) return r;
+    mark();
     if (int r = barrier(2)) return r;                      // every grid is complete
+    mark();
+    if (dbg) {
+        cudaStreamSynchronize(c->stream);
+        float ms[8] = {};
+        for (int k = 0; k + 1 < dbg_n; ++k) cudaEventElapsedTime(&ms[k], dbg_ev[k], dbg_ev[k + 1]);
+        std::fprintf(stderr, "[owners dbg] rank %d: hist+rows %.0f us, share+barrier0 %.0f us, plan %.0f us, scatter %.0f us, barrier1 %.0f us, "
+                             "fold %.0f us, barrier2 %.0f us (own frags %llu)\n",
+                     c->ow_rank, 1e3 * ms[0], 1e3 * ms[1], 1e3 * ms[2], 1e3 * ms[3], 1e3 * ms[4], 1e3 * ms[5], 1e3 * ms[6],
+                     static_cast<unsigned long long>(c->h_plan->total));
+        for (int k = 0; k < dbg_n; ++k) cudaEventDestroy(dbg_ev[k]);
+    }
     TB_CUDA(c, cudaEventRecord(ev[1], c->stream));
     return TB_OK;
 }

@@ -386,25 +386,26 @@ __device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__r
             for (uint32_t b = 0; b < cnt; ++b) ns[k] += bin_total[first + b];
         }
     }
-    auto want = [&](uint32_t frags, uint32_t cap_ls) -> uint32_t {
+    auto want = [&](uint32_t frags, unsigned long long at) -> uint32_t {
         uint32_t ls = 0;
-        if (frags > split_at) ls = 3;
-        if (frags > 4u * split_at) ls = 5;
-        if (frags > 16u * split_at) ls = 7;
-        if (ls > static_cast<uint32_t>(lS)) ls = static_cast<uint32_t>(lS);
-        return ls < cap_ls ? ls : cap_ls;
+        if (frags > at) ls = 3;
+        if (frags > 4ull * at) ls = 5;
+        if (frags > 16ull * at) ls = 7;
+        return ls > static_cast<uint32_t>(lS) ? static_cast<uint32_t>(lS) : ls;
     };
-    uint32_t cap_ls = 7;
+    // raise the threshold until the bins fit: the most crowded strips are the ones that stay split
+    unsigned long long at = split_at;
     unsigned long long base = 0ull;
-    for (;;) {                                   // lower the finest split until the bins fit
+    for (int guard = 0; guard < 64; ++guard) {
         unsigned long long bins = 0ull;
 #pragma unroll
         for (int k = 0; k < kPlanStrips; ++k)
-            if (u0 + k < T) bins += 1ull << want(ns[k], cap_ls);
+            if (u0 + k < T) bins += 1ull << want(ns[k], at);
         base = block_excl_scan64(bins, s_warp, s_total);
-        if (*s_total <= static_cast<unsigned long long>(kMaxBins) || cap_ls == 0u) break;
-        cap_ls = cap_ls > 5u ? 5u : (cap_ls > 3u ? 3u : 0u);
+        if (*s_total <= static_cast<unsigned long long>(kMaxBins)) break;
+        at += (at >> 1) + 1ull;
     }
+    const unsigned long long cap_ls = at;
     if (threadIdx.x == 0) *n_bins_next = static_cast<uint32_t>(*s_total);
 #pragma unroll
     for (int k = 0; k < kPlanStrips; ++k) {
