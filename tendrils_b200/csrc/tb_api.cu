@@ -72,6 +72,7 @@ struct tb_ctx {
     int map_parity = 0;
     int fold_parity = 0;                   // the map the last collect used
     uint32_t split_at = 8192;              // fragments per strip above which the next draw gives the strip 8 (32, 128) bins
+    uint32_t share_at = 12288;             // fragments per bin above which 2 (4, 8) warps share the bin's fold
     PlanOut *d_plan = nullptr;
     PlanOut *h_plan = nullptr;             // pinned; valid once ev_plan has completed
     cudaEvent_t ev_plan = nullptr;
@@ -232,7 +233,7 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     TB_CUDA(c, cudaMalloc(&c->seg_total, 2 * static_cast<size_t>(kMaxBins) * kHistSegs * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->bin_total, static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->bin_off, static_cast<size_t>(kMaxBins + 1) * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->items, static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->items, 8 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->split_map, 2 * static_cast<size_t>(T) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->bin_info, 2 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->n_bins, 2 * sizeof(uint32_t)));
@@ -378,6 +379,7 @@ int launch_collect(tb_ctx *c, float time) {
     PA.items = c->items;
     PA.cap = c->bin_cap;
     PA.split_at = c->split_at;
+    PA.share_at = c->share_at;
     PA.too_many = c->tickets + 4;
     PA.tickets = c->tickets;
     PA.map_next = c->split_map + static_cast<size_t>(mp ^ 1) * T;
@@ -580,6 +582,7 @@ int queue_owners(tb_ctx *c, float time) {
     PA.bin_sum = bin_sum; PA.scat_off = scat_off; PA.own_begin = own_begin; PA.own_count = own_count;
     PA.items = c->items;
     PA.split_at = c->split_at;
+    PA.share_at = c->share_at;
     PA.tickets = c->tickets;
     PA.map_next = c->split_map + static_cast<size_t>(mp ^ 1) * T;
     PA.bin_info_next = c->bin_info + static_cast<size_t>(mp ^ 1) * kMaxBins;
@@ -689,6 +692,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     c->overlap = std::getenv("TB_OVERLAP") != nullptr;
     c->stage_timing = std::getenv("TB_STAGE_TIMING") != nullptr;
     if (const char *e = std::getenv("TB_SPLIT_AT")) c->split_at = static_cast<uint32_t>(std::max(64, std::atoi(e)));
+    if (const char *e = std::getenv("TB_SHARE_AT")) c->share_at = static_cast<uint32_t>(std::max(64, std::atoi(e)));
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));

@@ -64,8 +64,8 @@ struct OwnerPlanArgs {
     uint32_t *__restrict__ scat_off;           // [kMaxBins] where MY fragments of bin b start in the array of rank b % n
     uint32_t *__restrict__ own_begin;          // [kMaxBins] for the bins I own: where the bin starts in my array ...
     uint32_t *__restrict__ own_count;          // [kMaxBins] ... and how many fragments it holds
-    uint32_t *__restrict__ items;              // [kMaxBins] bins I own that have fragments, longest first
-    uint32_t split_at;
+    uint32_t *__restrict__ items;              // [8 kMaxBins] fold work items of the bins I own, longest first
+    uint32_t split_at, share_at;
     uint32_t *tickets;
     uint32_t *map_next, *bin_info_next, *n_bins_next;
     PlanOut *out;
@@ -143,11 +143,11 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
         A.tickets[0] = 0u; A.tickets[1] = 0u; A.tickets[2] = 0u;
     }
     unsigned long long run = in_class ? s_cls[o * C + i] : 0ull;
-    uint32_t rank[kOwnerPlanPer];
+    uint32_t rank[kOwnerPlanPer], lparts[kOwnerPlanPer];
     int bucket[kOwnerPlanPer];
 #pragma unroll
     for (int k = 0; k < kOwnerPlanPer; ++k) {
-        rank[k] = 0u; bucket[k] = 0;
+        rank[k] = 0u; bucket[k] = 0; lparts[k] = 0u;
         const int b = o + P * (i * K + k);
         if (in_class && k < K && b < B) {
             A.scat_off[b] = ok ? static_cast<uint32_t>(run) + pre[k] : 0u;
@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
                 A.own_begin[b] = ok ? static_cast<uint32_t>(run) : 0u;
                 A.own_count[b] = ok ? S[k] : 0u;
                 bucket[k] = __clz(S[k] | 1u);
-                if (ok && S[k]) rank[k] = atomicAdd(&s_bucket[bucket[k]], 1u);
+                if (ok && S[k]) {
+                    lparts[k] = fold_lparts(S[k], (1u << A.lS) >> (A.bin_info[b] >> 24), A.share_at);
+                    rank[k] = atomicAdd(&s_bucket[bucket[k]], 1u << lparts[k]);
+                }
             }
             run += S[k];
         }
@@ -171,7 +174,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
 #pragma unroll
     for (int k = 0; k < kOwnerPlanPer; ++k) {
         const int b = o + P * (i * K + k);
-        if (in_class && k < K && b < B && o == A.me && ok && S[k]) A.items[s_bucket[bucket[k]] + rank[k]] = static_cast<uint32_t>(b);
+        if (in_class && k < K && b < B && o == A.me && ok && S[k])
+            for (uint32_t part = 0; part < (1u << lparts[k]); ++part)
+                A.items[s_bucket[bucket[k]] + rank[k] + part] = static_cast<uint32_t>(b) | (part << 16) | (lparts[k] << 24);
     }
     // the next draw's split map, from the fragments per strip over ALL ranks: identical on every rank
     plan_next_map(A.T, A.lS, A.bm.map, A.bin_sum, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);

@@ -331,9 +331,10 @@ struct PlanArgs {
     const uint32_t *__restrict__ bin_info;     // [n_bins] strip | sub << 16 | log2(bins of the strip) << 24
     const uint32_t *__restrict__ bin_total;    // [n_bins]
     uint32_t *__restrict__ bin_off;            // [n_bins + 1]
-    uint32_t *__restrict__ items;              // [kMaxBins] bins with fragments, longest first
+    uint32_t *__restrict__ items;              // [8 kMaxBins] fold work items, longest first: bin | part << 16 | log2(parts) << 24
     uint32_t cap;                              // capacity of the bin array (fragments)
     uint32_t split_at;                         // a strip with more fragments than this gets 8 bins next time, 4x: 32, 16x: 128
+    uint32_t share_at;                         // a bin with more fragments than this is folded by 2 warps, 2x: 4, 4x: 8
     uint32_t *too_many;                        // set by k_splat_rows; reset here
     uint32_t *tickets;                         // [0] hist (reset for the next draw), [1] scatter, [2] fold, [3] items
     uint32_t *map_next;                        // [T]   the next draw's map ...
@@ -419,6 +420,13 @@ __device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__r
     }
 }
 
+// log2 of the warps that share the fold of a bin of n fragments over R texels (every one streams the whole bin)
+__device__ __forceinline__ uint32_t fold_lparts(uint32_t n, uint32_t R, uint32_t share_at) {
+    uint32_t lp = 0;
+    while (lp < 3u && (R >> (lp + 1)) >= 1u && (n >> lp) > share_at) ++lp;
+    return lp;
+}
+
 __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     __syncthreads();
     const bool ok = s_ok != 0u;
     unsigned long long run = ex;
-    uint32_t rank[kPlanBins];
+    uint32_t rank[kPlanBins], lparts[kPlanBins];
     int bucket[kPlanBins];
 #pragma unroll
     for (int k = 0; k < kPlanBins; ++k) {
@@ -455,7 +463,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
         run += n[k];
         // work list, longest bins first (bucketed by log2 of the length): the tail of the fold is short bins
         bucket[k] = __clz(n[k] | 1u);
-        rank[k] = (ok && n[k]) ? atomicAdd(&s_bucket[bucket[k]], 1u) : 0u;
+        lparts[k] = 0u;
+        if (ok && n[k]) lparts[k] = fold_lparts(n[k], (1u << A.lS) >> (A.bin_info[t0 + k] >> 24), A.share_at);
+        rank[k] = (ok && n[k]) ? atomicAdd(&s_bucket[bucket[k]], 1u << lparts[k]) : 0u;
     }
     if (threadIdx.x == 0) A.bin_off[B] = ok ? static_cast<uint32_t>(s_total) : 0u;
     __syncthreads();
@@ -468,7 +478,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPlanBins; ++k)
-        if (ok && n[k]) A.items[s_bucket[bucket[k]] + rank[k]] = static_cast<uint32_t>(t0 + k);
+        if (ok && n[k])
+            for (uint32_t part = 0; part < (1u << lparts[k]); ++part)
+                A.items[s_bucket[bucket[k]] + rank[k] + part] = static_cast<uint32_t>(t0 + k) | (part << 16) | (lparts[k] << 24);
 
     plan_next_map(A.T, A.lS, A.bm.map, A.bin_total, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);
 }
@@ -688,8 +700,10 @@ struct FoldArgs {
     int n_flow;
 };
 
+constexpr int kFoldRing = 64;                            // compaction ring of a warp that shares a long bin
 struct __align__(16) FoldWarp {             // shared memory of one warp, followed by the bin's texels: float4[texels per strip]
     Frag stage[2][kFoldStage];
+    Frag ring[kFoldRing];
     float4 term[32];                         // chained batches: src*a per lane
     float om[32];                            //                  1 - a per lane
     unsigned long long bar[2];
@@ -820,10 +834,14 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
         if (lane == 0) item = atomicAdd(A.ticket, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const uint32_t bin_id = A.items[item];
+        const uint32_t icode = A.items[item];                        // bin | part << 16 | log2(parts) << 24
+        const uint32_t bin_id = icode & 0xffffu, part = (icode >> 16) & 0xffu, lparts = icode >> 24;
         const uint32_t code = A.bin_info[bin_id];
         const uint32_t st = code & 0xffffu, sub = (code >> 16) & 0xffu, ls = code >> 24;
-        const uint32_t R = S >> ls, lo = sub * R;                     // the bin's texels: local indices [lo, lo + R)
+        // the bin's texels are local indices [sub * (S >> ls), + S >> ls); a long bin is shared by 2^lparts warps, each of which
+        // streams the whole bin and keeps the fragments of its part of the texels
+        const uint32_t R = (S >> ls) >> lparts, lo = sub * (S >> ls) + part * R;
+        const bool whole = lparts == 0u;
         const uint32_t begin = A.bin_off[bin_id], n = A.bin_count ? A.bin_count[bin_id] : A.bin_off[bin_id + 1] - begin;
         const uint32_t n_stage = (n + kFoldStage - 1) / kFoldStage;
         const Frag *bin = A.bins + begin;
@@ -844,6 +862,7 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
             tex[l] = v;
         }
         __syncwarp();
+        uint32_t head = 0, queued = 0;
         for (uint32_t j = 0; j < n_stage; ++j) {
             const uint32_t s = j & 1u;
             const uint32_t c = (n - j * kFoldStage < static_cast<uint32_t>(kFoldStage)) ? n - j * kFoldStage : static_cast<uint32_t>(kFoldStage);
@@ -852,16 +871,49 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
             const bool a0 = static_cast<uint32_t>(lane) < c, a1 = static_cast<uint32_t>(32 + lane) < c;
             if (a0) f0 = W.stage[s][lane];
             if (a1) f1 = W.stage[s][32 + lane];
-            const FoldPrep p0 = fold_prep(f0, a0, lo, A.time, lane);
-            if (c > 32u) {
-                const FoldPrep p1 = fold_prep(f1, a1, lo, A.time, lane);
-                fold_apply(W, tex, p0, a0, lane);
-                fold_apply(W, tex, p1, a1, lane);
+            if (whole) {
+                const FoldPrep p0 = fold_prep(f0, a0, lo, A.time, lane);
+                if (c > 32u) {
+                    const FoldPrep p1 = fold_prep(f1, a1, lo, A.time, lane);
+                    fold_apply(W, tex, p0, a0, lane);
+                    fold_apply(W, tex, p1, a1, lane);
+                } else {
+                    fold_apply(W, tex, p0, a0, lane);
+                }
             } else {
-                fold_apply(W, tex, p0, a0, lane);
+                // keep my texels' fragments, in order, in the ring; blend whenever 32 are queued
+                const bool m0 = a0 && ((f0.key & kKeyLocalMask) - lo) < R, m1 = a1 && ((f1.key & kKeyLocalMask) - lo) < R;
+                const uint32_t b0 = __ballot_sync(0xffffffffu, m0), b1 = __ballot_sync(0xffffffffu, m1);
+                const uint32_t lt_mask = (1u << lane) - 1u;
+                if (m0) W.ring[(head + queued + static_cast<uint32_t>(__popc(b0 & lt_mask))) & (kFoldRing - 1)] = f0;
+                queued += static_cast<uint32_t>(__popc(b0));
+                if (queued >= 32u) {
+                    __syncwarp();
+                    const Frag g = W.ring[(head + lane) & (kFoldRing - 1)];
+                    fold_apply(W, tex, fold_prep(g, true, lo, A.time, lane), true, lane);
+                    head = (head + 32u) & (kFoldRing - 1);
+                    queued -= 32u;
+                }
+                if (m1) W.ring[(head + queued + static_cast<uint32_t>(__popc(b1 & lt_mask))) & (kFoldRing - 1)] = f1;
+                queued += static_cast<uint32_t>(__popc(b1));
+                if (queued >= 32u) {
+                    __syncwarp();
+                    const Frag g = W.ring[(head + lane) & (kFoldRing - 1)];
+                    fold_apply(W, tex, fold_prep(g, true, lo, A.time, lane), true, lane);
+                    head = (head + 32u) & (kFoldRing - 1);
+                    queued -= 32u;
+                }
+                __syncwarp();
             }
-            // (fold_apply ends with __syncwarp: every lane is done with this window)
+            // (every lane is done with this window)
             if (lane == 0 && j + 2 < n_stage) issue(j + 2);
+        }
+        if (queued) {
+            __syncwarp();
+            Frag g{0.f, 0.f, 0.f, 0u};
+            const bool act = static_cast<uint32_t>(lane) < queued;
+            if (act) g = W.ring[(head + lane) & (kFoldRing - 1)];
+            fold_apply(W, tex, fold_prep(g, act, lo, A.time, lane), act, lane);
         }
         for (uint32_t l = lane; l < R; l += 32) {
             const uint32_t loc = lo + l;
