@@ -255,6 +255,10 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     c->fold_ctas = std::max(1, per_sm) * c->n_sms;
     TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_hist, kHistThreads, kMaxBins * sizeof(uint32_t)));
     c->hist_ctas = std::max(1, per_sm) * c->n_sms;
+    // experiment knobs: resident CTAs per SM of the splat kernels (fewer leave room for the noise launch of TB_OVERLAP)
+    if (const char *e = std::getenv("TB_SCATTER_CTAS")) c->scatter_ctas = std::min(c->scatter_ctas, std::max(1, std::atoi(e)) * c->n_sms);
+    if (const char *e = std::getenv("TB_FOLD_CTAS")) c->fold_ctas = std::min(c->fold_ctas, std::max(1, std::atoi(e)) * c->n_sms);
+    if (const char *e = std::getenv("TB_HIST_CTAS")) c->hist_ctas = std::min(c->hist_ctas, std::max(1, std::atoi(e)) * c->n_sms);
     c->collected = false;
     c->pending = false;
     return TB_OK;
@@ -728,7 +732,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     if (c->n_prims >= (1LL << 31)) { c->err = "tendrils-b200: too many primitives per context"; return bail(TB_ERR_INVALID); }
     // slabs of consecutive primitives: the unit of work of the count and emit passes (about eight per SM)
     {
-        const long long want = (c->n_prims + 6LL * c->n_sms - 1) / (6LL * c->n_sms);
+        const long long want = (c->n_prims + 6LL * c->n_sms - 1) / (6LL * c->n_sms);      // two slabs per resident CTA of the count and emit kernels
         c->slab_prims = static_cast<int>(std::max<long long>(4 * kEmitThreads, (want + kEmitThreads - 1) / kEmitThreads * kEmitThreads));
         c->n_slabs = static_cast<int>((c->n_prims + c->slab_prims - 1) / c->slab_prims);
         c->slabs_per_seg = std::max(1, (c->n_slabs + kHistSegs - 1) / kHistSegs);

@@ -85,6 +85,20 @@ struct PrimGeom {
 };
 
 // [prim-begin]  (tests/test_raster_host.py compiles the text between these markers for the CPU)
+// The rare lines that touch the minor-axis borders of the grid are enumerated; kept out of line so that the kernels'
+// unrolled fragment rounds stay small (instruction cache).
+__device__ __noinline__ uint32_t prim_count_slow(float xa, float ya, float xb, float yb, int W, int H) {
+    uint32_t n = 0;
+    raster_line(xa, ya, xb, yb, W, H, [&](int, int, float) { ++n; });
+    return n;
+}
+__device__ __noinline__ void prim_fragment_slow(const PrimGeom &P, uint32_t j, int W, int H, int &gx, int &gy, float &t) {
+    const bool xmajor = (P.flags & 1u) != 0u;
+    uint32_t k = 0;
+    gx = gy = 0; t = 0.0f;
+    raster_line(xmajor ? P.ma : P.na, xmajor ? P.na : P.ma, xmajor ? P.mb : P.nb, xmajor ? P.nb : P.mb, W, H,
+                [&](int x, int y, float tt) { if (k == j) { gx = x; gy = y; t = tt; } ++k; });
+}
 // Number of fragments of the line sa -> sb and what is needed to enumerate them.  Same decisions as
 // count_fragments()/raster_line() (RASTER-1): when the line stays clear of the minor-axis borders, the
 // fragments are exactly the member columns c0, c0+1, ..., c0+n-1 of the major axis.
@@ -119,9 +133,7 @@ __device__ __forceinline__ uint32_t prim_setup(const float4 &sa, const float4 &s
         P.flags |= 2u;
         return n;
     }
-    uint32_t n = 0;
-    raster_line(xa, ya, xb, yb, W, H, [&](int, int, float) { ++n; });
-    return n;
+    return prim_count_slow(xa, ya, xb, yb, W, H);
 }
 
 // Fragment j (0 <= j < n) of a primitive: its texel and the interpolation parameter.  The order of a line's
@@ -138,10 +150,7 @@ __device__ __forceinline__ void prim_fragment(const PrimGeom &P, uint32_t j, int
         gy = xmajor ? jj : i;
         return;
     }
-    uint32_t k = 0;
-    gx = gy = 0; t = 0.0f;
-    raster_line(xmajor ? P.ma : P.na, xmajor ? P.na : P.ma, xmajor ? P.mb : P.nb, xmajor ? P.nb : P.mb, W, H,
-                [&](int x, int y, float tt) { if (k == j) { gx = x; gy = y; t = tt; } ++k; });
+    prim_fragment_slow(P, j, W, H, gx, gy, t);
 }
 // [prim-end]
 
@@ -175,7 +184,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 // slabs from a ticket counter.  slab_hist[slab * kMaxBins + bin]; seg_total[seg * kMaxBins + bin] accumulates
 // the slabs of a segment (zeroed by k_splat_rows of the previous draw).
 // ------------------------------------------------------------------------------------------
-constexpr int kHistThreads = 256;
+constexpr int kHistThreads = 512;
 
 struct HistArgs {
     PrimSource src;
@@ -220,15 +229,15 @@ __global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
         if (slab >= A.n_slabs) break;
         const long long p0 = static_cast<long long>(slab) * A.slab_prims;
         const long long p1 = (p0 + A.slab_prims < A.src.n_prims) ? p0 + A.slab_prims : A.src.n_prims;
-        // two primitives in flight per thread: the vertex loads of the second hide behind the first
-        for (long long pb = p0 + threadIdx.x; pb < p1; pb += 2 * kHistThreads) {
-            float4 sa[2], sb[2];
-            const bool have1 = pb + kHistThreads < p1;
-            load_prim(A.src, pb, sa[0], sb[0]);
-            if (have1) load_prim(A.src, pb + kHistThreads, sa[1], sb[1]);
+        // four primitives in flight per thread: the vertex loads hide behind one another
+        for (long long pb = p0 + threadIdx.x; pb < p1; pb += 4 * kHistThreads) {
+            float4 sa[4], sb[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (u == 1 && !have1) break;
+            for (int u = 0; u < 4; ++u)
+                if (pb + u * kHistThreads < p1) load_prim(A.src, pb + u * kHistThreads, sa[u], sb[u]);
+#pragma unroll 1
+            for (int u = 0; u < 4; ++u) {
+                if (pb + u * kHistThreads >= p1) break;
                 PrimGeom P;
                 const uint32_t n = prim_setup(sa[u], sb[u], A.vsx, A.vsy, A.g.W, A.g.H, P);
                 if (n == 0u) continue;
@@ -305,6 +314,18 @@ __global__ void __launch_bounds__(256) k_splat_rows(uint32_t *__restrict__ slab_
     }
     const int s0 = seg * slabs_per_seg, s1 = (s0 + slabs_per_seg < n_slabs) ? s0 + slabs_per_seg : n_slabs;
     uint32_t run = static_cast<uint32_t>(base);
+    if (s1 - s0 <= 64) {
+        // the whole segment in flight at once: one DRAM round trip instead of one per batch
+        uint32_t v[64];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v[k] = (s0 + k < s1) ? __ldcs(slab_hist + static_cast<size_t>(s0 + k) * kMaxBins + t) : 0u;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            if (s0 + k < s1) slab_hist[static_cast<size_t>(s0 + k) * kMaxBins + t] = run;
+            run += v[k];
+        }
+        return;
+    }
     for (int s = s0; s < s1; s += 8) {
         uint32_t v[8];
 #pragma unroll
