@@ -133,6 +133,11 @@ int tb_destroy(tb_ctx *ctx);
 /* Tendrils.state + viewSize, read at step/draw time (src/index.js:255-263,284-293) */
 int tb_set_state(tb_ctx *ctx, const tb_state *state);
 
+/* Scheduling switch, no effect on results: with `on` (the default) tb_step evaluates the two simplex noises of logic.frag, which
+ * do not read the flow grid, on a low-priority side stream under the previous flow splat and finishes the shader on the main
+ * stream.  Off: one fused launch (what a roofline measurement of the kernel wants). */
+int tb_set_overlap(tb_ctx *ctx, int32_t on);
+
 /* Tendrils.resize(): flow.shape = viewRes, which reallocates and zeroes (src/index.js:393-408) */
 int tb_resize_flow(tb_ctx *ctx, int32_t w, int32_t h);
 /* Tendrils.clearFlow() (src/index.js:234-239) */

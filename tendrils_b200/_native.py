@@ -53,6 +53,7 @@ SYMBOLS = {
     "tb_create": (C.c_int, [C.POINTER(TbConfig), C.POINTER(_ctx)]),
     "tb_destroy": (C.c_int, [_ctx]),
     "tb_set_state": (C.c_int, [_ctx, C.POINTER(TbState)]),
+    "tb_set_overlap": (C.c_int, [_ctx, C.c_int32]),
     "tb_resize_flow": (C.c_int, [_ctx, C.c_int32, C.c_int32]),
     "tb_clear_flow": (C.c_int, [_ctx]),
     "tb_step": (C.c_int, [_ctx, C.c_float, C.c_float]),

@@ -319,6 +319,10 @@ class Particles:
     def sync(self):
         N.check(self._ctx, self._L.tb_sync(self._ctx))
 
+    def set_overlap(self, on: bool):
+        """scheduling only: run the next step's noise under the flow splat (default) or fuse the whole logic pass"""
+        N.check(self._ctx, self._L.tb_set_overlap(self._ctx, 1 if on else 0))
+
     def stats(self):
         a, b = C.c_int64(), C.c_int64()
         N.check(self._ctx, self._L.tb_stats(self._ctx, C.byref(a), C.byref(b)))
