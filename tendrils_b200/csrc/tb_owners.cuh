@@ -20,13 +20,41 @@
 
 namespace tb {
 
-constexpr int kOwnerPhases = 3;
+constexpr int kOwnerPhases = 4;
 
 struct OwnerPeers {
     uint32_t *totals[kMaxBandRanks];     // every rank's table [n][kMaxBins]: row r = rank r's fragments per bin
-    uint32_t *flags[kMaxBandRanks];      // every rank's barrier flags [kOwnerPhases][kMaxBandRanks]
+    uint32_t *flags[kMaxBandRanks];      // every rank's barrier flags [kOwnerPhases][kMaxBandRanks], then [kMaxBandRanks] prune flags
+    uint32_t *last[kMaxBandRanks];       // every rank's table [n][W*H]: row r = rank r's "last opaque primitive" per texel
     int n, me;
 };
+
+// opaque pruning across the ranks: my table of last opaque primitives (and my "do not prune" flag) into row `me` of every rank's
+__global__ void __launch_bounds__(256) k_owners_push_last(const uint32_t *__restrict__ last, const uint32_t *__restrict__ flags, int G,
+                                                           const OwnerPeers P) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i == 0) {
+        const uint32_t f = *flags;
+        for (int r = 0; r < P.n; ++r) P.flags[r][kOwnerPhases * kMaxBandRanks + P.me] = f;
+    }
+    if (i >= G) return;
+    const uint32_t v = last[i];
+    for (int r = 0; r < P.n; ++r) P.last[r][static_cast<size_t>(P.me) * G + i] = v;
+}
+// ... and, behind a barrier, the maximum over the ranks (primitive indices are global: rank order = draw order)
+__global__ void __launch_bounds__(256) k_owners_last_max(const uint32_t *__restrict__ all, const uint32_t *__restrict__ my_flags, int n, int G,
+                                                          uint32_t *__restrict__ last, uint32_t *flags) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i == 0) {
+        uint32_t f = 0u;
+        for (int r = 0; r < n; ++r) f |= my_flags[kOwnerPhases * kMaxBandRanks + r];
+        *flags = f;
+    }
+    if (i >= G) return;
+    uint32_t m = 0u;
+    for (int r = 0; r < n; ++r) { const uint32_t v = all[static_cast<size_t>(r) * G + i]; m = v > m ? v : m; }
+    last[i] = m;
+}
 
 // my fragments per bin into row `me` of every rank's table
 __global__ void __launch_bounds__(256) k_owners_share(const uint32_t *__restrict__ bin_total, const uint32_t *__restrict__ n_bins, const OwnerPeers P) {

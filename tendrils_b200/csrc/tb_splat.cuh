@@ -180,6 +180,67 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Pass 0 (optional; sharded runs): opaque pruning.  A fragment with alpha == 1 overwrites its texel: dst = c*1 + dst*0.  For
+// every texel, `last[texel]` = 1 + the (global) index of the LAST primitive that lays such a fragment on it; every fragment
+// of an earlier primitive on that texel is dead -- it cannot influence the result -- and is neither counted, emitted nor
+// folded.  Exactness (spec/PARITY.md B3): c + dst*0 = c needs a finite dst (guaranteed when every skipped fragment is
+// finite with 0 <= a <= 1: the kernel raises `flags` bit 0 on a primitive that could break that, and the draw then prunes
+// nothing) and a colour that is not -0 (such primitives do not mark).  Only primitives with alpha == 1 at BOTH vertices
+// mark: then a = 1 + t*0 = 1 on every fragment.  Marking less than possible is always exact.
+// ------------------------------------------------------------------------------------------
+struct OpaqueArgs {
+    PrimSource src;
+    StripGeom g;
+    float vsx, vsy, speedLimit, time;
+    long long prim_base;                       // global index of this context's first primitive
+    uint32_t *__restrict__ last;               // [W*H], zeroed beforehand
+    uint32_t *flags;                           // bit 0: pruning would not be exact for this draw
+};
+
+__global__ void __launch_bounds__(256) k_splat_opaque(const OpaqueArgs A) {
+    const long long stride = static_cast<long long>(gridDim.x) * 256;
+    const bool time_ok = __float_as_uint(A.time) != 0x80000000u && A.speedLimit > 0.0f;
+    for (long long pb = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; pb < A.src.n_prims; pb += 4 * stride) {
+        float4 sa[4], sb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pb + u * stride < A.src.n_prims) load_prim(A.src, pb + u * stride, sa[u], sb[u]);
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+            const long long p = pb + u * stride;
+            if (p >= A.src.n_prims) break;
+            const float4 a = sa[u], b = sb[u];
+            if (!splat_vertex_ok(a) || !splat_vertex_ok(b)) continue;
+            const bool tame = fabsf(a.z) < 1.0e30f && fabsf(a.w) < 1.0e30f && fabsf(b.z) < 1.0e30f && fabsf(b.w) < 1.0e30f;
+            if (!tame || !time_ok) { atomicOr(A.flags, 1u); continue; }
+            const float aa = gmin(__fdiv_rn(glength(a.z, a.w), A.speedLimit), 1.0f);
+            const float ab = gmin(__fdiv_rn(glength(b.z, b.w), A.speedLimit), 1.0f);
+            if (!(aa == 1.0f && ab == 1.0f)) continue;
+            if (__float_as_uint(a.z) == 0x80000000u || __float_as_uint(a.w) == 0x80000000u) continue;     // the colour could be -0
+            PrimGeom P;
+            const uint32_t n = prim_setup(a, b, A.vsx, A.vsy, A.g.W, A.g.H, P);
+            const uint32_t mark = static_cast<uint32_t>(A.prim_base + p) + 1u;
+            for (uint32_t j = 0; j < n; ++j) {
+                int gx, gy; float t;
+                prim_fragment(P, j, A.g.W, A.g.H, gx, gy, t);
+                atomicMax(A.last + static_cast<size_t>(gy) * A.g.W + gx, mark);
+            }
+        }
+    }
+}
+
+// is the fragment of (global) primitive p on texel (gx, gy) overwritten by a later primitive?
+struct Prune {
+    const uint32_t *__restrict__ last;         // null: no pruning
+    const uint32_t *flags;
+    long long prim_base;
+};
+__device__ __forceinline__ bool prune_on(const Prune &Q) { return Q.last != nullptr && (*Q.flags & 1u) == 0u; }
+__device__ __forceinline__ bool fragment_dead(const uint32_t *__restrict__ last, uint32_t mark, int W, int gx, int gy) {
+    return __ldg(last + static_cast<size_t>(gy) * W + gx) > mark;
+}
+
+// ------------------------------------------------------------------------------------------
 // Pass 1: fragments per (slab, bin).  A slab is a fixed range of consecutive primitives; CTAs take
 // slabs from a ticket counter.  slab_hist[slab * kMaxBins + bin]; seg_total[seg * kMaxBins + bin] accumulates
 // the slabs of a segment (zeroed by k_splat_rows of the previous draw).
@@ -190,6 +251,7 @@ struct HistArgs {
     PrimSource src;
     StripGeom g;
     BinMap bm;
+    Prune prune;
     float vsx, vsy;
     int slab_prims, n_slabs, slabs_per_seg;
     uint32_t *__restrict__ slab_hist;
@@ -220,6 +282,7 @@ __global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);              // [n_bins]
     __shared__ int s_slab;
     const int B = static_cast<int>(*A.bm.n_bins);
+    const uint32_t *dead = prune_on(A.prune) ? A.prune.last : nullptr;
     for (int t = threadIdx.x; t < B; t += kHistThreads) hist[t] = 0u;
     for (;;) {
         __syncthreads();
@@ -242,9 +305,11 @@ __global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
                 const uint32_t n = prim_setup(sa[u], sb[u], A.vsx, A.vsy, A.g.W, A.g.H, P);
                 if (n == 0u) continue;
                 const bool xmajor = (P.flags & 1u) != 0u;
+                const uint32_t mark = static_cast<uint32_t>(A.prune.prim_base + pb + u * kHistThreads) + 1u;
                 int run_bin = -1;
                 uint32_t run = 0;
                 auto count = [&](int gx, int gy) {
+                    if (dead && fragment_dead(dead, mark, A.g.W, gx, gy)) return;
                     const int b = static_cast<int>(bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), local_of(A.g, gx, gy)));
                     if (b != run_bin) { if (run) atomicAdd(&hist[run_bin], run); run_bin = b; run = 0; }
                     ++run;
@@ -261,7 +326,7 @@ __global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
                     const int s0 = xmajor ? strip_of(A.g, m0, q0) : strip_of(A.g, q0, m0);
                     const int s1 = xmajor ? strip_of(A.g, m1, q1) : strip_of(A.g, q1, m1);
                     const uint32_t m = __ldg(A.bm.map + s0);
-                    if (s0 == s1 && (m >> 24) == 0u) {
+                    if (s0 == s1 && (m >> 24) == 0u && !dead) {
                         atomicAdd(&hist[m & 0xffffffu], n);
                         continue;
                     }
@@ -535,6 +600,7 @@ struct ScatterArgs {
     PrimSource src;
     StripGeom g;
     BinMap bm;
+    Prune prune;
     float vsx, vsy, speedLimit, time;
     int slab_prims, n_slabs;
     const uint32_t *__restrict__ slab_hist;     // scanned: fragments of this bin in earlier slabs
@@ -563,6 +629,7 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
     uint32_t *owner = reinterpret_cast<uint32_t *>(rec + 12 * 32);             // [kEmitSlots]
     __shared__ int s_slab;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t *dead = prune_on(A.prune) ? A.prune.last : nullptr;
 
     for (;;) {
         __syncthreads();
@@ -655,6 +722,8 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
                         fa[r] = __fadd_rn(aa, __fmul_rn(t, __fsub_rn(ab, aa)));
                         const uint32_t loc = local_of(A.g, gx, gy);
                         fbin[r] = bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), loc) | (loc << 16);
+                        // a fragment a later primitive overwrites takes no slot (k_splat_hist did not count it either)
+                        if (dead && fragment_dead(dead, static_cast<uint32_t>(A.prune.prim_base + w0 + warp * 32 + q) + 1u, A.g.W, gx, gy)) fbin[r] = 0xffffffffu;
                     }
                     fpeers[r] = __match_any_sync(0xffffffffu, fbin[r] & 0xffffu);
                 }

@@ -1,8 +1,10 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit.
 
-Tolerance: NONE for finite values -- integrate, spawners and the ordered flow blend all have to
-match the oracle exactly (any NaN equals any NaN, -0 equals +0)."""
+Tolerance: NONE -- integrate, spawners and the ordered flow blend all have to match the oracle's 32-bit patterns exactly
+(only the payload of a NaN is left open).  The whole module runs twice: as the library ships on one GPU, and with the
+opaque pruning that sharded runs use (TB_PRUNE=1), which must not change a bit."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -19,6 +21,27 @@ def T():
     import tendrils_b200
     tendrils_b200.load()
     return tendrils_b200
+
+
+@pytest.fixture(scope="module", params=["", "1"], ids=["default", "prune"], autouse=True)
+def prune_mode(request):
+    """TB_PRUNE is read when a context is created"""
+    old = os.environ.get("TB_PRUNE")
+    if request.param:
+        os.environ["TB_PRUNE"] = request.param
+    else:
+        os.environ.pop("TB_PRUNE", None)
+    yield request.param
+    if old is None:
+        os.environ.pop("TB_PRUNE", None)
+    else:
+        os.environ["TB_PRUNE"] = old
+
+
+def frags_ok(t, n):
+    """fragments the last splat blended: all the oracle rasterised -- or, with pruning, at most as many"""
+    got = t.particles.stats()["last_fragments"]
+    return got <= n if os.environ.get("TB_PRUNE") == "1" else got == n
 
 
 def make(T, R, G, state=None, view=None):
@@ -71,7 +94,7 @@ def test_ball_then_steps_bit_exact(T, oracle, R, G):
         t.step().draw()
         sim.step(np.float32(t.timer.time), np.float32(t.timer.dt))
         n = sim.draw(np.float32(t.timer.time))
-        assert t.particles.stats()["last_fragments"] == n, f"fragment count at step {k}"
+        assert frags_ok(t, n), f"fragment count at step {k}"
         assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state after step {k}")
         assert_bits_equal(t.flow.download(), sim.flow, f"flow after step {k}")
     assert_bits_equal(t.particles.buffers[1].download(), sim.prev, "previous state")
@@ -92,7 +115,7 @@ def test_strip_sizes_and_split_maps_bit_exact(T, oracle, R, G, radius, steps):
         t.step().draw()
         sim.step(np.float32(t.timer.time), np.float32(t.timer.dt))
         n = sim.draw(np.float32(t.timer.time))
-        assert t.particles.stats()["last_fragments"] == n, f"fragment count at step {k}"
+        assert frags_ok(t, n), f"fragment count at step {k}"
         assert_bits_equal(t.flow.download(), sim.flow, f"flow after step {k}")
     assert_bits_equal(t.particles.buffers[0].download(), sim.cur, "state")
 
@@ -239,7 +262,7 @@ def test_edge_states_bit_exact(T, oracle):
     for k in range(12):
         t.timer.tick(); t.step().draw()
         sim.step(np.float32(t.timer.time), np.float32(t.timer.dt)); n = sim.draw(np.float32(t.timer.time))
-        assert t.particles.stats()["last_fragments"] == n
+        assert frags_ok(t, n)
         assert_bits_equal(t.particles.buffers[0].download(), sim.cur, f"state {k}")
         assert_bits_equal(t.flow.download(), sim.flow, f"flow {k}")
     assert np.isnan(sim.cur[2, 0]).any() and (sim.cur[0, :, 0] == T.INERT).all()
@@ -283,7 +306,7 @@ def test_hot_texel_and_long_lines(T, oracle):
     t.timer.tick()
     t.draw()
     n = sim.draw(np.float32(t.timer.time))
-    assert t.particles.stats()["last_fragments"] == n and n > 5000
+    assert frags_ok(t, n) and n > 5000
     assert_bits_equal(t.flow.download(), sim.flow, "flow after a contended draw")
 
 
@@ -360,7 +383,7 @@ def test_opaque_cut_is_exact(T, oracle):
         t.timer.tick()
         t.draw()
         n = sim.draw(np.float32(t.timer.time))
-        assert t.particles.stats()["last_fragments"] == n
+        assert frags_ok(t, n)
         got = t.flow.download()
         assert_bits_equal(got, sim.flow, f"flow after draw {k}")
     assert (sim.flow[..., 3] == 1.0).sum() > 20, "the case must actually contain opaque fragments"
@@ -460,7 +483,7 @@ def test_redraw_after_parameter_change_recounts(T, oracle):
     P2 = oracle_params(O, t)
     flow = np.zeros((24, 56, 4), np.float32)
     n = O.splat(P2, cur, prev, flow, np.float32(t.timer.time))
-    assert t.particles.stats()["last_fragments"] == n
+    assert frags_ok(t, n)
     assert_bits_equal(t.flow.download(), flow, "flow after a resized draw")
 
 
@@ -489,7 +512,7 @@ def test_full_size_cfg3_bit_exact(T, oracle, steps):
         new = O.integrate(P, cur, targets, flow, np.float32(t.timer.time), np.float32(t.timer.dt))
         prev, cur = cur, new
         n = O.splat(P, cur, prev, flow, np.float32(t.timer.time), mt=True)
-        assert t.particles.stats()["last_fragments"] == n and n > 10_000_000
+        assert frags_ok(t, n) and n > 10_000_000
         assert_bits_equal(t.particles.buffers[0].download(), cur, f"full-size state {k}")
         assert_bits_equal(t.flow.download(), flow, f"full-size flow {k}")
     # size-independent properties (what the reference guarantees by construction)
@@ -609,6 +632,6 @@ def test_rows_drawn_twice_bit_exact(T, oracle, PW, PH, G):
         new = O.integrate(P, cur, targets, flow, np.float32(t.timer.time), np.float32(t.timer.dt))
         prev, cur = cur, new
         n = O.splat(P, cur, prev, flow, np.float32(t.timer.time))
-        assert t.particles.stats()["last_fragments"] == n and n > 100
+        assert frags_ok(t, n) and n > 100
         assert_bits_equal(t.particles.buffers[0].download(), cur, f"state {k}")
         assert_bits_equal(t.flow.download(), flow, f"flow {k}")
