@@ -232,6 +232,10 @@ int tb_optical_flow(tb_ctx *ctx, const tb_optical_flow_params *params, const uin
 /* plumbing for the host layer (PyTorch / NCCL): raw device pointers, stream, sync, timing */
 int tb_device_ptr(tb_ctx *ctx, tb_buffer which, void **ptr, int64_t *n_floats);
 int tb_stream(tb_ctx *ctx, void **cuda_stream);
+/* Inputs handed over as DEVICE pointers (tb_set_spawn_image, tb_optical_flow, tb_flow_line) are read in stream order on
+ * tb_stream.  If another stream wrote them (a decoder, torch's current stream), call this first: the context's stream then
+ * waits for everything queued so far on `producer_stream` (a cudaStream_t of the same device; NULL = the legacy default stream). */
+int tb_wait_stream(tb_ctx *ctx, void *producer_stream);
 int tb_sync(tb_ctx *ctx);
 /* counters since creation: kernels launched by this library, fragments blended by the last splat */
 int tb_stats(tb_ctx *ctx, int64_t *kernel_launches, int64_t *last_fragments);

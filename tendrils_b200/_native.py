@@ -80,6 +80,7 @@ SYMBOLS = {
     "tb_optical_flow": (C.c_int, [_ctx, C.POINTER(TbOpticalFlowParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "tb_device_ptr": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "tb_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
+    "tb_wait_stream": (C.c_int, [_ctx, C.c_void_p]),
     "tb_sync": (C.c_int, [_ctx]),
     "tb_stats": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tb_timing": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_int64), _fp, C.POINTER(C.c_int64), _fp,
@@ -126,6 +127,13 @@ def check(ctx, status: int):
 def is_device_array(a) -> bool:
     """A torch CUDA tensor (anything with .is_cuda set): its memory is handed to the library as a device pointer."""
     return bool(getattr(a, "is_cuda", False))
+
+
+def wait_for_producer(ctx, a):
+    """A torch CUDA tensor was (possibly) written on torch's current stream: order the library's stream after it."""
+    if is_device_array(a):
+        import torch
+        check(ctx, load().tb_wait_stream(ctx, C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)))
 
 
 def array_pointer(a, dtype: str) -> int:

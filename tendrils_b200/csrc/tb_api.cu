@@ -33,6 +33,7 @@ struct tb_ctx {
     cudaStream_t side = nullptr;            // noise of the next step under the previous splat (TB_OVERLAP)
     cudaEvent_t ev_state = nullptr;         // last write to the state buffers (main stream)
     cudaEvent_t ev_noise = nullptr;         // noise kernel done (side stream)
+    cudaEvent_t ev_producer = nullptr;      // tb_wait_stream
     float2 *wander = nullptr;
     bool splat_since_step = false;          // something HBM-bound is queued that the noise can hide under
     bool overlap = false;
@@ -706,6 +707,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     const int col0 = cfg->col0, col1 = cfg->col1 == 0 ? PW : cfg->col1;
     if (col0 < 0 || col1 > PW || col0 >= col1)
         return fail(nullptr, TB_ERR_INVALID, "tendrils-b200: invalid column range");
+    if (col1 - col0 > 65535 || PH > (1 << 24))
+        return fail(nullptr, TB_ERR_INVALID, "tendrils-b200: a context holds at most 65535 columns of at most 2^24 rows");
     if (!columns_are_identity(PW))
         return fail(nullptr, TB_ERR_UNSUPPORTED, "tendrils-b200: vertex LUT columns do not map 1:1 for this width");
     int ndev = 0;
@@ -835,6 +838,7 @@ int tb_destroy(tb_ctx *c) {
         for (int j = 0; j < 5; ++j)
             if (c->ev_stage[i][j]) cudaEventDestroy(c->ev_stage[i][j]);
     if (c->ev_state) cudaEventDestroy(c->ev_state);
+    if (c->ev_producer) cudaEventDestroy(c->ev_producer);
     if (c->ev_noise) cudaEventDestroy(c->ev_noise);
     if (c->side) cudaStreamDestroy(c->side);
     cudaFree(c->wander);
@@ -1387,6 +1391,17 @@ int tb_device_ptr(tb_ctx *c, tb_buffer which, void **ptr, int64_t *n_floats) {
     float4 *p; int64_t n;
     if (int r = buffer_of(c, which, &p, &n)) return r;
     *ptr = p; *n_floats = n;
+    return TB_OK;
+}
+
+// Order this context's stream after everything queued so far on `producer_stream` (a cudaStream_t of this device): for inputs
+// that live in device memory and were written by someone else's stream (a decoder, torch's current stream).
+int tb_wait_stream(tb_ctx *c, void *producer_stream) {
+    TB_REQUIRE(c, c, "null context");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->ev_producer) TB_CUDA(c, cudaEventCreateWithFlags(&c->ev_producer, cudaEventDisableTiming));
+    TB_CUDA(c, cudaEventRecord(c->ev_producer, static_cast<cudaStream_t>(producer_stream)));
+    TB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_producer, 0));
     return TB_OK;
 }
 

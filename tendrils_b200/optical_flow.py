@@ -47,6 +47,7 @@ class OpticalFlow:
         if tuple(view.shape) != tuple(last.shape):
             raise N.TendrilsError("tendrils-b200: optical-flow buffers differ in shape (call resize)")
         ctx = tendrils.particles._ctx
+        N.wait_for_producer(ctx, view)                 # device frames: ordered after the stream that wrote them
         N.check(ctx, N.load().tb_optical_flow(ctx, C.byref(p), N.array_pointer(view, "uint8"), N.array_pointer(last, "uint8"),
                                               view.shape[1], view.shape[0]))
         self._keep = (view, last)          # device frames are read in stream order: keep them alive until the next render

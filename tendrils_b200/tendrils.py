@@ -244,6 +244,7 @@ class Particles:
                 img = src if N.is_device_array(src) else np.ascontiguousarray(src, dtype=np.float32)
                 if img.ndim != 3 or img.shape[2] != 4:
                     raise N.TendrilsError("tendrils-b200: spawnData must be an [h,w,4] float image")
+                N.wait_for_producer(ctx, img)          # a device image: ordered after the stream that wrote it
                 ptr = C.cast(C.c_void_p(N.array_pointer(img, "float32")), N._fp)
                 N.check(ctx, L.tb_set_spawn_image(ctx, ptr, img.shape[1], img.shape[0]))
                 self._spawn_image = img       # a device image is copied in stream order: keep it alive
