@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
                 A.items[s_bucket[bucket[k]] + rank[k] + part] = static_cast<uint32_t>(b) | (part << 16) | (lparts[k] << 24);
     }
     // the next draw's split map, from the fragments per strip over ALL ranks: identical on every rank
-    plan_next_map(A.T, A.lS, A.bm.map, A.bin_sum, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);
+    unsigned long long all_ranks = 0ull;
+    for (int r = 0; r < P; ++r) all_ranks += s_owner_total[r];
+    plan_next_map(A.T, A.lS, A.bm.map, A.bin_sum, all_ranks, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);
 }
 
 }  // namespace tb

@@ -461,7 +461,7 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
 // The next draw's split map from this draw's fragments per bin: a strip with more than split_at fragments gets 8 bins,
 // 4x that: 32, 16x: 128 (as far as kMaxBins allows).  Called by every thread of the (single) plan CTA.
 __device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__restrict__ map, const uint32_t *__restrict__ bin_total,
-                                              uint32_t split_at, uint32_t *map_next, uint32_t *bin_info_next, uint32_t *n_bins_next,
+                                              unsigned long long total, uint32_t split_at, uint32_t *map_next, uint32_t *bin_info_next, uint32_t *n_bins_next,
                                               unsigned long long *s_warp, unsigned long long *s_total) {
     const int u0 = threadIdx.x * kPlanStrips;
     uint32_t ns[kPlanStrips];
@@ -480,8 +480,10 @@ __device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__r
         if (frags > 16ull * at) ls = 7;
         return ls > static_cast<uint32_t>(lS) ? static_cast<uint32_t>(lS) : ls;
     };
-    // raise the threshold until the bins fit: the most crowded strips are the ones that stay split
-    unsigned long long at = split_at;
+    // A small draw (few fragments for this many SMs) splits earlier, so that the fold still has a few thousand bins to hand
+    // out; then raise the threshold until the bins fit: the most crowded strips are the ones that stay split.
+    unsigned long long at = total / 4096ull;
+    at = at < 256ull ? 256ull : (at > split_at ? split_at : at);
     unsigned long long base = 0ull;
     for (int guard = 0; guard < 64; ++guard) {
         unsigned long long bins = 0ull;
@@ -528,6 +530,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
         mine += n[k];
     }
     const unsigned long long ex = block_excl_scan64(mine, s_warp, &s_total);
+    const unsigned long long total = s_total;
     if (threadIdx.x == 0) {
         const bool ok = s_total <= static_cast<unsigned long long>(A.cap) && *A.too_many == 0u;
         s_ok = ok ? 1u : 0u;
@@ -541,6 +544,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     __syncthreads();
     const bool ok = s_ok != 0u;
     unsigned long long run = ex;
+    const uint32_t share_at = static_cast<uint32_t>(total / 2048ull < 512ull ? 512ull : (total / 2048ull > A.share_at ? A.share_at : total / 2048ull));
     uint32_t rank[kPlanBins], lparts[kPlanBins];
     int bucket[kPlanBins];
 #pragma unroll
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
         // work list, longest bins first (bucketed by log2 of the length): the tail of the fold is short bins
         bucket[k] = __clz(n[k] | 1u);
         lparts[k] = 0u;
-        if (ok && n[k]) lparts[k] = fold_lparts(n[k], (1u << A.lS) >> (A.bin_info[t0 + k] >> 24), A.share_at);
+        if (ok && n[k]) lparts[k] = fold_lparts(n[k], (1u << A.lS) >> (A.bin_info[t0 + k] >> 24), share_at);
         rank[k] = (ok && n[k]) ? atomicAdd(&s_bucket[bucket[k]], 1u << lparts[k]) : 0u;
     }
     if (threadIdx.x == 0) A.bin_off[B] = ok ? static_cast<uint32_t>(s_total) : 0u;
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
             for (uint32_t part = 0; part < (1u << lparts[k]); ++part)
                 A.items[s_bucket[bucket[k]] + rank[k] + part] = static_cast<uint32_t>(t0 + k) | (part << 16) | (lparts[k] << 24);
 
-    plan_next_map(A.T, A.lS, A.bm.map, A.bin_total, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);
+    plan_next_map(A.T, A.lS, A.bm.map, A.bin_total, total, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);
 }
 
 // the identity map (one bin per strip): first draw, and after a resize
