@@ -257,7 +257,7 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     k_splat_map_identity<<<blocks_for(T, 256), 256, 0, c->stream>>>(T, c->split_map, c->bin_info, c->n_bins);     // one bin per strip to begin with
     if (cudaGetLastError() != cudaSuccess) return fail(c, TB_ERR_CUDA, "k_splat_map_identity failed to launch");
     // persistent grids of the splat kernels
-    TB_CUDA(c, cudaFuncSetAttribute(k_splat_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBins * static_cast<int>(sizeof(uint32_t))));
+    TB_CUDA(c, cudaFuncSetAttribute(k_splat_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHistSmemBytes)));
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kScatterSmemBytes)));
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)))));
     int per_sm = 0;
@@ -265,7 +265,7 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     c->scatter_ctas = std::max(1, per_sm) * c->n_sms;
     TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_fold, kFoldThreads, fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl))));
     c->fold_ctas = std::max(1, per_sm) * c->n_sms;
-    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_hist, kHistThreads, kMaxBins * sizeof(uint32_t)));
+    TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_hist, kHistThreads, kHistSmemBytes));
     c->hist_ctas = std::max(1, per_sm) * c->n_sms;
     // experiment knobs: resident CTAs per SM of the splat kernels (fewer leave room for the noise launch of TB_OVERLAP)
     if (const char *e = std::getenv("TB_SCATTER_CTAS")) c->scatter_ctas = std::min(c->scatter_ctas, std::max(1, std::atoi(e)) * c->n_sms);
@@ -369,7 +369,7 @@ int launch_count(tb_ctx *c, int mp, const Prune &prune) {
         HA.slab_hist = c->slab_hist;
         HA.seg_total = seg_now;
         HA.ticket = c->tickets + 0;
-        k_splat_hist<<<std::min(c->n_slabs, c->hist_ctas), kHistThreads, kMaxBins * sizeof(uint32_t), c->stream>>>(HA);
+        k_splat_hist<<<std::min(c->n_slabs, c->hist_ctas), kHistThreads, kHistSmemBytes, c->stream>>>(HA);
         if (int r = check_launch(c, "k_splat_hist")) return r;
         if (c->stage_timing) cudaEventRecord(stage[1], c->stream);
         k_splat_rows<<<dim3(kMaxBins / 256, kHistSegs), 256, 0, c->stream>>>(c->slab_hist, seg_now, seg_next, c->n_bins + mp, c->n_slabs,

@@ -277,46 +277,56 @@ __device__ __forceinline__ void prim_fragment_texel(const PrimGeom &P, uint32_t 
     gy = (P.flags & 1u) ? jj : i;
 }
 
+constexpr int kHistWarps = kHistThreads / 32;
+constexpr int kHistSlots = 128;                            // slots per pass of a warp (four rounds of 32)
+constexpr size_t kHistSmemBytes = static_cast<size_t>(kMaxBins) * 4 + static_cast<size_t>(kHistWarps) * (8 * 32 + kHistSlots) * 4;
+
+// Each warp takes 32 consecutive lines at a time, one per lane.  A line whose bounding box sits inside one unsplit strip adds its
+// fragment count at once.  The fragments of the other lines are numbered by a warp scan and enumerated 32 at a time (like the
+// emit pass, but in any order and without claims): all lanes busy whatever the lines' lengths.
 __global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);              // [n_bins]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);              // [kMaxBins]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *rec = reinterpret_cast<float *>(hist + kMaxBins) + warp * (8 * 32 + kHistSlots);    // [8][32]
+    uint32_t *owner = reinterpret_cast<uint32_t *>(rec + 8 * 32);                             // [kHistSlots]
     __shared__ int s_slab;
     const int B = static_cast<int>(*A.bm.n_bins);
     const uint32_t *dead = prune_on(A.prune) ? A.prune.last : nullptr;
-    for (int t = threadIdx.x; t < B; t += kHistThreads) hist[t] = 0u;
+    for (int t = tid; t < B; t += kHistThreads) hist[t] = 0u;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_slab = static_cast<int>(atomicAdd(A.ticket, 1u));
+        if (tid == 0) s_slab = static_cast<int>(atomicAdd(A.ticket, 1u));
         __syncthreads();
         const int slab = s_slab;
         if (slab >= A.n_slabs) break;
         const long long p0 = static_cast<long long>(slab) * A.slab_prims;
         const long long p1 = (p0 + A.slab_prims < A.src.n_prims) ? p0 + A.slab_prims : A.src.n_prims;
-        // four primitives in flight per thread: the vertex loads hide behind one another
-        for (long long pb = p0 + threadIdx.x; pb < p1; pb += 4 * kHistThreads) {
-            float4 sa[4], sb[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (pb + u * kHistThreads < p1) load_prim(A.src, pb + u * kHistThreads, sa[u], sb[u]);
-#pragma unroll 1
-            for (int u = 0; u < 4; ++u) {
-                if (pb + u * kHistThreads >= p1) break;
+        // the vertices of the warp's next 32 lines are loaded while these are worked on
+        float4 sa_nx = make_float4(0.f, 0.f, 0.f, 0.f), sb_nx = sa_nx;
+        if (p0 + tid < p1) load_prim(A.src, p0 + tid, sa_nx, sb_nx);
+        for (long long w0 = p0; w0 < p1; w0 += kHistThreads) {
+            const long long p = w0 + tid;
+            const float4 sa = sa_nx, sb = sb_nx;
+            if (p + kHistThreads < p1) load_prim(A.src, p + kHistThreads, sa_nx, sb_nx);
+            uint32_t n = 0;                                            // fragments of this lane's line still to be enumerated
+            if (p < p1) {
                 PrimGeom P;
-                const uint32_t n = prim_setup(sa[u], sb[u], A.vsx, A.vsy, A.g.W, A.g.H, P);
-                if (n == 0u) continue;
-                const bool xmajor = (P.flags & 1u) != 0u;
-                const uint32_t mark = static_cast<uint32_t>(A.prune.prim_base + pb + u * kHistThreads) + 1u;
-                int run_bin = -1;
-                uint32_t run = 0;
-                auto count = [&](int gx, int gy) {
-                    if (dead && fragment_dead(dead, mark, A.g.W, gx, gy)) return;
-                    const int b = static_cast<int>(bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), local_of(A.g, gx, gy)));
-                    if (b != run_bin) { if (run) atomicAdd(&hist[run_bin], run); run_bin = b; run = 0; }
-                    ++run;
-                };
-                if (P.flags & 2u) {
+                n = prim_setup(sa, sb, A.vsx, A.vsy, A.g.W, A.g.H, P);
+                const uint32_t mark = static_cast<uint32_t>(A.prune.prim_base + p) + 1u;
+                if (n != 0u && !(P.flags & 2u)) {
+                    // the rare line that touches the minor-axis borders: enumerated by its own lane
+                    const bool xmajor = (P.flags & 1u) != 0u;
+                    raster_line(xmajor ? P.ma : P.na, xmajor ? P.na : P.ma, xmajor ? P.mb : P.nb, xmajor ? P.nb : P.mb, A.g.W, A.g.H,
+                                [&](int gx, int gy, float) {
+                                    if (dead && fragment_dead(dead, mark, A.g.W, gx, gy)) return;
+                                    atomicAdd(&hist[bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), local_of(A.g, gx, gy))], 1u);
+                                });
+                    n = 0u;
+                } else if (n != 0u) {
                     // closed form.  All fragments lie in the box spanned by the two vertices (the minor coordinate up to a few
                     // ulps): when that box, widened by 1/16 texel, sits in one unsplit strip, so do they.
+                    const bool xmajor = (P.flags & 1u) != 0u;
                     const float mlo = gmin(P.ma, P.mb), mhi = gmax(P.ma, P.mb), nlo = __fsub_rn(gmin(P.na, P.nb), 0.0625f), nhi = __fadd_rn(gmax(P.na, P.nb), 0.0625f);
                     const int M = xmajor ? A.g.W : A.g.H, N = xmajor ? A.g.H : A.g.W;
                     int m0 = static_cast<int>(floorf(mlo)), m1 = static_cast<int>(floorf(mhi));
@@ -328,26 +338,49 @@ __global__ void __launch_bounds__(kHistThreads) k_splat_hist(const HistArgs A) {
                     const uint32_t m = __ldg(A.bm.map + s0);
                     if (s0 == s1 && (m >> 24) == 0u && !dead) {
                         atomicAdd(&hist[m & 0xffffffu], n);
-                        continue;
+                        n = 0u;
+                    } else {
+                        rec[0 * 32 + lane] = P.ma; rec[1 * 32 + lane] = P.mb;
+                        rec[2 * 32 + lane] = P.na; rec[3 * 32 + lane] = P.nb;
+                        rec[4 * 32 + lane] = __int_as_float(P.c0);
+                        rec[5 * 32 + lane] = __uint_as_float(P.flags);
+                        rec[6 * 32 + lane] = __fdiv_rn(1.0f, __fsub_rn(P.mb, P.ma));
+                        rec[7 * 32 + lane] = __fmul_rn(__fadd_rn(__fadd_rn(fabsf(P.na), fabsf(__fsub_rn(P.nb, P.na))), 1.0f), 1.9073486328125e-06f);   // 2^-19
                     }
-                    const float inv_dm = __fdiv_rn(1.0f, __fsub_rn(P.mb, P.ma));
-                    const float eps = __fmul_rn(__fadd_rn(__fadd_rn(fabsf(P.na), fabsf(__fsub_rn(P.nb, P.na))), 1.0f), 1.9073486328125e-06f);   // 2^-19
-                    for (uint32_t j = 0; j < n; ++j) {
-                        int gx, gy;
-                        prim_fragment_texel(P, j, inv_dm, eps, gx, gy);
-                        count(gx, gy);
-                    }
-                } else {
-                    raster_line(xmajor ? P.ma : P.na, xmajor ? P.na : P.ma, xmajor ? P.mb : P.nb, xmajor ? P.nb : P.mb, A.g.W, A.g.H,
-                                [&](int gx, int gy, float) { count(gx, gy); });
                 }
-                if (run) atomicAdd(&hist[run_bin], run);
+            }
+            // ---- the fragments still to be enumerated: slots by a warp scan, 32 per round
+            const uint32_t inc = warp_incl_scan(n, lane);
+            const uint32_t my_off = inc - n;
+            const uint32_t n_warp = __shfl_sync(0xffffffffu, inc, 31);
+            for (uint32_t s_lo = 0; s_lo < n_warp; s_lo += kHistSlots) {
+                const uint32_t cnt = (n_warp - s_lo < static_cast<uint32_t>(kHistSlots)) ? n_warp - s_lo : static_cast<uint32_t>(kHistSlots);
+                {
+                    const uint32_t b = my_off > s_lo ? my_off : s_lo;
+                    const uint32_t e = (my_off + n < s_lo + cnt) ? my_off + n : s_lo + cnt;
+                    for (uint32_t s = b; s < e; ++s) owner[s - s_lo] = (static_cast<uint32_t>(lane) << 20) | (s - my_off);
+                }
+                __syncwarp();
+                for (uint32_t s = lane; s < cnt; s += 32) {
+                    const uint32_t o = owner[s];
+                    const int q = static_cast<int>(o >> 20);
+                    PrimGeom P;
+                    P.ma = rec[0 * 32 + q]; P.mb = rec[1 * 32 + q];
+                    P.na = rec[2 * 32 + q]; P.nb = rec[3 * 32 + q];
+                    P.c0 = __float_as_int(rec[4 * 32 + q]);
+                    P.flags = __float_as_uint(rec[5 * 32 + q]);
+                    int gx, gy;
+                    prim_fragment_texel(P, o & 0xfffffu, rec[6 * 32 + q], rec[7 * 32 + q], gx, gy);
+                    if (dead && fragment_dead(dead, static_cast<uint32_t>(A.prune.prim_base + w0 + warp * 32 + q) + 1u, A.g.W, gx, gy)) continue;
+                    atomicAdd(&hist[bin_of(A.bm, static_cast<uint32_t>(strip_of(A.g, gx, gy)), local_of(A.g, gx, gy))], 1u);
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
         uint32_t *row = A.slab_hist + static_cast<size_t>(slab) * kMaxBins;
         uint32_t *seg = A.seg_total + static_cast<size_t>(slab / A.slabs_per_seg) * kMaxBins;
-        for (int t = threadIdx.x; t < B; t += kHistThreads) {
+        for (int t = tid; t < B; t += kHistThreads) {
             const uint32_t h = hist[t];
             row[t] = h;
             if (h) { atomicAdd(&seg[t], h); hist[t] = 0u; }
