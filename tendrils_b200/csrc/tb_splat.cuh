@@ -917,24 +917,43 @@ __device__ __forceinline__ void fold_apply(FoldWarp &W, float4 *tex, const FoldP
         W.term[lane] = make_float4(p.tx, p.ty, p.tz, p.tw);
         W.om[lane] = p.om;
         __syncwarp();
-        if (active && rank == 0u) {
-            float4 d = tex[p.rel];
-            uint32_t rem = p.peers & ~p.cut;
+        // The chain of a crowded texel is serial: two dependent roundings per fragment and channel.  The first FOUR lanes of the
+        // texel's group run it, one colour channel each (a group of fewer than four fragments: its first lane, all channels),
+        // over the group's fragments in lane order, operands read from shared memory four steps ahead of the chain.
+        const uint32_t members = p.peers & ~p.cut;
+        const bool wide = __popc(p.peers) >= 4;
+        if (active && wide && rank < 4u) {
+            const float *term = reinterpret_cast<const float *>(W.term) + rank;          // channel `rank` of lane j at term[4 j]
+            float *slot = reinterpret_cast<float *>(tex + p.rel) + rank;
+            float d = *slot;
+            uint32_t rem = members;
             while (rem) {
-                // two steps per trip: the operand loads do not depend on d
+                int j[4];
+                bool on[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    on[k] = rem != 0u;
+                    j[k] = on[k] ? __ffs(rem) - 1 : 0;
+                    rem &= rem - 1u;
+                }
+                float v[4], m[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { v[k] = term[4 * j[k]]; m[k] = W.om[j[k]]; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (on[k]) d = __fadd_rn(v[k], __fmul_rn(d, m[k]));
+            }
+            *slot = d;
+        } else if (active && !wide && rank == 0u) {
+            float4 d = tex[p.rel];
+            uint32_t rem = members;
+            while (rem) {
                 const int j0 = __ffs(rem) - 1;
                 rem &= rem - 1u;
-                const int j1 = rem ? __ffs(rem) - 1 : j0;
-                const bool two = rem != 0u;
-                rem &= rem - 1u;
-                const float4 v0 = W.term[j0], v1 = W.term[j1];
-                const float m0 = W.om[j0], m1 = W.om[j1];
+                const float4 v0 = W.term[j0];
+                const float m0 = W.om[j0];
                 d.x = __fadd_rn(v0.x, __fmul_rn(d.x, m0)); d.y = __fadd_rn(v0.y, __fmul_rn(d.y, m0));
                 d.z = __fadd_rn(v0.z, __fmul_rn(d.z, m0)); d.w = __fadd_rn(v0.w, __fmul_rn(d.w, m0));
-                if (two) {
-                    d.x = __fadd_rn(v1.x, __fmul_rn(d.x, m1)); d.y = __fadd_rn(v1.y, __fmul_rn(d.y, m1));
-                    d.z = __fadd_rn(v1.z, __fmul_rn(d.z, m1)); d.w = __fadd_rn(v1.w, __fmul_rn(d.w, m1));
-                }
             }
             tex[p.rel] = d;
         }
