@@ -506,26 +506,25 @@ __device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__r
             for (uint32_t b = 0; b < cnt; ++b) ns[k] += bin_total[first + b];
         }
     }
+    // as many bins (a power of two, at most one per texel) as it takes to bring a strip's bins down to `at` fragments
     auto want = [&](uint32_t frags, unsigned long long at) -> uint32_t {
         uint32_t ls = 0;
-        if (frags > at) ls = 3;
-        if (frags > 4ull * at) ls = 5;
-        if (frags > 16ull * at) ls = 7;
-        return ls > static_cast<uint32_t>(lS) ? static_cast<uint32_t>(lS) : ls;
+        while (ls < static_cast<uint32_t>(lS) && (static_cast<unsigned long long>(frags) >> ls) > at) ++ls;
+        return ls;
     };
     // A small draw (few fragments for this many SMs) splits earlier, so that the fold still has a few thousand bins to hand
     // out; then raise the threshold until the bins fit: the most crowded strips are the ones that stay split.
     unsigned long long at = total / 4096ull;
     at = at < 256ull ? 256ull : (at > split_at ? split_at : at);
     unsigned long long base = 0ull;
-    for (int guard = 0; guard < 64; ++guard) {
+    for (int guard = 0; guard < 200; ++guard) {
         unsigned long long bins = 0ull;
 #pragma unroll
         for (int k = 0; k < kPlanStrips; ++k)
             if (u0 + k < T) bins += 1ull << want(ns[k], at);
         base = block_excl_scan64(bins, s_warp, s_total);
         if (*s_total <= static_cast<unsigned long long>(kMaxBins)) break;
-        at += (at >> 1) + 1ull;
+        at += (at >> 2) + 1ull;
     }
     const unsigned long long cap_ls = at;
     if (threadIdx.x == 0) *n_bins_next = static_cast<uint32_t>(*s_total);
