@@ -212,6 +212,9 @@ int tb_blend_into_flow(tb_ctx *ctx, const float *rgba, int32_t w, int32_t h);
  * log2(bins of the strip) << 24; the strip size in texels.  Used by tools/ to study the load distribution of the fold. */
 int tb_debug_max_bins(void);
 int tb_debug_bins(tb_ctx *ctx, uint32_t *offsets, uint32_t *info, int32_t *n_bins, int32_t *strip_w, int32_t *strip_h);
+/* diagnostic tap: how many bins the last splat folded in segments (spec/PARITY.md B4), in how many segments, and how many
+ * fragments the segments left on record for the join. */
+int tb_debug_segments(tb_ctx *ctx, int32_t *bins, int32_t *segments, int64_t *records);
 
 /* OpticalFlow.update() + screen.render() with the flow FBO bound (src/optical-flow/index.frag:55-81,
  * src/optical-flow/index.js:50-58, call site src/demo.main.js:1131-1156): the gradient optical flow of two RGBA8

@@ -74,6 +74,7 @@ SYMBOLS = {
     "tb_download": (C.c_int, [_ctx, C.c_int, _fp, C.c_int64]),
     "tb_blend_into_flow": (C.c_int, [_ctx, _fp, C.c_int32, C.c_int32]),
     "tb_debug_max_bins": (C.c_int, []),
+    "tb_debug_segments": (C.c_int, [_ctx, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "tb_debug_bins": (C.c_int, [_ctx, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int32)]),
     "tb_flow_line": (C.c_int, [_ctx, C.POINTER(TbFlowLineParams), C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp]),

@@ -79,6 +79,14 @@ struct tb_ctx {
     cudaEvent_t ev_plan = nullptr;
     Frag *bins = nullptr;                  // every fragment of a draw, binned by tile, draw order inside a bin
     uint32_t bin_cap = 0;
+    // long bins folded in segments (tb_splat.cuh, PARITY B4)
+    uint32_t seg_at = 16384, seg_len = 8192;   // TB_SEG_AT (0: off), TB_SEG_LEN
+    bool seg_scaled = true;                // an explicit TB_SEG_AT is taken literally
+    uint32_t seg_out_cap = 4u << 20;       // float4 entries of segment results (64 MB)
+    uint4 *seg_desc = nullptr;
+    uint32_t *seg_of_bin = nullptr, *seg_cnt = nullptr;
+    float4 *seg_out = nullptr;
+    Frag *replay = nullptr;                // as large as `bins`: the records of the segments
     bool bin_fixed = false;                // the bin array is mapped by other ranks: it cannot grow without a reconnect
     // column-sharded run over peer memory (tb_owners.cuh): every rank maps every rank's bins, grid, totals table, flags
     bool owners_connected = false;
@@ -230,6 +238,8 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     TB_REQUIRE(c, (1 << (g.sxl + g.syl)) <= kMaxStripTexels, "flow grid too large for the strip binning (at most 8192 strips of 512 texels)");
     cudaFree(c->flow); cudaFree(c->slab_hist); cudaFree(c->seg_total); cudaFree(c->bin_total); cudaFree(c->bin_off); cudaFree(c->items);
     cudaFree(c->split_map); cudaFree(c->bin_info); cudaFree(c->n_bins); cudaFree(c->last_local); cudaFree(c->last_global); cudaFree(c->prune_flags);
+    cudaFree(c->seg_desc); cudaFree(c->seg_of_bin); cudaFree(c->seg_cnt); cudaFree(c->seg_out);
+    c->seg_desc = nullptr; c->seg_of_bin = nullptr; c->seg_cnt = nullptr; c->seg_out = nullptr;
     c->last_local = nullptr; c->last_global = nullptr; c->prune_flags = nullptr;
     c->flow = nullptr; c->slab_hist = nullptr; c->seg_total = nullptr; c->bin_total = nullptr; c->bin_off = nullptr; c->items = nullptr;
     c->split_map = nullptr; c->bin_info = nullptr; c->n_bins = nullptr;
@@ -242,7 +252,13 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     TB_CUDA(c, cudaMalloc(&c->seg_total, 2 * static_cast<size_t>(kMaxBins) * kHistSegs * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->bin_total, static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->bin_off, static_cast<size_t>(kMaxBins + 1) * sizeof(uint32_t)));
-    TB_CUDA(c, cudaMalloc(&c->items, 8 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+    TB_CUDA(c, cudaMalloc(&c->items, 16 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+    if (c->seg_at) {
+        TB_CUDA(c, cudaMalloc(&c->seg_desc, static_cast<size_t>(kMaxBins) * sizeof(uint4)));
+        TB_CUDA(c, cudaMalloc(&c->seg_of_bin, static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMalloc(&c->seg_cnt, 16 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
+        TB_CUDA(c, cudaMalloc(&c->seg_out, static_cast<size_t>(c->seg_out_cap) * sizeof(float4)));
+    }
     TB_CUDA(c, cudaMalloc(&c->split_map, 2 * static_cast<size_t>(T) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->bin_info, 2 * static_cast<size_t>(kMaxBins) * sizeof(uint32_t)));
     TB_CUDA(c, cudaMalloc(&c->n_bins, 2 * sizeof(uint32_t)));
@@ -260,6 +276,7 @@ int alloc_flow(tb_ctx *c, int w, int h) {
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHistSmemBytes)));
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kScatterSmemBytes)));
     TB_CUDA(c, cudaFuncSetAttribute(k_splat_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)))));
+    TB_CUDA(c, cudaFuncSetAttribute(k_splat_mend, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)))));
     int per_sm = 0;
     TB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_splat_scatter, kEmitThreads, kScatterSmemBytes));
     c->scatter_ctas = std::max(1, per_sm) * c->n_sms;
@@ -287,9 +304,10 @@ int ensure_bin_cap(tb_ctx *c, uint64_t need) {
     uint64_t cap = std::max<uint64_t>(need + need / 4, 1u << 16);
     if (cap >= (1ull << 31)) cap = (1ull << 31) - 1;
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->bins);
-    c->bins = nullptr; c->bin_cap = 0;
+    cudaFree(c->bins); cudaFree(c->replay);
+    c->bins = nullptr; c->replay = nullptr; c->bin_cap = 0;
     TB_CUDA(c, cudaMalloc(&c->bins, cap * sizeof(Frag)));
+    if (c->seg_at) TB_CUDA(c, cudaMalloc(&c->replay, cap * sizeof(Frag)));
     c->bin_cap = static_cast<uint32_t>(cap);
     return TB_OK;
 }
@@ -402,6 +420,36 @@ int launch_scatter(tb_ctx *c, float time, int mp, const uint32_t *bin_off, Frag 
     return check_launch(c, "k_splat_scatter");
 }
 
+SegPlan seg_plan(tb_ctx *c) {
+    SegPlan G{};
+    G.seg_at = c->replay ? c->seg_at : 0u;
+    G.scaled = c->seg_scaled ? 1u : 0u;
+    G.seg_len = std::max<uint32_t>(c->seg_len, 64u);
+    G.out_cap = c->seg_out_cap;
+    G.desc = c->seg_desc;
+    G.of_bin = c->seg_of_bin;
+    return G;
+}
+
+// the fold proper, then the join of the bins that were folded in segments
+int launch_fold_kernels(tb_ctx *c, FoldArgs &FA) {
+    FA.seg_desc = c->seg_desc;
+    FA.seg_of_bin = c->seg_of_bin;
+    FA.seg_out = c->seg_out;
+    FA.seg_cnt = c->seg_cnt;
+    FA.replay = c->replay;
+    FA.n_seg = c->tickets + 5;
+    FA.seg_ticket = c->tickets + 6;
+    const size_t smem = fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl));
+    k_splat_fold<<<c->fold_ctas, kFoldThreads, smem, c->stream>>>(FA);
+    if (int r = check_launch(c, "k_splat_fold")) return r;
+    if (c->seg_at && c->replay) {
+        k_splat_mend<<<c->fold_ctas, kFoldThreads, smem, c->stream>>>(FA);
+        if (int r = check_launch(c, "k_splat_mend")) return r;
+    }
+    return TB_OK;
+}
+
 int launch_collect(tb_ctx *c, float time) {
     const int T = c->geom.T;
     cudaEvent_t *stage = c->ev_stage[c->ev_count[1] % tb_ctx::kTimingSlots];
@@ -424,6 +472,7 @@ int launch_collect(tb_ctx *c, float time) {
     PA.cap = c->bin_cap;
     PA.split_at = c->split_at;
     PA.share_at = c->share_at;
+    PA.seg = seg_plan(c);
     PA.too_many = c->tickets + 4;
     PA.tickets = c->tickets;
     PA.map_next = c->split_map + static_cast<size_t>(mp ^ 1) * T;
@@ -455,8 +504,7 @@ int launch_fold(tb_ctx *c, float time) {
     FA.ticket = c->tickets + 2;
     FA.flow[0] = c->flow;
     FA.n_flow = 1;
-    k_splat_fold<<<c->fold_ctas, kFoldThreads, fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)), c->stream>>>(FA);
-    return check_launch(c, "k_splat_fold");
+    return launch_fold_kernels(c, FA);
 }
 
 int queue_owners(tb_ctx *c, float time);
@@ -641,6 +689,7 @@ int queue_owners(tb_ctx *c, float time) {
     PA.items = c->items;
     PA.split_at = c->split_at;
     PA.share_at = c->share_at;
+    PA.seg = seg_plan(c);
     PA.tickets = c->tickets;
     PA.map_next = c->split_map + static_cast<size_t>(mp ^ 1) * T;
     PA.bin_info_next = c->bin_info + static_cast<size_t>(mp ^ 1) * kMaxBins;
@@ -671,8 +720,7 @@ int queue_owners(tb_ctx *c, float time) {
     for (int r = 0; r < P; ++r)
         if (r != c->ow_rank) FA.flow[nf++] = c->ow_flow[r];
     FA.n_flow = nf;
-    k_splat_fold<<<c->fold_ctas, kFoldThreads, fold_smem_bytes(1 << (c->geom.sxl + c->geom.syl)), c->stream>>>(FA);
-    if (int r = check_launch(c, "k_splat_fold")) return r;
+    if (int r = launch_fold_kernels(c, FA)) return r;
     mark();
     if (int r = barrier(2)) return r;                      // every grid is complete
     mark();
@@ -756,6 +804,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     if (const char *e = std::getenv("TB_SPLIT_AT")) c->split_at = static_cast<uint32_t>(std::max(64, std::atoi(e)));
     if (const char *e = std::getenv("TB_PRUNE")) c->prune_mode = std::atoi(e) != 0 ? 1 : 0;
     if (const char *e = std::getenv("TB_SHARE_AT")) c->share_at = static_cast<uint32_t>(std::max(64, std::atoi(e)));
+    if (const char *e = std::getenv("TB_SEG_AT")) { c->seg_at = static_cast<uint32_t>(std::max(0, std::atoi(e))); c->seg_scaled = false; }
+    if (const char *e = std::getenv("TB_SEG_LEN")) c->seg_len = static_cast<uint32_t>(std::max(64, std::atoi(e)));
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
     TB_TRY(cudaMalloc(&c->buf[0], bytes));
@@ -826,7 +876,8 @@ int tb_destroy(tb_ctx *c) {
     cudaFree(c->image); cudaFree(c->layer); cudaFree(c->pairs); cudaFree(c->d_flag);
     cudaFree(c->slab_hist); cudaFree(c->seg_total); cudaFree(c->bin_total); cudaFree(c->bin_off); cudaFree(c->tickets); cudaFree(c->items);
     cudaFree(c->split_map); cudaFree(c->bin_info); cudaFree(c->n_bins);
-    cudaFree(c->d_plan); cudaFree(c->bins);
+    cudaFree(c->d_plan); cudaFree(c->bins); cudaFree(c->replay);
+    cudaFree(c->seg_desc); cudaFree(c->seg_of_bin); cudaFree(c->seg_cnt); cudaFree(c->seg_out);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_plan) cudaFreeHost(c->h_plan);
     if (c->ev_plan) cudaEventDestroy(c->ev_plan);
@@ -1383,6 +1434,29 @@ int tb_debug_bins(tb_ctx *c, uint32_t *offsets, uint32_t *info, int32_t *n_bins,
     *n_bins = static_cast<int32_t>(nb);
     if (strip_w) *strip_w = 1 << c->geom.sxl;
     if (strip_h) *strip_h = 1 << c->geom.syl;
+    return TB_OK;
+}
+
+int tb_debug_segments(tb_ctx *c, int32_t *bins, int32_t *segments, int64_t *records) {
+    TB_REQUIRE(c, c && bins && segments && records, "null argument");
+    TB_CUDA(c, cudaSetDevice(c->device));
+    if (int r = resolve_pending(c)) return r;
+    *bins = 0; *segments = 0; *records = 0;
+    if (!c->seg_at || !c->replay) return TB_OK;
+    uint32_t nb = 0;
+    TB_CUDA(c, cudaMemcpyAsync(&nb, c->tickets + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (nb == 0 || nb > static_cast<uint32_t>(kMaxBins)) return TB_OK;
+    std::vector<uint4> desc(nb);
+    std::vector<uint32_t> cnt(16 * static_cast<size_t>(kMaxBins));
+    TB_CUDA(c, cudaMemcpyAsync(desc.data(), c->seg_desc, nb * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(cnt.data(), c->seg_cnt, cnt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    *bins = static_cast<int32_t>(nb);
+    for (const uint4 &d : desc) {
+        *segments += 1 << d.y;
+        for (uint32_t part = 1; part < (1u << d.y); ++part) *records += cnt[d.w + part];
+    }
     return TB_OK;
 }
 

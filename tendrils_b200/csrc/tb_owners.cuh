@@ -92,8 +92,9 @@ struct OwnerPlanArgs {
     uint32_t *__restrict__ scat_off;           // [kMaxBins] where MY fragments of bin b start in the array of rank b % n
     uint32_t *__restrict__ own_begin;          // [kMaxBins] for the bins I own: where the bin starts in my array ...
     uint32_t *__restrict__ own_count;          // [kMaxBins] ... and how many fragments it holds
-    uint32_t *__restrict__ items;              // [8 kMaxBins] fold work items of the bins I own, longest first
+    uint32_t *__restrict__ items;              // [16 kMaxBins] fold work items of the bins I own, longest first
     uint32_t split_at, share_at;
+    SegPlan seg;
     uint32_t *tickets;
     uint32_t *map_next, *bin_info_next, *n_bins_next;
     PlanOut *out;
@@ -106,8 +107,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
     __shared__ unsigned long long s_total;
     __shared__ uint32_t s_bucket[33];
     __shared__ uint32_t s_ok;
+    __shared__ uint32_t s_seg[3];
     const int B = static_cast<int>(*A.bm.n_bins);
     const int P = A.n;
+    if (threadIdx.x < 3) s_seg[threadIdx.x] = 0u;
     const int C = kPlanThreads / P;                          // threads per owner class
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int o = tid % P, i = tid / P;                      // this thread: owner class o, i-th thread of the class
@@ -184,8 +187,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
                 A.own_count[b] = ok ? S[k] : 0u;
                 bucket[k] = __clz(S[k] | 1u);
                 if (ok && S[k]) {
-                    lparts[k] = fold_lparts(S[k], (1u << A.lS) >> (A.bin_info[b] >> 24), A.share_at);
-                    rank[k] = atomicAdd(&s_bucket[bucket[k]], 1u << lparts[k]);
+                    const uint32_t R = (1u << A.lS) >> (A.bin_info[b] >> 24);
+                    const uint32_t lseg = plan_segments(static_cast<uint32_t>(b), S[k], R, 1u << A.lS, s_owner_total[A.me], A.seg, s_seg);
+                    lparts[k] = lseg ? (lseg | 0x80u) : fold_lparts(S[k], R, A.share_at);
+                    rank[k] = atomicAdd(&s_bucket[bucket[k]], 1u << (lparts[k] & 0x7fu));
                 }
             }
             run += S[k];
@@ -197,13 +202,15 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
         for (int b = 0; b < 32; ++b) { const uint32_t c = s_bucket[b]; s_bucket[b] = r; r += c; }
         A.out->n_items = r;
         A.tickets[3] = r;
+        A.tickets[5] = s_seg[0];
+        A.tickets[6] = 0u;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kOwnerPlanPer; ++k) {
         const int b = o + P * (i * K + k);
         if (in_class && k < K && b < B && o == A.me && ok && S[k])
-            for (uint32_t part = 0; part < (1u << lparts[k]); ++part)
+            for (uint32_t part = 0; part < (1u << (lparts[k] & 0x7fu)); ++part)
                 A.items[s_bucket[bucket[k]] + rank[k] + part] = static_cast<uint32_t>(b) | (part << 16) | (lparts[k] << 24);
     }
     // the next draw's split map, from the fragments per strip over ALL ranks: identical on every rank

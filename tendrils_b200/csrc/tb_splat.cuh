@@ -444,18 +444,50 @@ constexpr int kPlanThreads = 1024;
 constexpr int kPlanBins = kMaxBins / kPlanThreads;       // bins per thread
 constexpr int kPlanStrips = kMaxStrips / kPlanThreads;   // strips per thread
 
+// Segments (spec/PARITY.md B4).  A bin too long for one warp is folded by 2 .. 16 warps, a range of the bin's fragments
+// each; k_splat_mend joins the ranges.  Per such bin: log2 of its segments, where its segment results and record counts live.
+constexpr uint32_t kSegMaxLog = 4;
+struct SegPlan {
+    uint32_t seg_at;                           // fragments above which a (split) bin is folded in segments; 0: never
+    uint32_t scaled;                           // 1: ... and above 1/1024 of the draw (a draw that large does not wait for one bin)
+    uint32_t seg_len;                          // fragments per segment aimed at
+    uint32_t out_cap;                          // float4 entries of the segment results
+    uint4 *desc;                               // [kMaxBins] bin, log2(segments), first result entry, first count entry
+    uint32_t *of_bin;                          // [kMaxBins] bin -> entry of desc
+};
+// fragments per segment: the bin cut into 2^lp ranges, whole bulk-copy windows each
+__host__ __device__ __forceinline__ uint32_t seg_span(uint32_t n, uint32_t lp) { return ((n + (64u << lp) - 1u) >> (lp + 6u)) << 6u; }
+// Is a bin of n fragments over R of the strip's S texels folded in segments, and in how many (log2)?  `s_seg`: shared counters
+// [0] such bins, [1] result entries, [2] count entries.  Both bracketing chains of a texel live in the warp's texel array: R <= S/2.
+__device__ __forceinline__ uint32_t plan_segments(uint32_t bin, uint32_t n, uint32_t R, uint32_t S, unsigned long long total, const SegPlan &G,
+                                                  uint32_t *s_seg) {
+    if (G.seg_at == 0u || 2u * R > S) return 0u;
+    const unsigned long long at = (G.scaled && total >> 10 > G.seg_at) ? total >> 10 : G.seg_at;
+    if (n <= at) return 0u;
+    const unsigned long long len = total / (2ull * kMaxBins) > G.seg_len ? total / (2ull * kMaxBins) : G.seg_len;
+    uint32_t lp = 1u;
+    while (lp < kSegMaxLog && (n >> lp) > len) ++lp;
+    const uint32_t slot = atomicAdd(&s_seg[1], R << lp);
+    if (slot + (R << lp) > G.out_cap) return 0u;
+    const uint32_t at_desc = atomicAdd(&s_seg[0], 1u), cnt = atomicAdd(&s_seg[2], 1u << lp);
+    G.desc[at_desc] = make_uint4(bin, lp, slot, cnt);
+    G.of_bin[bin] = at_desc;
+    return lp;
+}
+
 struct PlanArgs {
     int T, lS;                                 // strips, log2 of the texels per strip
     BinMap bm;                                 // this draw's map
     const uint32_t *__restrict__ bin_info;     // [n_bins] strip | sub << 16 | log2(bins of the strip) << 24
     const uint32_t *__restrict__ bin_total;    // [n_bins]
     uint32_t *__restrict__ bin_off;            // [n_bins + 1]
-    uint32_t *__restrict__ items;              // [8 kMaxBins] fold work items, longest first: bin | part << 16 | log2(parts) << 24
+    uint32_t *__restrict__ items;              // [16 kMaxBins] fold work items, longest first: bin | part << 16 | log2(parts) << 24 | segments << 31
     uint32_t cap;                              // capacity of the bin array (fragments)
     uint32_t split_at;                         // a strip with more fragments than this gets 8 bins next time, 4x: 32, 16x: 128
     uint32_t share_at;                         // a bin with more fragments than this is folded by 2 warps, 2x: 4, 4x: 8
+    SegPlan seg;                               // bins long enough to be folded in segments (k_splat_mend)
     uint32_t *too_many;                        // set by k_splat_rows; reset here
-    uint32_t *tickets;                         // [0] hist (reset for the next draw), [1] scatter, [2] fold, [3] items
+    uint32_t *tickets;                         // [0] hist (reset for the next draw), [1] scatter, [2] fold, [3] items, [5] mended bins, [6] mend
     uint32_t *map_next;                        // [T]   the next draw's map ...
     uint32_t *bin_info_next;                   // [kMaxBins]
     uint32_t *n_bins_next;                     // ... and its bin count
@@ -552,8 +584,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
     __shared__ unsigned long long s_total;
     __shared__ uint32_t s_bucket[33];
     __shared__ uint32_t s_ok;
+    __shared__ uint32_t s_seg[3];
     const int B = static_cast<int>(*A.bm.n_bins);
     const int t0 = threadIdx.x * kPlanBins;
+    if (threadIdx.x < 3) s_seg[threadIdx.x] = 0u;
     uint32_t n[kPlanBins];
     unsigned long long mine = 0ull;
 #pragma unroll
@@ -586,8 +620,12 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
         // work list, longest bins first (bucketed by log2 of the length): the tail of the fold is short bins
         bucket[k] = __clz(n[k] | 1u);
         lparts[k] = 0u;
-        if (ok && n[k]) lparts[k] = fold_lparts(n[k], (1u << A.lS) >> (A.bin_info[t0 + k] >> 24), share_at);
-        rank[k] = (ok && n[k]) ? atomicAdd(&s_bucket[bucket[k]], 1u << lparts[k]) : 0u;
+        if (ok && n[k]) {
+            const uint32_t R = (1u << A.lS) >> (A.bin_info[t0 + k] >> 24);
+            const uint32_t lseg = plan_segments(static_cast<uint32_t>(t0 + k), n[k], R, 1u << A.lS, total, A.seg, s_seg);
+            lparts[k] = lseg ? (lseg | 0x80u) : fold_lparts(n[k], R, share_at);
+        }
+        rank[k] = (ok && n[k]) ? atomicAdd(&s_bucket[bucket[k]], 1u << (lparts[k] & 0x7fu)) : 0u;
     }
     if (threadIdx.x == 0) A.bin_off[B] = ok ? static_cast<uint32_t>(s_total) : 0u;
     __syncthreads();
@@ -596,12 +634,14 @@ __global__ void __launch_bounds__(kPlanThreads) k_splat_plan(const PlanArgs A) {
         for (int b = 0; b < 32; ++b) { const uint32_t c = s_bucket[b]; s_bucket[b] = r; r += c; }
         A.out->n_items = r;
         A.tickets[3] = r;
+        A.tickets[5] = s_seg[0];
+        A.tickets[6] = 0u;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPlanBins; ++k)
         if (ok && n[k])
-            for (uint32_t part = 0; part < (1u << lparts[k]); ++part)
+            for (uint32_t part = 0; part < (1u << (lparts[k] & 0x7fu)); ++part)
                 A.items[s_bucket[bucket[k]] + rank[k] + part] = static_cast<uint32_t>(t0 + k) | (part << 16) | (lparts[k] << 24);
 
     plan_next_map(A.T, A.lS, A.bm.map, A.bin_total, total, A.split_at, A.map_next, A.bin_info_next, A.n_bins_next, s_warp, &s_total);
@@ -824,6 +864,14 @@ struct FoldArgs {
     uint32_t *ticket;
     float4 *flow[kMaxBandRanks];             // [0] the grid that is read; every entry below n_flow is written
     int n_flow;
+    // bins folded in segments (plan_segments)
+    const uint4 *__restrict__ seg_desc;      // bin, log2(segments), first result entry, first count entry
+    const uint32_t *__restrict__ seg_of_bin;
+    float4 *seg_out;                         // per segment the bin's texels: what the segment leaves behind (or kSegOpen / kSegRedo in .x)
+    uint32_t *seg_cnt;                       // per segment: records in `replay`
+    Frag *replay;                            // laid out like `bins`: a segment's records start where the segment starts
+    const uint32_t *n_seg;                   // device: bins folded in segments
+    uint32_t *seg_ticket;
 };
 
 constexpr int kFoldRing = 64;                            // compaction ring of a warp that shares a long bin
@@ -960,6 +1008,166 @@ __device__ __forceinline__ void fold_apply(FoldWarp &W, float4 *tex, const FoldP
     __syncwarp();
 }
 
+// ---- segments (spec/PARITY.md B4) -----------------------------------------------------------------------------------
+// One step of a texel's chain, x -> fl(c + fl(x * m)), is monotone in x for finite c, m (each rounding is), so a run of steps
+// is.  Segment j >= 1 of a long bin does not know what the earlier segments leave in its texels, so it runs every texel's
+// chain twice, from -FLT_MAX and from +FLT_MAX.  Once the two agree bit for bit (and are finite) the texel has SETTLED: every
+// finite start value lies between them, so the true chain has the same value from there on, whatever came before.  Hot texels
+// settle after a few hundred fragments (the start's weight shrinks by 1 - a per fragment); until they do -- and for texels
+// that never do (few fragments, tiny alphas) -- the segment RECORDS the texel's fragments, in order, and k_splat_mend
+// replays the records onto the true value.  Nothing is approximated: a settled value is the value the sequential blend has.
+constexpr uint32_t kSegOpen = 0x7fc00001u;               // result .x of a texel that did not settle: replay its records
+constexpr uint32_t kSegRedo = 0x7fc00002u;               // settled, but not finite in the end: fold the bin again, serially
+constexpr float kSegLo = -3.402823466e+38f, kSegHi = 3.402823466e+38f;
+
+__device__ __forceinline__ bool finite4(const float4 &v) { return is_finite(v.x) && is_finite(v.y) && is_finite(v.z) && is_finite(v.w); }
+__device__ __forceinline__ bool same_bits4(const float4 &a, const float4 &b) {
+    return __float_as_uint(a.x) == __float_as_uint(b.x) && __float_as_uint(a.y) == __float_as_uint(b.y) &&
+           __float_as_uint(a.z) == __float_as_uint(b.z) && __float_as_uint(a.w) == __float_as_uint(b.w);
+}
+__device__ __forceinline__ bool seg_bit(const uint32_t *mask, uint32_t i) { return ((mask[i >> 5] >> (i & 31u)) & 1u) != 0u; }
+
+__device__ __forceinline__ void seg_begin(float4 *lo_tex, float4 *hi_tex, uint32_t *settled, uint32_t R, int lane) {
+    for (uint32_t l = lane; l < R; l += 32) {
+        lo_tex[l] = make_float4(kSegLo, kSegLo, kSegLo, kSegLo);
+        hi_tex[l] = make_float4(kSegHi, kSegHi, kSegHi, kSegHi);
+    }
+    for (uint32_t l = lane; l < (R + 31u) / 32u; l += 32) settled[l] = 0u;
+    __syncwarp();
+}
+// one batch of a segment: record the fragments of texels that have not settled, blend onto both chains, see who settles
+__device__ __forceinline__ void seg_batch(FoldWarp &W, float4 *lo_tex, float4 *hi_tex, uint32_t *settled, const Frag &f, bool active, uint32_t lo,
+                                          float time, int lane, Frag *rec, uint32_t &n_rec) {
+    const FoldPrep p = fold_prep(f, active, lo, time, lane);
+    const bool open = active && !seg_bit(settled, p.rel);
+    const uint32_t ob = __ballot_sync(0xffffffffu, open);
+    if (open) rec[n_rec + static_cast<uint32_t>(__popc(ob & ((1u << lane) - 1u)))] = f;
+    n_rec += static_cast<uint32_t>(__popc(ob));
+    fold_apply(W, lo_tex, p, active, lane);
+    fold_apply(W, hi_tex, p, active, lane);
+    if (open && (p.peers >> lane) == 1u) {                            // the texel's last fragment in this batch
+        const float4 l = lo_tex[p.rel], h = hi_tex[p.rel];
+        if (same_bits4(l, h) && finite4(l)) atomicOr(&settled[p.rel >> 5], 1u << (p.rel & 31u));
+    }
+    __syncwarp();
+}
+// what the segment leaves behind, per texel: the settled value, or "replay my records", or "cannot tell"
+__device__ __forceinline__ void seg_end(const float4 *lo_tex, const float4 *hi_tex, const uint32_t *settled, uint32_t R, float4 *out, int lane) {
+    for (uint32_t l = lane; l < R; l += 32) {
+        float4 e = lo_tex[l];
+        if (!seg_bit(settled, l)) e.x = __uint_as_float(kSegOpen);
+        else if (!(same_bits4(e, hi_tex[l]) && finite4(e))) e.x = __uint_as_float(kSegRedo);
+        out[l] = e;
+    }
+}
+// k_splat_mend, before segment j's records are replayed onto the true values T: which texels the segment settles (mask).
+// True: the bin has to be folded again serially (a settled value holds for a finite start only).
+__device__ __forceinline__ bool mend_begin(const float4 *T, const float4 *E, uint32_t R, uint32_t *mask, int lane) {
+    bool redo = false;
+    for (uint32_t l0 = 0; l0 < R; l0 += 32) {
+        const uint32_t l = l0 + static_cast<uint32_t>(lane);
+        bool settles = false;
+        if (l < R) {
+            const uint32_t ex = __float_as_uint(E[l].x);
+            if (ex == kSegRedo) redo = true;
+            else if (ex != kSegOpen) { settles = true; if (!finite4(T[l])) redo = true; }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, settles);
+        if (lane == 0) mask[l0 >> 5] = m;
+    }
+    __syncwarp();
+    return __any_sync(0xffffffffu, redo);
+}
+__device__ __forceinline__ void mend_batch(FoldWarp &W, float4 *T, const uint32_t *mask, const Frag &f, bool active, uint32_t lo, float time, int lane) {
+    const bool act = active && !seg_bit(mask, (f.key & kKeyLocalMask) - lo);           // records made before the texel settled: moot
+    fold_apply(W, T, fold_prep(f, act, lo, time, lane), act, lane);
+}
+__device__ __forceinline__ void mend_end(float4 *T, const float4 *E, uint32_t R, const uint32_t *mask, int lane) {
+    for (uint32_t l = lane; l < R; l += 32)
+        if (seg_bit(mask, l)) T[l] = E[l];
+    __syncwarp();
+}
+
+// [fold-host-end]  (tests/test_fold_host.py runs everything from fold_prep to here on an emulated warp)
+
+// the warp's window over fragments [src, src + n): batch(fragment of this lane, active) for every 32 of them, in order
+template <class Batch>
+__device__ __forceinline__ void fold_stream(FoldWarp &W, const Frag *src, uint32_t n, int lane, uint32_t &phase0, uint32_t &phase1, Batch &&batch) {
+    const uint32_t n_stage = (n + kFoldStage - 1) / kFoldStage;
+    auto issue = [&](uint32_t j) {
+        const uint32_t c = (n - j * kFoldStage < static_cast<uint32_t>(kFoldStage)) ? n - j * kFoldStage : static_cast<uint32_t>(kFoldStage);
+        bulk_load(W.stage[j & 1u], src + static_cast<size_t>(j) * kFoldStage, c * static_cast<uint32_t>(sizeof(Frag)), &W.bar[j & 1u]);
+    };
+    if (lane == 0) {
+        if (n_stage > 0) issue(0);
+        if (n_stage > 1) issue(1);
+    }
+    for (uint32_t j = 0; j < n_stage; ++j) {
+        const uint32_t s = j & 1u;
+        const uint32_t c = (n - j * kFoldStage < static_cast<uint32_t>(kFoldStage)) ? n - j * kFoldStage : static_cast<uint32_t>(kFoldStage);
+        if (s == 0u) { mbar_wait(&W.bar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&W.bar[1], phase1); phase1 ^= 1u; }
+        Frag f0{0.f, 0.f, 0.f, 0u}, f1{0.f, 0.f, 0.f, 0u};
+        const bool a0 = static_cast<uint32_t>(lane) < c, a1 = static_cast<uint32_t>(32 + lane) < c;
+        if (a0) f0 = W.stage[s][lane];
+        if (a1) f1 = W.stage[s][32 + lane];
+        batch(f0, a0);
+        if (c > 32u) batch(f1, a1);
+        __syncwarp();
+        if (lane == 0 && j + 2 < n_stage) issue(j + 2);
+    }
+}
+
+__device__ __forceinline__ void fold_load_texels(const FoldArgs &A, float4 *tex, uint32_t lo, uint32_t R, int gx0, int gy0, int lane) {
+    for (uint32_t l = lane; l < R; l += 32) {
+        const uint32_t loc = lo + l;
+        const int gx = gx0 + static_cast<int>(loc & ((1u << A.g.sxl) - 1u)), gy = gy0 + static_cast<int>(loc >> A.g.sxl);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx < A.g.W && gy < A.g.H) v = A.flow[0][static_cast<size_t>(gy) * A.g.W + gx];
+        tex[l] = v;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void fold_store_texels(const FoldArgs &A, const float4 *tex, uint32_t lo, uint32_t R, int gx0, int gy0, int lane) {
+    for (uint32_t l = lane; l < R; l += 32) {
+        const uint32_t loc = lo + l;
+        const int gx = gx0 + static_cast<int>(loc & ((1u << A.g.sxl) - 1u)), gy = gy0 + static_cast<int>(loc >> A.g.sxl);
+        if (gx < A.g.W && gy < A.g.H) {
+            const float4 v = tex[l];
+            const size_t at = static_cast<size_t>(gy) * A.g.W + gx;
+            for (int r = 0; r < A.n_flow; ++r) A.flow[r][at] = v;
+        }
+    }
+    __syncwarp();
+}
+
+// One segment of a long bin (work item with bit 31): fragments [part * span, + span) of the bin, all of its texels.
+__device__ __forceinline__ void fold_segment(const FoldArgs &A, FoldWarp &W, float4 *tex, uint32_t bin_id, uint32_t part, uint32_t lp, uint32_t st,
+                                             uint32_t lo, uint32_t R, int lane, uint32_t &phase0, uint32_t &phase1) {
+    const uint32_t begin = A.bin_off[bin_id], n = A.bin_count ? A.bin_count[bin_id] : A.bin_off[bin_id + 1] - begin;
+    const uint4 d = A.seg_desc[A.seg_of_bin[bin_id]];
+    const uint32_t span = seg_span(n, lp);
+    const uint32_t b0 = part * span < n ? part * span : n, b1 = b0 + span < n ? b0 + span : n;
+    float4 *out = A.seg_out + d.z + static_cast<size_t>(part) * R;
+    if (part == 0u) {                                      // the first segment starts from the grid: its result is the truth so far
+        const int gx0 = (static_cast<int>(st) % A.g.strips_x) << A.g.sxl, gy0 = (static_cast<int>(st) / A.g.strips_x) << A.g.syl;
+        fold_load_texels(A, tex, lo, R, gx0, gy0, lane);
+        fold_stream(W, A.bins + begin, b1, lane, phase0, phase1,
+                    [&](const Frag &f, bool act) { fold_apply(W, tex, fold_prep(f, act, lo, A.time, lane), act, lane); });
+        for (uint32_t l = lane; l < R; l += 32) out[l] = tex[l];
+    } else {
+        float4 *hi_tex = tex + R;
+        uint32_t *settled = reinterpret_cast<uint32_t *>(W.ring);
+        seg_begin(tex, hi_tex, settled, R, lane);
+        uint32_t n_rec = 0;
+        Frag *rec = A.replay + begin + b0;
+        fold_stream(W, A.bins + begin + b0, b1 - b0, lane, phase0, phase1,
+                    [&](const Frag &f, bool act) { seg_batch(W, tex, hi_tex, settled, f, act, lo, A.time, lane, rec, n_rec); });
+        seg_end(tex, hi_tex, settled, R, out, lane);
+        if (lane == 0) A.seg_cnt[d.w + part] = n_rec;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -980,9 +1188,13 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         const uint32_t icode = A.items[item];                        // bin | part << 16 | log2(parts) << 24
-        const uint32_t bin_id = icode & 0xffffu, part = (icode >> 16) & 0xffu, lparts = icode >> 24;
+        const uint32_t bin_id = icode & 0xffffu, part = (icode >> 16) & 0xffu, lparts = (icode >> 24) & 0x7fu;
         const uint32_t code = A.bin_info[bin_id];
         const uint32_t st = code & 0xffffu, sub = (code >> 16) & 0xffu, ls = code >> 24;
+        if (icode >> 31) {
+            fold_segment(A, W, tex, bin_id, part, lparts, st, sub * (S >> ls), S >> ls, lane, phase0, phase1);
+            continue;
+        }
         // the bin's texels are local indices [sub * (S >> ls), + S >> ls); a long bin is shared by 2^lparts warps, each of which
         // streams the whole bin and keeps the fragments of its part of the texels
         const uint32_t R = (S >> ls) >> lparts, lo = sub * (S >> ls) + part * R;
@@ -1070,6 +1282,58 @@ __global__ void __launch_bounds__(kFoldThreads, 4) k_splat_fold(const FoldArgs A
             }
         }
         __syncwarp();
+    }
+}
+
+// Pass 5: join the segments of the long bins.  One warp per bin: the first segment's result is the truth; every later
+// segment either settles a texel (take its value) or left the texel's fragments on record (replay them, in order).
+__global__ void __launch_bounds__(kFoldThreads, 4) k_splat_mend(const FoldArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t S = 1u << (A.g.sxl + A.g.syl);
+    FoldWarp &W = *reinterpret_cast<FoldWarp *>(smem_raw + fold_warp_bytes(static_cast<int>(S)) * warp);
+    float4 *T = reinterpret_cast<float4 *>(&W + 1);
+    uint32_t *mask = reinterpret_cast<uint32_t *>(W.ring);
+    const uint32_t n_seg = *A.n_seg;
+    if (n_seg == 0u) return;
+    if (lane == 0) {
+        mbar_init(&W.bar[0], 1u);
+        mbar_init(&W.bar[1], 1u);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase0 = 0u, phase1 = 0u;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(A.seg_ticket, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_seg) break;
+        const uint4 d = A.seg_desc[item];
+        const uint32_t bin_id = d.x, lp = d.y;
+        const uint32_t code = A.bin_info[bin_id];
+        const uint32_t st = code & 0xffffu, sub = (code >> 16) & 0xffu, ls = code >> 24;
+        const uint32_t R = S >> ls, lo = sub * R;
+        const uint32_t begin = A.bin_off[bin_id], n = A.bin_count ? A.bin_count[bin_id] : A.bin_off[bin_id + 1] - begin;
+        const uint32_t span = seg_span(n, lp);
+        const int gx0 = (static_cast<int>(st) % A.g.strips_x) << A.g.sxl, gy0 = (static_cast<int>(st) / A.g.strips_x) << A.g.syl;
+        for (uint32_t l = lane; l < R; l += 32) T[l] = A.seg_out[d.z + l];
+        __syncwarp();
+        bool redo = false;
+        for (uint32_t part = 1; part < (1u << lp) && !redo; ++part) {
+            const float4 *E = A.seg_out + d.z + static_cast<size_t>(part) * R;
+            redo = mend_begin(T, E, R, mask, lane);
+            if (redo) break;
+            const uint32_t b0 = part * span < n ? part * span : n;
+            fold_stream(W, A.replay + begin + b0, A.seg_cnt[d.w + part], lane, phase0, phase1,
+                        [&](const Frag &f, bool act) { mend_batch(W, T, mask, f, act, lo, A.time, lane); });
+            mend_end(T, E, R, mask, lane);
+        }
+        if (redo) {                                        // a non-finite texel, or a settled chain that overflowed: the plain way
+            fold_load_texels(A, T, lo, R, gx0, gy0, lane);
+            fold_stream(W, A.bins + begin, n, lane, phase0, phase1,
+                        [&](const Frag &f, bool act) { fold_apply(W, T, fold_prep(f, act, lo, A.time, lane), act, lane); });
+        }
+        fold_store_texels(A, T, lo, R, gx0, gy0, lane);
     }
 }
 

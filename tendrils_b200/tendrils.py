@@ -329,6 +329,12 @@ class Particles:
         N.check(self._ctx, self._L.tb_stats(self._ctx, C.byref(a), C.byref(b)))
         return {"kernel_launches": a.value, "last_fragments": b.value}
 
+    def segment_stats(self):
+        """Diagnostics of the last flow splat: bins folded in segments, segments, fragments left on record for the join."""
+        nb, ns, nr = C.c_int32(), C.c_int32(), C.c_int64()
+        N.check(self._ctx, self._L.tb_debug_segments(self._ctx, C.byref(nb), C.byref(ns), C.byref(nr)))
+        return {"bins": nb.value, "segments": ns.value, "records": nr.value}
+
     def timing(self, reset=False):
         """Summed CUDA-event time of the integrate launches, the flow splats and the side-stream noise
         launches since the last reset."""

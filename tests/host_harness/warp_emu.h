@@ -78,6 +78,7 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 
 /* run one warp: body() is called by 32 lane threads with threadIdx.x = first_thread + lane */
 static inline void tb_run_warp(unsigned block, unsigned first_thread, const std::function<void()> &body) {

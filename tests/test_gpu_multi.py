@@ -17,7 +17,9 @@ def _free_port():
 
 def _worker(rank, world, port, shape, G, steps, out_dir, ring, radius, prune):
     sys.path.insert(0, ROOT)
-    if prune is not None:
+    if prune == "seg":
+        os.environ.update({"TB_SEG_AT": "96", "TB_SEG_LEN": "64", "TB_SPLIT_AT": "512"})
+    elif prune is not None:
         os.environ["TB_PRUNE"] = prune
     import torch
     import torch.distributed as dist
@@ -34,7 +36,7 @@ def _worker(rank, world, port, shape, G, steps, out_dir, ring, radius, prune):
         t.step().draw()
     np.save(os.path.join(out_dir, f"flow_{rank}.npy"), t.flow.download())
     np.save(os.path.join(out_dir, f"state_{rank}.npy"), t.particles.buffers[0].download())
-    np.save(os.path.join(out_dir, f"frags_{rank}.npy"), np.array([t.particles.stats()["last_fragments"]]))
+    np.save(os.path.join(out_dir, f"frags_{rank}.npy"), np.array([t.particles.stats()["last_fragments"], t.particles.segment_stats()["bins"]]))
     dist.destroy_process_group()
 
 
@@ -42,10 +44,12 @@ def _worker(rank, world, port, shape, G, steps, out_dir, ring, radius, prune):
 #   square and ragged grids; the TALL textures of the weak-scaling bench (columns sharded, many rows); a small ball so that
 #   strips get crowded and the split map kicks in (the same map must come out on every rank)
 #   prune "1": the opaque pruning across the ranks (TB_PRUNE=1; fewer fragments than the oracle rasterises)
+#   prune "seg": the owners fold their crowded bins in segments (PARITY B4) -- forced onto bins above 96 fragments
 @pytest.mark.parametrize("ring,shape,G,radius,prune", [("owners", (96, 96), 64, 0.3, None), ("owners", (96, 96), 50, 0.3, "1"),
                                                        ("dist", (96, 96), 64, 0.3, None), ("owners", (16, 2048), 128, 0.3, None),
                                                        ("owners", (64, 1024), 96, 0.02, "1"), ("owners", (8, 8192), 64, 0.3, None),
-                                                       ("owners", (64, 512), 64, 0.05, "1")])
+                                                       ("owners", (64, 512), 64, 0.05, "1"), ("owners", (64, 1024), 96, 0.02, "seg"),
+                                                       ("owners", (96, 96), 64, 0.3, "seg")])
 def test_sharded_draw_equals_oracle(oracle, tmp_path, ring, shape, G, radius, prune):
     import torch
     if torch.cuda.device_count() < 2:
@@ -74,3 +78,5 @@ def test_sharded_draw_equals_oracle(oracle, tmp_path, ring, shape, G, radius, pr
     assert np.array_equal(got, cur)
     emitted = sum(int(np.load(tmp_path / f"frags_{r}.npy")[0]) for r in range(world))
     assert 0 < emitted <= n if prune == "1" else emitted == n
+    if prune == "seg" and radius < 0.1:
+        assert sum(int(np.load(tmp_path / f"frags_{r}.npy")[1]) for r in range(world)) > 0, "no bin was folded in segments"

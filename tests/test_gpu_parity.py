@@ -1,8 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit.
 
 Tolerance: NONE -- integrate, spawners and the ordered flow blend all have to match the oracle's 32-bit patterns exactly
-(only the payload of a NaN is left open).  The whole module runs twice: as the library ships on one GPU, and with the
-opaque pruning that sharded runs use (TB_PRUNE=1), which must not change a bit."""
+(only the payload of a NaN is left open).  The whole module runs three times: as the library ships on one GPU, with the
+opaque pruning that sharded runs may use (TB_PRUNE=1), and with the segmented fold forced onto small bins -- none may change a bit."""
 import ctypes as C
 import os
 
@@ -23,19 +23,23 @@ def T():
     return tendrils_b200
 
 
-@pytest.fixture(scope="module", params=["", "1"], ids=["default", "prune"], autouse=True)
+MODES = {"default": {}, "prune": {"TB_PRUNE": "1"}, "segments": {"TB_SEG_AT": "96", "TB_SEG_LEN": "64", "TB_SPLIT_AT": "512"}}
+
+
+@pytest.fixture(scope="module", params=list(MODES), autouse=True)
 def prune_mode(request):
-    """TB_PRUNE is read when a context is created"""
-    old = os.environ.get("TB_PRUNE")
-    if request.param:
-        os.environ["TB_PRUNE"] = request.param
-    else:
-        os.environ.pop("TB_PRUNE", None)
+    """The knobs are read when a context is created.  `segments`: every split bin above 96 fragments is folded in segments of
+    64 (PARITY B4: bracketing chains, records, the join) -- the path sharded runs and crowded draws depend on."""
+    keys = sorted({k for m in MODES.values() for k in m})
+    old = {k: os.environ.get(k) for k in keys}
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ.update(MODES[request.param])
     yield request.param
-    if old is None:
-        os.environ.pop("TB_PRUNE", None)
-    else:
-        os.environ["TB_PRUNE"] = old
+    for k in keys:
+        os.environ.pop(k, None)
+        if old[k] is not None:
+            os.environ[k] = old[k]
 
 
 def frags_ok(t, n):
@@ -102,7 +106,7 @@ def test_ball_then_steps_bit_exact(T, oracle, R, G):
 
 
 @pytest.mark.parametrize("R,G,radius,steps", [(192, 1100, 0.9, 4), (160, 2048, 0.9, 3), (256, 64, 0.03, 12), (192, 2048, 0.01, 6)])
-def test_strip_sizes_and_split_maps_bit_exact(T, oracle, R, G, radius, steps):
+def test_strip_sizes_and_split_maps_bit_exact(T, oracle, prune_mode, R, G, radius, steps):
     """Grids beyond 1024^2 (strips of 256 / 512 texels), and balls so small that strips get crowded: the split map the plan
     derives from one draw (8 / 32 / 128 bins per strip) must not change the next draw's result."""
     from tendrils_b200.spawn import spawnBall
@@ -118,6 +122,9 @@ def test_strip_sizes_and_split_maps_bit_exact(T, oracle, R, G, radius, steps):
         assert frags_ok(t, n), f"fragment count at step {k}"
         assert_bits_equal(t.flow.download(), sim.flow, f"flow after step {k}")
     assert_bits_equal(t.particles.buffers[0].download(), sim.cur, "state")
+    if prune_mode == "segments" and radius < 0.1:
+        seg = t.particles.segment_stats()
+        assert seg["bins"] > 0 and seg["segments"] >= 2 * seg["bins"], seg      # the crowd was folded in segments, and joined
 
 
 @pytest.mark.parametrize("R,G,chunks", [(96, 50, 16), (64, 32, 1), (40, 24, 64)])

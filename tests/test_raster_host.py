@@ -99,7 +99,7 @@ def rh(tmp_path_factory):
     cpp = d / "raster_host.cpp"
     ssrc = open(os.path.join(ROOT, "tendrils_b200", "csrc", "tb_splat.cuh")).read()
     prim = ssrc[ssrc.index("// [prim-begin]"):ssrc.index("// [prim-end]")].replace("__device__", "").replace("__noinline__", "")
-    texel = ssrc[ssrc.index("__device__ __forceinline__ void prim_fragment_texel("):ssrc.index("__global__ void __launch_bounds__(kHistThreads) k_splat_hist")]
+    texel = ssrc[ssrc.index("__device__ __forceinline__ void prim_fragment_texel("):ssrc.index("constexpr int kHistWarps")]
     cpp.write_text(HARNESS % {"math": str(math), "body": body, "prim": prim, "texel": texel.replace("__device__", "")})
     out = d / "libraster_host.so"
     subprocess.run(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
