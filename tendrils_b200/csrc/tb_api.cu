@@ -80,8 +80,8 @@ struct tb_ctx {
     Frag *bins = nullptr;                  // every fragment of a draw, binned by tile, draw order inside a bin
     uint32_t bin_cap = 0;
     // long bins folded in segments (tb_splat.cuh, PARITY B4)
-    uint32_t seg_at = 16384, seg_len = 8192;   // TB_SEG_AT (0: off), TB_SEG_LEN
-    bool seg_scaled = true;                // an explicit TB_SEG_AT is taken literally
+    uint32_t seg_at = 0, seg_len = 8192;   // TB_SEG_AT (0: off, the default -- see DESIGN.md 4), TB_SEG_LEN
+    bool seg_scaled = false;               // TB_SEG_SCALED=1: ... and not below 1/1024 of the draw
     uint32_t seg_out_cap = 4u << 20;       // float4 entries of segment results (64 MB)
     uint4 *seg_desc = nullptr;
     uint32_t *seg_of_bin = nullptr, *seg_cnt = nullptr;
@@ -444,7 +444,7 @@ int launch_fold_kernels(tb_ctx *c, FoldArgs &FA) {
     k_splat_fold<<<c->fold_ctas, kFoldThreads, smem, c->stream>>>(FA);
     if (int r = check_launch(c, "k_splat_fold")) return r;
     if (c->seg_at && c->replay) {
-        k_splat_mend<<<c->fold_ctas, kFoldThreads, smem, c->stream>>>(FA);
+        k_splat_mend<<<std::min(c->fold_ctas, 2 * c->n_sms), kFoldThreads, smem, c->stream>>>(FA);
         if (int r = check_launch(c, "k_splat_mend")) return r;
     }
     return TB_OK;
@@ -804,7 +804,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     if (const char *e = std::getenv("TB_SPLIT_AT")) c->split_at = static_cast<uint32_t>(std::max(64, std::atoi(e)));
     if (const char *e = std::getenv("TB_PRUNE")) c->prune_mode = std::atoi(e) != 0 ? 1 : 0;
     if (const char *e = std::getenv("TB_SHARE_AT")) c->share_at = static_cast<uint32_t>(std::max(64, std::atoi(e)));
-    if (const char *e = std::getenv("TB_SEG_AT")) { c->seg_at = static_cast<uint32_t>(std::max(0, std::atoi(e))); c->seg_scaled = false; }
+    if (const char *e = std::getenv("TB_SEG_AT")) c->seg_at = static_cast<uint32_t>(std::max(0, std::atoi(e)));
+    if (const char *e = std::getenv("TB_SEG_SCALED")) c->seg_scaled = std::atoi(e) != 0;
     if (const char *e = std::getenv("TB_SEG_LEN")) c->seg_len = static_cast<uint32_t>(std::max(64, std::atoi(e)));
     TB_TRY(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device));
     const size_t bytes = static_cast<size_t>(c->n_local) * sizeof(float4);
