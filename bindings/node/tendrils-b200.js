@@ -61,6 +61,18 @@ export const accelerate = (Tendrils, shaderKinds /* Map(shader -> {kind, variant
       return this.drawView();                             // the reference's view half of draw()
     }
 
+    /**
+     * step() for apps that keep the particle state on the CPU (`particles.pixels`, src/particles.js:76-78): one pipelined
+     * upload + logic pass + download (tb_step_streamed).  Asynchronous: `sync()` before the host array is read.
+     */
+    stepStreamed(hostState = this.particles.pixels.data, chunks = 16) {
+      addon.setState(this.b200, this.state, this.viewSize);
+      addon.stepStreamed(this.b200, this.timer.time, this.timer.dt, hostState, hostState, chunks);
+      return this;
+    }
+
+    sync() { addon.sync(this.b200); return this; }
+
     spawn(spawner) {
       if(spawner === undefined) { addon.reset(this.b200); return this; }
       super.spawn(spawner);                               // fills this.particles.pixels on the CPU

@@ -303,6 +303,59 @@ napi_value BlendIntoFlow(napi_env env, napi_callback_info info) {
     return check(env, ctx, tb_blend_into_flow(ctx, static_cast<const float *>(data), w, h));
 }
 
+// stepStreamed(ctx, time, dt, Float32Array hostIn, Float32Array hostOut, chunks): tb_step for callers that keep the state on
+// the host (Particles.pixels): upload, logic pass and download as one pipelined pass.  ASYNCHRONOUS -- call sync(ctx) before
+// reading hostOut; the arrays must stay alive (and should be pinned / not moved by the GC: use external ArrayBuffers).
+napi_value StepStreamed(napi_env env, napi_callback_info info) {
+    size_t argc = 6;
+    napi_value argv[6];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    tb_ctx *ctx = unwrap(env, argv[0]);
+    size_t n_in = 0, n_out = 0;
+    const float *in = static_cast<const float *>(typed(env, argv[3], napi_float32_array, &n_in));
+    float *out = static_cast<float *>(typed(env, argv[4], napi_float32_array, &n_out));
+    if (!in || !out) return nullptr;
+    if (n_in != n_out) {
+        napi_throw_error(env, nullptr, "tendrils-b200: stepStreamed needs two state arrays of the same length");
+        return nullptr;
+    }
+    return check(env, ctx, tb_step_streamed(ctx, static_cast<float>(num(env, argv[1])), static_cast<float>(num(env, argv[2])), in, out,
+                                            static_cast<int32_t>(num(env, argv[5]))));
+}
+
+napi_value Sync(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    tb_ctx *ctx = unwrap(env, argv[0]);
+    return check(env, ctx, tb_sync(ctx));
+}
+
+napi_value SetOverlap(napi_env env, napi_callback_info info) {   // setOverlap(ctx, on)
+    size_t argc = 2;
+    napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    tb_ctx *ctx = unwrap(env, argv[0]);
+    return check(env, ctx, tb_set_overlap(ctx, static_cast<int32_t>(num(env, argv[1]))));
+}
+
+// stats(ctx) -> { kernelLaunches, lastFragments }
+napi_value Stats(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    tb_ctx *ctx = unwrap(env, argv[0]);
+    int64_t launches = 0, frags = 0;
+    if (int st = tb_stats(ctx, &launches, &frags)) return check(env, ctx, st);
+    napi_value out, a, b;
+    NAPI_OK(napi_create_object(env, &out));
+    NAPI_OK(napi_create_double(env, static_cast<double>(launches), &a));
+    NAPI_OK(napi_create_double(env, static_cast<double>(frags), &b));
+    NAPI_OK(napi_set_named_property(env, out, "kernelLaunches", a));
+    NAPI_OK(napi_set_named_property(env, out, "lastFragments", b));
+    return out;
+}
+
 napi_value Init(napi_env env, napi_value exports) {
     const napi_property_descriptor props[] = {
         {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -321,6 +374,10 @@ napi_value Init(napi_env env, napi_value exports) {
         {"opticalFlow", nullptr, OpticalFlow, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"flowLine", nullptr, FlowLine, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"blendIntoFlow", nullptr, BlendIntoFlow, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"stepStreamed", nullptr, StepStreamed, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"sync", nullptr, Sync, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"setOverlap", nullptr, SetOverlap, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"stats", nullptr, Stats, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
     return exports;

@@ -34,6 +34,9 @@ napi_status napi_has_named_property(napi_env env, napi_value object, const char 
 napi_status napi_get_named_property(napi_env env, napi_value object, const char *utf8name, napi_value *result);
 napi_status napi_get_cb_info(napi_env env, napi_callback_info cbinfo, size_t *argc, napi_value *argv, napi_value *this_arg, void **data);
 napi_status napi_create_external(napi_env env, void *data, napi_finalize finalize_cb, void *finalize_hint, napi_value *result);
+napi_status napi_create_object(napi_env env, napi_value *result);
+napi_status napi_create_double(napi_env env, double value, napi_value *result);
+napi_status napi_set_named_property(napi_env env, napi_value object, const char *utf8name, napi_value value);
 napi_status napi_get_element(napi_env env, napi_value object, uint32_t index, napi_value *result);
 napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type *type, size_t *length, void **data,
                                      napi_value *arraybuffer, size_t *byte_offset);

@@ -190,7 +190,8 @@ def test_napi_shim_matches_the_c_header():
                         os.path.join(ROOT, "bindings", "node", "tendrils_b200_napi.cc")], capture_output=True, text=True)
     assert r.returncode == 0 and not r.stderr.strip(), r.stderr
     shim = open(os.path.join(ROOT, "bindings", "node", "tendrils_b200_napi.cc")).read()
-    for sym in ("tb_create", "tb_step", "tb_splat_flow", "tb_spawn_pixels", "tb_optical_flow", "tb_flow_line", "tb_blend_into_flow"):
+    for sym in ("tb_create", "tb_step", "tb_splat_flow", "tb_spawn_pixels", "tb_optical_flow", "tb_flow_line", "tb_blend_into_flow",
+                "tb_step_streamed", "tb_sync", "tb_set_overlap", "tb_stats"):
         assert sym + "(" in shim, sym
 
 
