@@ -690,6 +690,12 @@ struct ScatterArgs {
 constexpr size_t kScatterSmemBytes = static_cast<size_t>(kMaxBins) * 4                                   // cursors
                                      + static_cast<size_t>(kEmitWarps) * (12 * 32 + kEmitSlots) * 4;   // per warp: primitive records (SoA), slot table
 
+// The claim loop of k_splat_scatter relies on a converged warp issuing its (predicated, unrolled) shared-memory atomics in
+// program order.  tests/test_pipeline_host.py runs the lanes as free OS threads and defines this as a warp barrier.
+#ifndef TB_LOCKSTEP_FENCE
+#define TB_LOCKSTEP_FENCE()
+#endif
+
 // [bar-begin]  (the CPU tests swap the helpers between these markers for host equivalents)
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -814,6 +820,7 @@ __global__ void __launch_bounds__(kEmitThreads, 3) k_splat_scatter(const Scatter
                     if (static_cast<uint32_t>(r * 32) >= cnt) continue;                       // warp-uniform
                     if (fbin[r] != 0xffffffffu && lane == __ffs(fpeers[r]) - 1)
                         fdst[r] = atomicAdd(&cur[fbin[r] & 0xffffu], static_cast<uint32_t>(__popc(fpeers[r])));
+                    TB_LOCKSTEP_FENCE();
                 }
                 if (last_pass) release();
                 // ---- store

@@ -49,11 +49,58 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
     return r;
 }
 template <class T> static inline T __shfl_up_sync(unsigned m, T v, int delta) { return __shfl_sync(m, v, tb_lane >= delta ? tb_lane - delta : tb_lane); }
+static inline unsigned tb_gather(uint64_t v, uint64_t *all) {       /* every lane's value, to every lane */
+    tb_warp->slot[tb_lane] = v;
+    tb_warp->bar.arrive_and_wait();
+    for (int i = 0; i < 32; ++i) all[i] = tb_warp->slot[i];
+    tb_warp->bar.arrive_and_wait();
+    return 0;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    uint64_t all[32]; tb_gather(pred ? 1u : 0u, all);
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= static_cast<unsigned>(all[i]) << i;
+    return m;
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+static inline unsigned __match_any_sync(unsigned, uint32_t v) {
+    uint64_t all[32]; tb_gather(v, all);
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (all[i] == v ? 1u : 0u) << i;
+    return m;
+}
+static inline unsigned __reduce_max_sync(unsigned, uint32_t v) {
+    uint64_t all[32]; tb_gather(v, all);
+    uint64_t m = 0;
+    for (int i = 0; i < 32; ++i) m = all[i] > m ? all[i] : m;
+    return static_cast<unsigned>(m);
+}
+template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcs(const T *p) { return *p; }
+static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline uint32_t atomicMax(uint32_t *p, uint32_t v) {
+    uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+
+/* a kernel without barriers: its threads one after the other, no OS threads (grid gx x gy blocks of n_threads) */
+static inline void tb_run_serial(unsigned gx, unsigned gy, unsigned n_threads, const std::function<void()> &body) {
+    tb_host_blockDim = {n_threads, 1, 1};
+    tb_host_gridDim = {gx, gy, 1};
+    for (unsigned by = 0; by < gy; ++by)
+        for (unsigned bx = 0; bx < gx; ++bx)
+            for (unsigned t = 0; t < n_threads; ++t) {
+                tb_host_blockIdx = {bx, by, 0};
+                tb_host_threadIdx = {t, 0, 0};
+                body();
+            }
+}
 
 /* run one block of n_threads (a multiple of 32): body() is called by every thread with threadIdx.x set */
 static inline void tb_run_block(unsigned n_threads, const std::function<void()> &body) {
@@ -72,6 +119,8 @@ static inline void tb_run_block(unsigned n_threads, const std::function<void()> 
             tb_host_blockIdx = {0, 0, 0};
             tb_host_threadIdx = {t, 0, 0};
             body();
+            tb_warp->bar.arrive_and_drop();              /* a thread that returns early must not stall the others */
+            block_bar.arrive_and_drop();
         });
     for (auto &t : threads) t.join();
     tb_block_bar = nullptr;

@@ -1,0 +1,358 @@
+"""The whole flow splat -- k_splat_hist, k_splat_rows, k_splat_plan / k_owners_plan, k_splat_scatter, k_splat_fold, k_splat_mend
+of tendrils_b200/csrc/tb_splat.cuh and tb_owners.cuh, source text unchanged -- on a CPU emulation of thread blocks
+(tests/host_harness/block_emu.h: one OS thread per CUDA thread; __syncthreads, shuffles, votes and the named barriers of the
+scatter kernel's token ring as real barriers; the bulk copies of the fold as plain copies) against the oracle's splat, bit for
+bit, over several consecutive draws so that the split map evolves -- on one "GPU" and column-sharded over several, every
+rank's kernels run one after the other with the peer arrays being plain memory.  This is the block-level plumbing (tickets,
+cursors, token ring, windows, work lists, segments) that the arithmetic tests cannot see, checked without a GPU.
+Nothing here is used by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_fp = C.POINTER(C.c_float)
+
+HARNESS = r'''
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <cuda_runtime.h>
+#undef __shared__
+#undef __global__
+#undef __launch_bounds__
+#include "cuda_intrinsics_shim.h"
+#include "block_emu.h"
+#include "%(math)s"
+#define TB_LOCKSTEP_FENCE() __syncwarp()      /* the lanes of the emulation are free-running threads */
+namespace tb {
+using std::min; using std::max;
+static constexpr float kInert = -1000000.0f;
+constexpr int kMaxBandRanks = 16;
+struct PairEntry { int32_t k, row_a, row_b, pad; };
+%(raster)s
+}
+// host equivalents of the two inline-PTX islands of tb_splat.cuh
+namespace tb {
+struct NamedBar { std::mutex m; std::condition_variable cv; int arrived = 0; unsigned gen = 0; };
+static NamedBar g_named[16];
+inline void named_bar_arrive(int id, int count) {
+    NamedBar &b = g_named[id];
+    std::unique_lock<std::mutex> l(b.m);
+    if (++b.arrived == count) { b.arrived = 0; ++b.gen; b.cv.notify_all(); }
+}
+inline void named_bar_sync(int id, int count) {
+    NamedBar &b = g_named[id];
+    std::unique_lock<std::mutex> l(b.m);
+    const unsigned g = b.gen;
+    if (++b.arrived == count) { b.arrived = 0; ++b.gen; b.cv.notify_all(); }
+    else b.cv.wait(l, [&] { return b.gen != g; });
+}
+inline void mbar_init(unsigned long long *bar, uint32_t) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
+inline void mbar_fence_init() {}
+inline void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    std::memcpy(dst, src, bytes);
+    __atomic_fetch_add(bar, 1ull, __ATOMIC_SEQ_CST);                   // this window's phase is complete
+}
+inline void mbar_wait(unsigned long long *bar, uint32_t parity) {      // at most one phase ahead: its parity tells
+    while ((__atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1ull) == parity) std::this_thread::yield();
+}
+}
+%(splat)s
+%(owners)s
+using namespace tb;
+namespace {
+%(pairs)s
+%(geom)s
+}
+
+// One context (one rank's column block) and the launch sequence of tb_api.cu, restated for the emulation.
+struct Rank {
+    int cols = 0, PH = 0, n_pairs = 0;
+    long long n_prims = 0;
+    int slab_prims = 0, n_slabs = 0, slabs_per_seg = 1;
+    std::vector<PairEntry> pairs;
+    std::vector<uint32_t> slab_hist, seg_total, bin_total, bin_off, items, tickets, seg_of_bin, seg_cnt, scratch;
+    std::vector<uint4> seg_desc;
+    std::vector<float4> seg_out;
+    std::vector<Frag> bins, replay;
+    PlanOut plan{};
+    int seg_parity = 0;
+};
+struct Sim {
+    StripGeom g{};
+    int P = 1, map_parity = 0;
+    uint32_t split_at = 8192, share_at = 12288, seg_at = 0, seg_len = 8192, out_cap = 1u << 18;
+    std::vector<uint32_t> split_map, bin_info, n_bins, totals;
+    std::vector<Rank> ranks;
+    int fold_warps = 2;
+};
+
+extern "C" void *ps_create(int W, int H, int PW, int PH, int P, uint32_t cap, uint32_t split_at, uint32_t share_at, uint32_t seg_at,
+                           uint32_t seg_len, int n_sms, int fold_warps) {
+    Sim *s = new Sim;
+    s->g = choose_geom(W, H);
+    s->P = P; s->split_at = split_at; s->share_at = share_at; s->seg_at = seg_at; s->seg_len = seg_len; s->fold_warps = fold_warps;
+    const int T = s->g.T;
+    s->split_map.assign(2 * (size_t)T, 0u); s->bin_info.assign(2 * (size_t)kMaxBins, 0u); s->n_bins.assign(2, 0u);
+    s->totals.assign((size_t)P * kMaxBins, 0u);
+    tb_run_serial((T + 255) / 256, 1, 256, [&] { k_splat_map_identity(T, s->split_map.data(), s->bin_info.data(), s->n_bins.data()); });
+    s->ranks.resize(P);
+    for (int r = 0; r < P; ++r) {
+        Rank &R = s->ranks[r];
+        R.cols = PW / P; R.PH = PH;
+        R.pairs = build_pairs(PH);
+        R.n_pairs = (int)R.pairs.size();
+        R.n_prims = (long long)R.cols * R.n_pairs;
+        const long long want = (R.n_prims + 6LL * n_sms - 1) / (6LL * n_sms);
+        R.slab_prims = (int)std::max<long long>(4 * kEmitThreads, (want + kEmitThreads - 1) / kEmitThreads * kEmitThreads);
+        R.n_slabs = (int)((R.n_prims + R.slab_prims - 1) / R.slab_prims);
+        R.slabs_per_seg = std::max(1, (R.n_slabs + kHistSegs - 1) / kHistSegs);
+        R.slab_hist.assign((size_t)kMaxBins * std::max(R.n_slabs, 1), 0u);
+        R.seg_total.assign(2 * (size_t)kMaxBins * kHistSegs, 0u);
+        R.bin_total.assign(kMaxBins, 0u); R.bin_off.assign(kMaxBins + 1, 0u); R.items.assign(16 * (size_t)kMaxBins, 0u);
+        R.tickets.assign(8, 0u); R.seg_of_bin.assign(kMaxBins, 0u); R.seg_cnt.assign(16 * (size_t)kMaxBins, 0u);
+        R.seg_desc.assign(kMaxBins, make_uint4(0, 0, 0, 0)); R.seg_out.assign(s->out_cap, make_float4(0, 0, 0, 0));
+        R.scratch.assign(4 * (size_t)kMaxBins, 0u);
+        R.bins.assign(cap, Frag{0.f, 0.f, 0.f, 0u}); R.replay.assign(cap, Frag{0.f, 0.f, 0.f, 0u});
+    }
+    return s;
+}
+extern "C" void ps_destroy(void *p) { delete static_cast<Sim *>(p); }
+
+// One draw.  cur / prev: the whole particle texture, x-major (PW columns of PH); flows: P grids (all are written alike).
+// Returns the fragments of the draw, or -1 if they did not fit the bin arrays.  stats: [0] bins after the draw's plan,
+// [1] bins folded in segments, [2] work items.
+extern "C" long long ps_draw(void *p, const float *cur, const float *prev, float *const *flows, float vsx, float vsy, float speedLimit,
+                             float time, long long *stats) {
+    Sim &s = *static_cast<Sim *>(p);
+    const int T = s.g.T, P = s.P, mp = s.map_parity;
+    s.map_parity ^= 1;
+    BinMap bm{s.split_map.data() + (size_t)mp * T, s.n_bins.data() + mp, s.g.sxl + s.g.syl};
+    const uint32_t *bin_info = s.bin_info.data() + (size_t)mp * kMaxBins;
+    const Prune none{nullptr, nullptr, 0};
+    auto source = [&](int r) {
+        const Rank &R = s.ranks[r];
+        const size_t first = (size_t)r * R.cols * R.PH * 4;
+        return PrimSource{reinterpret_cast<const float4 *>(cur + first), reinterpret_cast<const float4 *>(prev + first), R.pairs.data(), R.n_pairs,
+                          R.PH, R.n_prims};
+    };
+    auto seg_plan = [&](Rank &R) { return SegPlan{s.seg_at, 0u, std::max(s.seg_len, 64u), s.out_cap, R.seg_desc.data(), R.seg_of_bin.data()}; };
+    // count
+    for (int r = 0; r < P; ++r) {
+        Rank &R = s.ranks[r];
+        uint32_t *seg_now = R.seg_total.data() + (size_t)R.seg_parity * kHistSegs * kMaxBins;
+        uint32_t *seg_next = R.seg_total.data() + (size_t)(R.seg_parity ^ 1) * kHistSegs * kMaxBins;
+        R.seg_parity ^= 1;
+        HistArgs HA{};
+        HA.src = source(r); HA.g = s.g; HA.bm = bm; HA.prune = none; HA.vsx = vsx; HA.vsy = vsy;
+        HA.slab_prims = R.slab_prims; HA.n_slabs = R.n_slabs; HA.slabs_per_seg = R.slabs_per_seg;
+        HA.slab_hist = R.slab_hist.data(); HA.seg_total = seg_now; HA.ticket = R.tickets.data() + 0;
+        tb_run_block(kHistThreads, [&] { k_splat_hist(HA); });
+        tb_run_serial(kMaxBins / 256, kHistSegs, 256, [&] {
+            k_splat_rows(R.slab_hist.data(), seg_now, seg_next, s.n_bins.data() + mp, R.n_slabs, R.slabs_per_seg, R.bin_total.data(), R.tickets.data() + 4);
+        });
+        if (P > 1) std::copy(R.bin_total.begin(), R.bin_total.end(), s.totals.begin() + (size_t)r * kMaxBins);      // k_owners_share
+    }
+    // plan (the next map is written P times, identically)
+    long long total = 0;
+    bool overflow = false;
+    for (int r = 0; r < P; ++r) {
+        Rank &R = s.ranks[r];
+        if (P == 1) {
+            PlanArgs PA{};
+            PA.T = T; PA.lS = bm.lS; PA.bm = bm; PA.bin_info = bin_info; PA.bin_total = R.bin_total.data(); PA.bin_off = R.bin_off.data();
+            PA.items = R.items.data(); PA.cap = (uint32_t)R.bins.size(); PA.split_at = s.split_at; PA.share_at = s.share_at; PA.seg = seg_plan(R);
+            PA.too_many = R.tickets.data() + 4; PA.tickets = R.tickets.data();
+            PA.map_next = s.split_map.data() + (size_t)(mp ^ 1) * T; PA.bin_info_next = s.bin_info.data() + (size_t)(mp ^ 1) * kMaxBins;
+            PA.n_bins_next = s.n_bins.data() + (mp ^ 1); PA.out = &R.plan;
+            tb_run_block(kPlanThreads, [&] { k_splat_plan(PA); });
+        } else {
+            OwnerPlanArgs PA{};
+            PA.T = T; PA.lS = bm.lS; PA.bm = bm; PA.bin_info = bin_info; PA.totals = s.totals.data(); PA.n = P; PA.me = r;
+            for (int q = 0; q < P; ++q) PA.caps[q] = (uint32_t)s.ranks[q].bins.size();
+            PA.bin_sum = R.scratch.data(); PA.scat_off = R.scratch.data() + kMaxBins; PA.own_begin = R.scratch.data() + 2 * kMaxBins;
+            PA.own_count = R.scratch.data() + 3 * kMaxBins;
+            PA.items = R.items.data(); PA.split_at = s.split_at; PA.share_at = s.share_at; PA.seg = seg_plan(R); PA.tickets = R.tickets.data();
+            PA.map_next = s.split_map.data() + (size_t)(mp ^ 1) * T; PA.bin_info_next = s.bin_info.data() + (size_t)(mp ^ 1) * kMaxBins;
+            PA.n_bins_next = s.n_bins.data() + (mp ^ 1); PA.out = &R.plan;
+            tb_run_block(kPlanThreads, [&] { k_owners_plan(PA); });
+        }
+        total += (long long)R.plan.total;
+        overflow = overflow || R.plan.overflow;
+    }
+    // scatter: every rank's fragments straight into the owners' arrays
+    for (int r = 0; r < P; ++r) {
+        Rank &R = s.ranks[r];
+        ScatterArgs SA{};
+        SA.src = source(r); SA.g = s.g; SA.bm = bm; SA.prune = none; SA.vsx = vsx; SA.vsy = vsy; SA.speedLimit = speedLimit; SA.time = time;
+        SA.slab_prims = R.slab_prims; SA.n_slabs = R.n_slabs; SA.slab_hist = R.slab_hist.data();
+        SA.bin_off = P == 1 ? R.bin_off.data() : R.scratch.data() + kMaxBins;
+        SA.plan = &R.plan; SA.ticket = R.tickets.data() + 1;
+        for (int q = 0; q < P; ++q) SA.bins[q] = s.ranks[q].bins.data();
+        SA.n_ranks = P;
+        tb_run_block(kEmitThreads, [&] { k_splat_scatter(SA); });
+    }
+    // fold (+ the join of segmented bins): every owner writes its finished texels into every grid
+    stats[0] = s.n_bins[mp]; stats[1] = 0; stats[2] = 0;
+    for (int r = 0; r < P; ++r) {
+        Rank &R = s.ranks[r];
+        FoldArgs FA{};
+        FA.g = s.g; FA.time = time; FA.bins = R.bins.data();
+        FA.bin_off = P == 1 ? R.bin_off.data() : R.scratch.data() + 2 * kMaxBins;
+        FA.bin_count = P == 1 ? nullptr : R.scratch.data() + 3 * kMaxBins;
+        FA.bin_info = bin_info; FA.items = R.items.data(); FA.n_items = R.tickets.data() + 3; FA.ticket = R.tickets.data() + 2;
+        FA.flow[0] = reinterpret_cast<float4 *>(flows[r]);
+        int nf = 1;
+        for (int q = 0; q < P; ++q) if (q != r) FA.flow[nf++] = reinterpret_cast<float4 *>(flows[q]);
+        FA.n_flow = nf;
+        FA.seg_desc = R.seg_desc.data(); FA.seg_of_bin = R.seg_of_bin.data(); FA.seg_out = R.seg_out.data(); FA.seg_cnt = R.seg_cnt.data();
+        FA.replay = R.replay.data(); FA.n_seg = R.tickets.data() + 5; FA.seg_ticket = R.tickets.data() + 6;
+        tb_run_block(32 * s.fold_warps, [&] { k_splat_fold(FA); });
+        if (s.seg_at) tb_run_block(32 * s.fold_warps, [&] { k_splat_mend(FA); });
+        stats[1] += R.tickets[5]; stats[2] += R.tickets[3];
+    }
+    return overflow ? -1 : total;
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def ps(tmp_path_factory):
+    return build_harness(tmp_path_factory.mktemp("ps"))
+
+
+def build_harness(d):
+    csrc = os.path.join(ROOT, "tendrils_b200", "csrc")
+    strip = lambda s: s.replace("__host__", "").replace("__device__", "").replace("__noinline__", "")
+    math = d / "tb_math_host.cuh"
+    math.write_text(strip(open(os.path.join(csrc, "tb_math.cuh")).read()))
+    ksrc = open(os.path.join(csrc, "tb_kernels.cuh")).read()
+    raster = ksrc[ksrc.index("// [raster-begin]"):ksrc.index("// [raster-end]")]
+    ssrc = open(os.path.join(csrc, "tb_splat.cuh")).read()
+    splat = ssrc[ssrc.index("namespace tb {"):]
+    for a, b in (("// [bar-begin]", "// [bar-end]"), ("// [bulk-begin]", "// [bulk-end]")):        # the inline-PTX islands: host equivalents above
+        splat = splat[:splat.index(a)] + splat[splat.index(b):]
+    assert "asm" not in splat
+    shared = "extern __shared__ __align__(16) unsigned char smem_raw[];"
+    assert splat.count(shared) == 4
+    splat = splat.replace(shared, "static __attribute__((aligned(16))) unsigned char smem_raw[1 << 18];")
+    osrc = open(os.path.join(csrc, "tb_owners.cuh")).read()
+    owners = "namespace tb {\n" + osrc[osrc.index("constexpr int kOwnerPlanPer"):]
+    asrc = open(os.path.join(csrc, "tb_api.cu")).read()
+    pairs = asrc[asrc.index("int host_texel(float u, int size) {"):asrc.index("// column sampled by vertex column i")]
+    geom = asrc[asrc.index("StripGeom choose_geom(int W, int H) {"):asrc.index("int tiles_release(tb_ctx *c);")]
+    cpp = d / "pipeline_host.cpp"
+    cpp.write_text(HARNESS % {"math": str(math), "raster": strip(raster), "splat": strip(splat), "owners": strip(owners), "pairs": pairs, "geom": geom})
+    out = d / "libpipeline_host.so"
+    subprocess.run(["g++", "-O2", "-std=c++20", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
+                    "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-Wno-unused-variable", "-I/usr/local/cuda/include",
+                    "-I", os.path.join(ROOT, "tests", "host_harness"), "-o", str(out), str(cpp)], check=True)
+    L = C.CDLL(str(out))
+    L.ps_create.restype = C.c_void_p
+    L.ps_create.argtypes = [C.c_int] * 5 + [C.c_uint32] * 5 + [C.c_int, C.c_int]
+    L.ps_destroy.argtypes = [C.c_void_p]
+    L.ps_draw.restype = C.c_longlong
+    L.ps_draw.argtypes = [C.c_void_p, _fp, _fp, C.POINTER(_fp), C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_longlong)]
+    return L
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def synthetic_states(PW, PH, G, seed, crowd=0.6, reach=3.0, hot=3):
+    """(cur, prev) particle textures made to load the splat: lines up to `reach` texels long, a share `crowd` of them through a few
+    hot spots (the same ones in every draw, so that the split map finds them), alphas from 0 to beyond 1, some inert particles."""
+    W, H = (G, G) if isinstance(G, int) else G
+    spots = np.random.default_rng(1000 + seed // 100).uniform(-0.7, 0.7, (hot, 2))
+    rng = np.random.default_rng(seed)
+    n = PW * PH
+    pos = rng.uniform(-1.05, 1.05, (n, 2))
+    in_crowd = rng.random(n) < crowd
+    pos[in_crowd] = spots[rng.integers(0, hot, in_crowd.sum())] + rng.normal(0, 1.5 / W, (in_crowd.sum(), 2))
+    step = rng.normal(0, reach / W, (n, 2)) * (rng.random((n, 1)) < 0.9)
+    vel = rng.normal(0, 0.006, (n, 2)) * rng.choice([0.05, 0.5, 1.0, 3.0], (n, 1))
+    cur = np.concatenate([pos, vel], 1).astype(np.float32)
+    prev = np.concatenate([pos - step, vel * rng.uniform(0.5, 1.5, (n, 1))], 1).astype(np.float32)
+    inert = rng.random(n) < 0.02
+    cur[inert, :2] = -1000000.0
+    return cur.reshape(PW, PH, 4), prev.reshape(PW, PH, 4)
+
+
+def run_case(ps, O, PW, PH, G, P, radius, steps, split_at=8192, share_at=12288, seg_at=0, seg_len=8192, n_sms=2, fold_warps=2, cap=1 << 21,
+             synthetic=None):
+    """`steps` draws through the oracle and through the emulated pipeline on its own grid(s).  The states are the oracle's own
+    (ball spawn, integrate) or, with `synthetic=seed`, made up to load the splat."""
+    W, H = (G, G) if isinstance(G, int) else G
+    DT = 1000 / 60
+    prm = O.make_params()
+    cur, prev = O.spawn_ball(PW, PH, radius, 0.005), O.spawn_init(PW, PH)
+    targets, flow = np.zeros((PW, PH, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    grids = [np.zeros((H, W, 4), np.float32) for _ in range(P)]
+    gp = (_fp * P)(*[g.ctypes.data_as(_fp) for g in grids])
+    sim = ps.ps_create(W, H, PW, PH, P, cap, split_at, share_at, seg_at, seg_len, n_sms, fold_warps)
+    stats = (C.c_longlong * 3)()
+    seen = dict(bins=0, segs=0, items=0, frags=0)
+    t = DT
+    try:
+        for k in range(steps):
+            t += DT
+            if synthetic is None:
+                new = O.integrate(prm, cur, targets, flow, np.float32(t), np.float32(DT))
+                prev, cur = cur, new
+            else:
+                cur, prev = synthetic_states(PW, PH, G, 100 * synthetic + k)
+            n = O.splat(prm, cur, prev, flow, np.float32(t))
+            c32, p32 = np.ascontiguousarray(cur, np.float32), np.ascontiguousarray(prev, np.float32)
+            got = ps.ps_draw(sim, c32.ctypes.data_as(_fp), p32.ctypes.data_as(_fp), gp, prm.viewSize[0], prm.viewSize[1], prm.speedLimit,
+                             np.float32(t), stats)
+            assert got == n, f"fragments of draw {k}"
+            for r, g in enumerate(grids):
+                assert np.array_equal(bits(g), bits(flow)), f"grid of rank {r} after draw {k}"
+            seen["bins"] = max(seen["bins"], stats[0]); seen["segs"] += stats[1]; seen["items"] = max(seen["items"], stats[2])
+            seen["frags"] = max(seen["frags"], n)
+    finally:
+        ps.ps_destroy(sim)
+    return seen
+
+
+@pytest.mark.parametrize("PW,PH,G,radius,steps", [(32, 32, 40, 0.3, 4), (24, 20, (50, 33), 0.4, 3)])
+def test_single_context_pipeline_equals_oracle(ps, oracle, PW, PH, G, radius, steps):
+    """the oracle's own states: ball spawn, then integrate + splat"""
+    seen = run_case(ps, oracle, PW, PH, G, 1, radius, steps, split_at=256)
+    assert seen["items"] > 0
+
+
+@pytest.mark.parametrize("PW,PH,G,seed", [(64, 96, 64, 1), (40, 200, (100, 37), 2), (128, 64, 256, 3)])
+def test_loaded_pipeline_equals_oracle(ps, oracle, PW, PH, G, seed):
+    """thousands of fragments per draw, crowds on a few texels, several slabs per pass, ragged grids"""
+    seen = run_case(ps, oracle, PW, PH, G, 1, 0, 4, split_at=256, share_at=512, synthetic=seed)
+    assert seen["frags"] > 3000 and seen["bins"] > 8
+
+
+def test_crowded_draw_splits_shares_and_segments(ps, oracle):
+    """Crowds on a small grid: the map splits the strips, long bins are shared by several warps (no segments) or folded in
+    segments and joined (PARITY B4) -- the result may not change."""
+    a = run_case(ps, oracle, 64, 96, 32, 1, 0, 4, split_at=256, share_at=96, synthetic=4)
+    assert a["bins"] > 8 and a["segs"] == 0
+    b = run_case(ps, oracle, 64, 96, 32, 1, 0, 4, split_at=256, share_at=96, seg_at=96, seg_len=64, synthetic=4)
+    assert b["segs"] > 0
+
+
+@pytest.mark.parametrize("P,PW,PH,G,seg_at,seed", [(2, 64, 64, 40, 0, 5), (4, 32, 160, 48, 0, 6), (3, 48, 80, 32, 96, 7), (8, 64, 50, (64, 24), 0, 8)])
+def test_sharded_pipeline_equals_oracle(ps, oracle, P, PW, PH, G, seg_at, seed):
+    """Column shards, bins owned round-robin (tb_owners.cuh): the totals table, the identical plan, fragments scattered straight
+    into the owners' arrays, every grid written by every owner."""
+    seen = run_case(ps, oracle, PW, PH, G, P, 0, 4, split_at=256, share_at=96, seg_at=seg_at, seg_len=64, synthetic=seed)
+    assert seen["items"] > 0 and seen["frags"] > 1500 and (seg_at == 0 or seen["segs"] > 0)
