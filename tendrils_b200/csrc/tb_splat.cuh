@@ -690,8 +690,10 @@ struct ScatterArgs {
 constexpr size_t kScatterSmemBytes = static_cast<size_t>(kMaxBins) * 4                                   // cursors
                                      + static_cast<size_t>(kEmitWarps) * (12 * 32 + kEmitSlots) * 4;   // per warp: primitive records (SoA), slot table
 
-// The claim loop of k_splat_scatter relies on a converged warp issuing its (predicated, unrolled) shared-memory atomics in
-// program order.  tests/test_pipeline_host.py runs the lanes as free OS threads and defines this as a warp barrier.
+// The claim loop of k_splat_scatter relies on a converged warp issuing its (unrolled) shared-memory atomics in program order.
+// In the SASS every round's ATOMS sits between BSSY.RECONVERGENT / BSYNC.RECONVERGENT, i.e. the warp reconverges before the
+// next round's atomic (cuobjdump -sass; tests/test_host.py keeps an eye on it).  tests/test_pipeline_host.py runs the lanes as
+// free OS threads and defines this as a warp barrier.
 #ifndef TB_LOCKSTEP_FENCE
 #define TB_LOCKSTEP_FENCE()
 #endif

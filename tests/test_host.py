@@ -224,3 +224,22 @@ def test_buffer_download_into_caller_memory(monkeypatch):
     for bad in (np.zeros((2, 6, 4), np.float64), np.zeros((6, 2, 4), np.float32), np.zeros((2, 6, 8), np.float32)[..., ::2]):
         with pytest.raises(N.TendrilsError):
             buf.download(out=bad)
+
+
+def test_scatter_claims_reconverge_between_rounds():
+    """k_splat_scatter claims bin slots with one shared-memory atomic per round and relies on round r's atomics being issued
+    before round r + 1's (draw order).  In the shipped SASS that holds because the warp reconverges after every round's atomic:
+    between two consecutive ATOMS there must be a BSYNC.RECONVERGENT (or a WARPSYNC)."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "tendrils_b200", "lib", "libtendrils_b200.so")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.exists(lib) and os.path.exists(tool)):
+        pytest.skip("needs the built library and cuobjdump")
+    sass = subprocess.run([tool, "-sass", "-fun", "_ZN2tb15k_splat_scatterENS_11ScatterArgsE", lib], capture_output=True, text=True).stdout
+    lines = [l for l in sass.splitlines() if "/*" in l and ";" in l]
+    atoms = [i for i, l in enumerate(lines) if "ATOMS" in l]
+    assert len(atoms) >= 5, "the claim loop's atomics are gone?"
+    for a, b in zip(atoms, atoms[1:]):
+        between = lines[a + 1:b]
+        assert any("BSYNC.RECONVERGENT" in l or "WARPSYNC" in l for l in between), "two claim atomics without a reconvergence point in between"
