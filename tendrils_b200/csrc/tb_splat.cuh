@@ -538,10 +538,12 @@ __device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__r
             for (uint32_t b = 0; b < cnt; ++b) ns[k] += bin_total[first + b];
         }
     }
-    // as many bins (a power of two, at most one per texel) as it takes to bring a strip's bins down to `at` fragments
+    // as many bins (a power of two, at most one per texel and at most 256: `sub` has 8 bits in bin_info) as it takes to bring a
+    // strip's bins down to `at` fragments
+    const uint32_t max_ls = lS < 8 ? static_cast<uint32_t>(lS) : 8u;
     auto want = [&](uint32_t frags, unsigned long long at) -> uint32_t {
         uint32_t ls = 0;
-        while (ls < static_cast<uint32_t>(lS) && (static_cast<unsigned long long>(frags) >> ls) > at) ++ls;
+        while (ls < max_ls && (static_cast<unsigned long long>(frags) >> ls) > at) ++ls;
         return ls;
     };
     // A small draw (few fragments for this many SMs) splits earlier, so that the fold still has a few thousand bins to hand

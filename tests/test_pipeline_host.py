@@ -9,6 +9,7 @@ Nothing here is used by the product."""
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -380,6 +381,15 @@ def test_loaded_pipeline_equals_oracle(ps, oracle, PW, PH, G, seed):
     """thousands of fragments per draw, crowds on a few texels, several slabs per pass, ragged grids"""
     seen = run_case(ps, oracle, PW, PH, G, 1, 0, 4, split_at=256, share_at=512, synthetic=seed)
     assert seen["frags"] > 3000 and seen["bins"] > 8
+
+
+def test_crowd_on_a_grid_with_512_texel_strips(ps, oracle, monkeypatch):
+    """Grids beyond 1024^2 have strips of 512 texels; a crowd that would want one bin per texel (512 > the 8 bits `sub` has in
+    bin_info) must stop at 256 bins per strip.  Found by the random stress of this emulation; cannot happen up to 1024^2."""
+    import functools
+    monkeypatch.setattr(sys.modules[__name__], "synthetic_states", functools.partial(synthetic_states, crowd=0.95, reach=30.0, hot=1))
+    seen = run_case(ps, oracle, 32, 1024, (2048, 1040), 1, 0, 3, split_at=256, share_at=96, synthetic=90012)
+    assert seen["bins"] >= 4160 + 255
 
 
 def test_crowded_draw_splits_shares_and_segments(ps, oracle):

@@ -114,7 +114,7 @@ def ptr(a):
 
 def random_map(rng, T, lS, split_frac):
     """a split map as a previous draw could have left it: some strips split 2^ls ways"""
-    ls = np.where(rng.random(T) < split_frac, rng.integers(1, lS + 1, T), 0)
+    ls = np.where(rng.random(T) < split_frac, rng.integers(1, min(lS, 8) + 1, T), 0)
     while (1 << ls).sum() > MAX_BINS:
         ls[np.argmax(ls)] = 0
     first = np.concatenate([[0], np.cumsum(1 << ls)[:-1]])
@@ -128,7 +128,7 @@ def random_map(rng, T, lS, split_frac):
 
 def want(frags, at, lS):
     ls = 0
-    while ls < lS and (int(frags) >> ls) > at:
+    while ls < min(lS, 8) and (int(frags) >> ls) > at:          # at most 256 bins per strip: `sub` has 8 bits in bin_info
         ls += 1
     return ls
 
@@ -184,6 +184,7 @@ def check_items(items, n_items, counts, R_of, owned, expect_lp):
     (4096, 7, 0.1, 5000, 100000, 0, 5),              # does not fit: overflow, nothing may be scattered
     (8192, 7, 0.05, 20000, 1 << 30, 16384, 6),       # long split bins are folded in segments
     (300, 8, 0.2, 0, 1 << 30, 0, 7),                 # an empty draw
+    (64, 9, 0.0, 300000, 1 << 30, 0, 8),             # strips of 512 texels with crowds that want 512 bins each: capped at 256
 ])
 def test_single_gpu_plan(ph, T, lS, split_frac, scale, cap, seg_at, seed):
     rng = np.random.default_rng(seed)
