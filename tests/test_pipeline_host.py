@@ -415,3 +415,30 @@ def test_opaque_pruning_does_not_change_the_result(ps, oracle, P, PW, PH, G, see
     neither counted nor scattered nor folded -- fewer fragments, the same grid (PARITY B3)."""
     seen = run_case(ps, oracle, PW, PH, G, P, 0, 4, split_at=256, share_at=96, synthetic=seed, prune=True)
     assert seen["pruned"] > 0 and seen["frags"] > 1500
+
+
+@pytest.mark.parametrize("P,PW,PH,G,share,seed", [(1, 12, 100, 40, 0.3, 31), (4, 24, 100, 64, 0.2, 32), (5, 30, 257, 64, 0.5, 33), (7, 35, 33, 16, 4.0, 34)])
+def test_overflowing_draw_touches_nothing(ps, oracle, P, PW, PH, G, share, seed):
+    """The plan's capacity verdict (on a sharded run: the same on every rank): when the fragments do not fit the bin array(s),
+    scatter and fold do nothing -- the host grows the array and queues the draw again -- and when they fit, the draw is exact."""
+    prm = oracle.make_params()
+    cur, prev = synthetic_states(PW, PH, G, seed)
+    want = np.full((G, G, 4), 0.25, np.float32)
+    n = oracle.splat(prm, cur, prev, want.copy(), np.float32(50.0))
+    cap = int(max(n * share / P, 1))
+    grids = [np.full((G, G, 4), 0.25, np.float32) for _ in range(P)]
+    gp = (_fp * P)(*[g.ctypes.data_as(_fp) for g in grids])
+    sim = ps.ps_create(G, G, PW, PH, P, cap, 256, 96, 0, 64, 2, 2)
+    stats = (C.c_longlong * 3)()
+    try:
+        got = ps.ps_draw(sim, cur.ctypes.data_as(_fp), prev.ctypes.data_as(_fp), gp, prm.viewSize[0], prm.viewSize[1], prm.speedLimit,
+                         np.float32(50.0), stats)
+    finally:
+        ps.ps_destroy(sim)
+    if share < 1.0:
+        assert got == -1
+    else:
+        assert got == n
+        oracle.splat(prm, cur, prev, want, np.float32(50.0))
+    for g in grids:
+        assert np.array_equal(bits(g), bits(want))
