@@ -1,0 +1,59 @@
+"""Random stress of the CPU emulation of the flow splat (tests/test_pipeline_host.py) against the oracle: hostile states (NaN,
+Inf, astronomic and denormal coordinates, -0 velocities), ragged, tiny and 2048-wide grids, 1-16 ranks, forced splits, sharing,
+segments and pruning, several consecutive draws per case.  CPU only; prints every failing configuration.
+    python tools/stress_pipeline.py [seed=0] [seconds=300]
+Round 2: some 300 cases; one defect found (512-way split of a 512-texel strip), fixed."""
+import os
+import pathlib
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import test_pipeline_host as TP  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+t_end = time.time() + (float(sys.argv[2]) if len(sys.argv) > 2 else 300.0)
+ps = TP.build_harness(pathlib.Path(tempfile.mkdtemp()))
+rng = np.random.default_rng(seed)
+plain = TP.synthetic_states
+
+
+def hostile(PW, PH, G, s, **kw):
+    cur, prev = plain(PW, PH, G, s, crowd=float(rng.choice([0.0, 0.5, 0.95])), reach=float(rng.choice([0.5, 3.0, 30.0])), hot=int(rng.integers(1, 5)))
+    r = np.random.default_rng(s + 7)
+    n = PW * PH
+    c, p = cur.reshape(n, 4), prev.reshape(n, 4)
+    k = r.integers(0, n, max(n // 200, 1))
+    q = len(k) // 4
+    c[k[:q], 0] = np.float32(np.nan)
+    p[k[q:2 * q], 1] = np.float32(np.inf)
+    c[k[2 * q:3 * q], :2] = r.choice([1e9, -3e38, 1e-30, 12345.678], (len(k[2 * q:3 * q]), 2)).astype(np.float32)
+    c[k[3 * q:], 2] = np.float32(-0.0)
+    return cur, prev
+
+
+TP.synthetic_states = hostile
+n_ok = n_bad = 0
+while time.time() < t_end:
+    P = int(rng.choice([1, 1, 2, 3, 4, 5, 7, 8, 16]))
+    PW = P * int(rng.integers(1, 6)) * int(rng.choice([1, 4]))
+    PH = int(rng.choice([1, 2, 7, 33, 100, 257, 1024]))
+    G = (int(rng.choice([1, 5, 16, 33, 64, 130, 700])), int(rng.choice([1, 8, 9, 40, 64, 300])))
+    if rng.random() < 0.08:
+        G = (2048, 1040)                                                  # strips of 512 texels
+    kw = dict(split_at=int(rng.choice([256, 8192])), share_at=int(rng.choice([64, 96, 12288])), seg_at=int(rng.choice([0, 0, 64, 200])),
+              seg_len=int(rng.choice([64, 128, 8192])), n_sms=int(rng.choice([1, 2, 7])), fold_warps=int(rng.choice([1, 2, 8])),
+              prune=bool(rng.random() < 0.3), synthetic=int(rng.integers(0, 1 << 20)))
+    try:
+        TP.run_case(ps, O, PW, PH, G, P, 0, int(rng.integers(1, 5)), **kw)
+        n_ok += 1
+    except AssertionError as e:
+        n_bad += 1
+        print("FAIL", P, PW, PH, G, kw, str(e)[:200], flush=True)
+print(f"cases ok: {n_ok}, failed: {n_bad}")
