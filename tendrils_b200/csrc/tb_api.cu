@@ -72,7 +72,7 @@ struct tb_ctx {
     uint32_t *n_bins = nullptr;            // [2] device scalars
     int map_parity = 0;
     int fold_parity = 0;                   // the map the last collect used
-    uint32_t split_at = 8192;              // fragments per strip above which the next draw gives the strip 8 (32, 128) bins
+    uint32_t split_at = 8192;              // the most fragments a bin should hold: the next draw splits a strip 2, 4, ... 256 ways to get there
     uint32_t share_at = 12288;             // fragments per bin above which 2 (4, 8) warps share the bin's fold
     PlanOut *d_plan = nullptr;
     PlanOut *h_plan = nullptr;             // pinned; valid once ev_plan has completed

@@ -5,7 +5,7 @@
 // (src/index.js:267-268,278-303, src/particles.js:147-158,182-186).  The blend is not
 // commutative, so per texel the fragments must be applied in draw order.  This file does that
 // without a global sort.  The grid is cut into STRIPS (16 x 8 texels at 1024^2); a strip is one BIN
-// of the fragment array, or -- where the previous draw found it crowded -- 8, 32 or 128 bins, one
+// of the fragment array, or -- where the previous draw found it crowded -- 2, 4, ... 256 bins, one
 // per range of its texels (the split map; any map gives the same result, it only balances the work):
 //
 //   k_splat_hist     per slab of consecutive primitives: fragments per bin                    (count)
@@ -483,7 +483,7 @@ struct PlanArgs {
     uint32_t *__restrict__ bin_off;            // [n_bins + 1]
     uint32_t *__restrict__ items;              // [16 kMaxBins] fold work items, longest first: bin | part << 16 | log2(parts) << 24 | segments << 31
     uint32_t cap;                              // capacity of the bin array (fragments)
-    uint32_t split_at;                         // a strip with more fragments than this gets 8 bins next time, 4x: 32, 16x: 128
+    uint32_t split_at;                         // the most fragments a bin should hold (upper end of the target of plan_next_map)
     uint32_t share_at;                         // a bin with more fragments than this is folded by 2 warps, 2x: 4, 4x: 8
     SegPlan seg;                               // bins long enough to be folded in segments (k_splat_mend)
     uint32_t *too_many;                        // set by k_splat_rows; reset here
@@ -523,8 +523,9 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
     return r;
 }
 
-// The next draw's split map from this draw's fragments per bin: a strip with more than split_at fragments gets 8 bins,
-// 4x that: 32, 16x: 128 (as far as kMaxBins allows).  Called by every thread of the (single) plan CTA.
+// The next draw's split map from this draw's fragments per bin: every strip gets as many bins (a power of two) as it takes to
+// bring its bins under a target -- 1/4096 of the draw, between 256 and split_at fragments -- and the target is raised until the
+// map fits kMaxBins.  Called by every thread of the (single) plan CTA.
 __device__ __forceinline__ void plan_next_map(int T, int lS, const uint32_t *__restrict__ map, const uint32_t *__restrict__ bin_total,
                                               unsigned long long total, uint32_t split_at, uint32_t *map_next, uint32_t *bin_info_next, uint32_t *n_bins_next,
                                               unsigned long long *s_warp, unsigned long long *s_total) {

@@ -108,7 +108,7 @@ def test_ball_then_steps_bit_exact(T, oracle, R, G):
 @pytest.mark.parametrize("R,G,radius,steps", [(192, 1100, 0.9, 4), (160, 2048, 0.9, 3), (256, 64, 0.03, 12), (192, 2048, 0.01, 6)])
 def test_strip_sizes_and_split_maps_bit_exact(T, oracle, prune_mode, R, G, radius, steps):
     """Grids beyond 1024^2 (strips of 256 / 512 texels), and balls so small that strips get crowded: the split map the plan
-    derives from one draw (8 / 32 / 128 bins per strip) must not change the next draw's result."""
+    derives from one draw (2, 4, ... 256 bins per strip) must not change the next draw's result."""
     from tendrils_b200.spawn import spawnBall
     t = make(T, R, G)
     sim = OracleSim(oracle, R, G, G, oracle_params(oracle, t))
