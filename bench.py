@@ -406,6 +406,7 @@ def run_ours(args, wl, rank, world, local_rank):
                                       "integrate_finish_main_stream_us": fin_us, "integrate_noise_side_stream_us": noise_us,
                                       "splat_us": spl_us},
                      "note": "k_integrate is FP32-issue bound (2 simplex noises per particle), not HBM bound; see DESIGN.md section 3",
+                     "issue_active": traffic.get("issue_active"),
                      "splat_pipeline": {"kernels": "k_splat_hist + k_splat_rows + k_splat_plan + k_splat_scatter + k_splat_fold",
                                         "algorithmic_bytes": ab["splat"], "avg_us": spl_iso_us, "achieved": splat_gbs, "frac": splat_gbs / peak,
                                         "traffic": traffic.get("splat_pipeline"),
