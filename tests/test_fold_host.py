@@ -107,7 +107,10 @@ extern "C" void fh_fold_segments(const float *frags, int n, int lo, int R, float
 @pytest.fixture(scope="module", params=["6", "1", "31"], ids=["rounds6", "rounds1", "rounds31"])
 def fh(request, tmp_path_factory):
     """Built with the product's threshold between the two paths, with everything chained and with (almost) nothing chained."""
-    d = tmp_path_factory.mktemp("fh")
+    return build_harness(tmp_path_factory.mktemp("fh"), request.param)
+
+
+def build_harness(d, rounds):
     csrc = os.path.join(ROOT, "tendrils_b200", "csrc")
     math = d / "tb_math_host.cuh"
     math.write_text(open(os.path.join(csrc, "tb_math.cuh")).read().replace("__device__", ""))
@@ -115,7 +118,7 @@ def fh(request, tmp_path_factory):
     fold = src[src.index("// The order-independent half of one batch"):src.index("// [fold-host-end]")]
     assert "kFoldRounds" in fold and "asm" not in fold
     cpp = d / "fold_host.cpp"
-    cpp.write_text(HARNESS % {"math": str(math), "fold": fold.replace("__device__", ""), "rounds": request.param})
+    cpp.write_text(HARNESS % {"math": str(math), "fold": fold.replace("__device__", ""), "rounds": rounds})
     out = d / "libfold_host.so"
     subprocess.run(["g++", "-O2", "-std=c++20", "-march=x86-64-v3", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
                     "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes", "-I/usr/local/cuda/include",
