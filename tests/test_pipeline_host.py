@@ -331,12 +331,12 @@ def synthetic_states(PW, PH, G, seed, crowd=0.6, reach=3.0, hot=3):
 
 
 def run_case(ps, O, PW, PH, G, P, radius, steps, split_at=8192, share_at=12288, seg_at=0, seg_len=8192, n_sms=2, fold_warps=2, cap=1 << 21,
-             synthetic=None, prune=False):
+             synthetic=None, prune=False, params=None, t0=None):
     """`steps` draws through the oracle and through the emulated pipeline on its own grid(s).  The states are the oracle's own
     (ball spawn, integrate) or, with `synthetic=seed`, made up to load the splat."""
     W, H = (G, G) if isinstance(G, int) else G
     DT = 1000 / 60
-    prm = O.make_params()
+    prm = O.make_params(**(params or {}))
     cur, prev = O.spawn_ball(PW, PH, radius, 0.005), O.spawn_init(PW, PH)
     targets, flow = np.zeros((PW, PH, 4), np.float32), np.zeros((H, W, 4), np.float32)
     grids = [np.zeros((H, W, 4), np.float32) for _ in range(P)]
@@ -345,7 +345,7 @@ def run_case(ps, O, PW, PH, G, P, radius, steps, split_at=8192, share_at=12288, 
     ps.ps_set_prune(sim, int(prune))
     stats = (C.c_longlong * 3)()
     seen = dict(bins=0, segs=0, items=0, frags=0, pruned=0)
-    t = DT
+    t = DT if t0 is None else t0
     try:
         for k in range(steps):
             t += DT

@@ -49,7 +49,10 @@ while time.time() < t_end:
         G = (2048, 1040)                                                  # strips of 512 texels
     kw = dict(split_at=int(rng.choice([256, 8192])), share_at=int(rng.choice([64, 96, 12288])), seg_at=int(rng.choice([0, 0, 64, 200])),
               seg_len=int(rng.choice([64, 128, 8192])), n_sms=int(rng.choice([1, 2, 7])), fold_warps=int(rng.choice([1, 2, 8])),
-              prune=bool(rng.random() < 0.3), synthetic=int(rng.integers(0, 1 << 20)))
+              prune=bool(rng.random() < 0.3), synthetic=int(rng.integers(0, 1 << 20)),
+              params=dict(viewSize=(float(rng.choice([1.0, 0.66, 1.0, 0.3])), float(rng.choice([1.0, 1.0, 0.75]))),
+                          speedLimit=float(rng.choice([0.01, 0.01, 0.002, 0.5]))),
+              t0=float(rng.choice([1000 / 60, 0.0, -50.0, 1e7])))
     try:
         TP.run_case(ps, O, PW, PH, G, P, 0, int(rng.integers(1, 5)), **kw)
         n_ok += 1
