@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
     __shared__ uint32_t s_bucket[33];
-    __shared__ uint32_t s_ok;
     __shared__ uint32_t s_seg[3];
     const int B = static_cast<int>(*A.bm.n_bins);
     const int P = A.n;
@@ -167,7 +166,6 @@ __global__ void __launch_bounds__(kPlanThreads) k_owners_plan(const OwnerPlanArg
     block_excl_scan64(emitted, s_warp, &s_total);
     const unsigned long long total_emitted = s_total;          // this rank's fragments
     if (tid == 0) {
-        s_ok = ok ? 1u : 0u;
         A.out->total = total_emitted;
         A.out->needed = s_owner_total[A.me];
         A.out->overflow = ok ? 0u : 1u;
